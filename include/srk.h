@@ -1,0 +1,172 @@
+/* srk.h -- C ABI of the B200-native super-resolution conv hot path (libsrk.so).
+ *
+ * Drop-in boundary for the convolutional hot path of imironhead/ml_super_resolution.  The
+ * reference has no native ABI: its seam is the TensorFlow-1.8 op layer that the model builders
+ * call (tf.layers.conv2d, tf.image.resize_bicubic, tf.losses.mean_squared_error,
+ * tf.train.AdamOptimizer, ...).  Each entry point below replaces one of those op call sites; the
+ * comment on each cites the reference file:line (relative to the reference root) it stands in for.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes.  All tensor pointers are DEVICE pointers unless the
+ *     name ends in `_host`.  The caller owns every buffer; the library owns only its handle.
+ *   - Every call is asynchronous on the supplied cudaStream_t (passed as void*), performs no
+ *     host<->device synchronisation and no allocation, and is CUDA-graph capturable.
+ *   - Return value: 0 = OK, negative = error; text via srk_last_error() (thread-local).
+ *   - There is no CPU fallback: every compute entry point fails if no sm_100 device is present.
+ *
+ * Activation layout ("FPA" = flat padded activation), the HBM format between conv layers:
+ *   bf16 [rows][C] (C = 64 or 32), one row per pixel.  n_img images of H x W are stored with
+ *   pitch Wp = W+1 and image stride S = (H+1)*Wp; pixel (n,y,x) lives at row n*S + (y+1)*Wp + x.
+ *   Row y = -1 of every image and column x = W of every row are ZERO, so the 3x3 tap (dy,dx) of
+ *   pixel row p is simply row p + dy*Wp + dx: a convolution is 9 shifted GEMMs over one flat
+ *   matrix.  srk_fpa_rows() gives the allocation size in rows (multiple of 128).
+ */
+#ifndef SRK_H_
+#define SRK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct srk_ctx* srk_handle_t;
+typedef void* srk_stream_t; /* cudaStream_t */
+
+enum { SRK_ACT_NONE = 0, SRK_ACT_RELU = 1, SRK_ACT_TANH = 2 };
+enum { SRK_PAD_SAME = 0, SRK_PAD_VALID = 1 };
+enum { SRK_PACK_FWD = 0, SRK_PACK_DGRAD = 1 };
+
+/* One entry per FPA image when a large frame is processed as column/row panels (tiled inference,
+ * SURVEY 8e): the panel's top-left corner in the frame and the rectangle (panel-local, half-open)
+ * of output pixels this panel owns. */
+typedef struct {
+  int32_t frame, y0, x0;
+  int32_t own_y0, own_y1, own_x0, own_x1;
+  int32_t reserved;
+} srk_panel;
+
+/* ---- handle / errors ------------------------------------------------------------------------- */
+int srk_version(void);
+const char* srk_last_error(void);
+int srk_create(int device, srk_handle_t* out);
+int srk_destroy(srk_handle_t h);
+int srk_num_sms(srk_handle_t h);
+
+/* rows (multiple of 128) an FPA buffer for n_img images of H x W must hold */
+int64_t srk_fpa_rows(int n_img, int H, int W);
+
+/* ---- weight layout prep ----------------------------------------------------------------------
+ * TF HWIO fp32 kernel [k,k,cin,cout] (tf.layers.conv2d `kernel:0`, vdsr/vdsr/model_vdsr.py:62-70)
+ * -> bf16 [k*k][np][cinp] K-major GEMM-B blocks (np, cinp = cout, cin rounded up; zero padded).
+ * mode SRK_PACK_DGRAD packs the transposed, 180-degree rotated kernel used by the data-gradient
+ * convolution (dX = dY * rot180(W)^T), i.e. block[tap'][ci][co] = w[k-1-u][k-1-v][ci][co]. */
+int srk_pack_conv_weights(srk_handle_t h, const float* w_hwio, int k, int cin, int cout, int mode,
+                          int np, int cinp, void* packed_bf16, srk_stream_t stream);
+
+/* ---- conv layers ------------------------------------------------------------------------------
+ * First layer of every model: small-Cin conv from an fp32 NHWC frame straight into an FPA.
+ *   replaces tf.layers.conv2d(sd_images, 64, 3, 'same', relu)  vdsr/vdsr/model_vdsr.py:62 (i=0)
+ *            tf.layers.conv2d(lr_source, 64, 5, 'same', tanh)  espcn/espcn/model_espcn.py:30-38
+ *            convolution2d(lo_images, 64, 9, 'VALID', relu)    srcnn/srcnn.py:100-108
+ *            tf.layers.conv2d(sd_images, 64, 3, 'same', relu)  enet/enet/model_enet.py:63-70
+ * x: fp32 [n_frames, FH, FW, cin] ; w_hwio fp32 [k,k,cin,64] ; bias fp32 [64].
+ * y: FPA bf16 64ch of (n_img, H, W).  Without panels n_img == n_frames and (H,W) is the output
+ * size (FH-k+1 for VALID).  With panels each FPA image n reads the frame window at panels[n].
+ * relu_mask_src (optional FPA, same geometry): multiplies the result by (mask_src > 0); this is
+ * how the last layer's data gradient is produced (conv of dY[...,cout<=4] with the packed
+ * rot180 kernel, masked by ReLU' of the saved activation). */
+int srk_conv_first(srk_handle_t h, const float* x, int n_frames, int FH, int FW, int cin,
+                   const float* w_hwio, const float* bias, int k, int pad_mode, int act,
+                   const srk_panel* panels, int n_img, int H, int W, void* y_fpa,
+                   const void* relu_mask_src, srk_stream_t stream);
+
+/* Tensor-core conv between FPA buffers (tcgen05 implicit GEMM, 9 shifted GEMMs, fp32 TMEM accum):
+ *   y = act(conv_kxk(x) + bias) [* act'(mask_src)] [then relu(y + addend)]
+ *   replaces tf.layers.conv2d(t, 64, 3, 'same', relu)   vdsr/vdsr/model_vdsr.py:62-70 (i>=1)
+ *            tf.layers.conv2d(t, 32, 3, 'same', tanh)   espcn/espcn/model_espcn.py:40-48
+ *            residual_block convs (3x3 relu, 1x1)       enet/enet/model_enet.py:13-31
+ *   and, with SRK_PACK_DGRAD weights + mask_src, the data gradient of the same layers.
+ * x: FPA bf16 [rows, cin_p] (cin_p 64 or 32); y: FPA bf16 [rows, cout_p] (64 or 32).
+ * k is 3 or 1.  mask_kind: SRK_ACT_RELU -> (mask_src>0), SRK_ACT_TANH -> (1-mask_src^2).
+ * addend (optional FPA, cout_p channels): y = relu(addend + y) when relu_after_add, else sum. */
+int srk_conv_tc(srk_handle_t h, const void* x_fpa, int cin_p, const void* w_packed, const float* bias,
+                int k, int cout_p, int act, int n_img, int H, int W, void* y_fpa,
+                const void* mask_src, int mask_kind, const void* addend_fpa, int relu_after_add,
+                srk_stream_t stream);
+
+/* Last layer: tensor-core conv from an FPA into an fp32 NHWC frame, fused with the global
+ * residual add and (ESPCN) the depth_to_space pixel shuffle:
+ *   out[n, Y*r+dy, X*r+dx, c] = act(conv(x)[n,Y,X,(dy*r+dx)*C + c] + bias) + addend[same index]
+ *   replaces tf.layers.conv2d(t, 3, 3, 'same') + `sd_images + tensors` vdsr/vdsr/model_vdsr.py:85-104
+ *            f3 conv + host un-pack  espcn/espcn/model_espcn.py:54-62, experiment_test.py:173-177
+ *            last conv + `bq_images + tensors`  enet/enet/model_enet.py:102-113
+ * cout = true output channels (<= 32); r = 1 (no shuffle) or the ESPCN scaling factor.
+ * out / addend: fp32 [n_frames, FH*r, FW*r, cout/(r*r)].  Without panels FH=H, FW=W. */
+int srk_conv_tc_last(srk_handle_t h, const void* x_fpa, int cin_p, const void* w_packed, const float* bias,
+                     int k, int cout, int cout_p, int act, int n_img, int H, int W,
+                     const srk_panel* panels, int n_frames, int FH, int FW, int shuffle_r,
+                     const float* addend, float* out, srk_stream_t stream);
+
+/* Weight gradient of a 3x3 64->64 layer on tensor cores: dW[u,v,ci,co] = sum_p x[p+(u-1)*Wp+(v-1)][ci]
+ * * dy[p][co]; split over CTAs, accumulated with fp32 atomics into dw_hwio (caller zeroes it, or
+ * pre-loads it with weight_decay*w); dbias[co] = sum_p dy[p][co].
+ *   replaces the wgrad/bgrad ops autodiff adds for  vdsr/vdsr/model_vdsr.py:146-148 (minimize). */
+int srk_conv_wgrad_tc(srk_handle_t h, const void* x_fpa, const void* dy_fpa, int n_img, int H, int W,
+                      float* dw_hwio, float* dbias, srk_stream_t stream);
+
+/* Weight gradient of the first layer (x fp32 NHWC cin<=4, dy FPA 64ch) -> dw [k,k,cin,64], db[64]. */
+int srk_conv_first_wgrad(srk_handle_t h, const float* x, int n_img, int H, int W, int cin, int k,
+                         const void* dy_fpa, float* dw_hwio, float* dbias, srk_stream_t stream);
+/* Weight gradient of the last layer (x FPA 64ch, dy fp32 NHWC cout<=4) -> dw [3,3,64,cout], db[cout]. */
+int srk_conv_last_wgrad(srk_handle_t h, const void* x_fpa, const float* dy, int n_img, int H, int W,
+                        int cout, float* dw_hwio, float* dbias, srk_stream_t stream);
+
+/* ---- bandwidth kernels ------------------------------------------------------------------------ */
+/* Standalone depth_to_space: [N,H,W,C*r*r] -> [N,H*r,W*r,C], packed channel (dy*r+dx)*C+c.
+ * espcn/espcn/experiment_test.py:173-177 (host np.split/reshape/concatenate). fp32. */
+int srk_pixel_shuffle(srk_handle_t h, const float* x, int N, int H, int W, int C, int r, float* y,
+                      srk_stream_t stream);
+/* Inverse packing, espcn/espcn/dataset.py:140-156. */
+int srk_pixel_unshuffle(srk_handle_t h, const float* x, int N, int H, int W, int C, int r, float* y,
+                        srk_stream_t stream);
+/* TF1-legacy bicubic (A=-0.75, 1024-entry table, no half-pixel centres): srcnn/srcnn.py:89-93. */
+int srk_resize_bicubic_tf1(srk_handle_t h, const float* x, int N, int H, int W, int C, int OH, int OW,
+                           float* y, srk_stream_t stream);
+/* VDSR degrade pre-pass: gaussian(sigma=0.5(s-1), replicate) -> bilinear down to int(H/s) x int(W/s)
+ * -> bilinear up (half-pixel, edge clamp), per-sample scale: vdsr/vdsr/dataset.py:13-38. */
+int srk_degrade_gauss_bilinear(srk_handle_t h, const float* hd, int N, int H, int W, int C,
+                               const float* scale_per_sample, float* sd, srk_stream_t stream);
+/* Nearest-neighbour x2 upsample of an FPA (enet/enet/model_enet.py:78-80) and its backward (2x2 sum). */
+int srk_fpa_upsample2(srk_handle_t h, const void* x_fpa, int n_img, int H, int W, void* y_fpa,
+                      srk_stream_t stream);
+int srk_fpa_upsample2_bwd(srk_handle_t h, const void* dy_fpa, int n_img, int H, int W, void* dx_fpa,
+                          srk_stream_t stream);
+/* MSE (tf.losses.mean_squared_error MEAN, vdsr/vdsr/model_vdsr.py:120-123): *loss_accum += sum((sr-hd)^2)/numel_total
+ * and dsr = 2(sr-hd)/numel_total.  numel_total lets a data-parallel rank scale by the GLOBAL element count. */
+int srk_mse_fwd_bwd(srk_handle_t h, const float* sr, const float* hd, size_t numel, double numel_total,
+                    float* loss_accum, float* dsr, srk_stream_t stream);
+/* SRCNN loss (srcnn/srcnn.py:142-144): mean over rows of ||reshape(sr-hd,[rows,cols])||_2, and its gradient. */
+int srk_l2norm_rows_mean_fwd_bwd(srk_handle_t h, const float* sr, const float* hd, int rows, int cols,
+                                 float* loss_accum, float* dsr, srk_stream_t stream);
+/* tf.train.AdamOptimizer step over a flat fp32 arena (vdsr/vdsr/model_vdsr.py:145-148; A.8 epsilon-hat
+ * form); t = 1-based step.  decay_mask (optional, n floats): g += weight_decay * decay_mask[i] * w[i]
+ * (the l2_regularizer term of model_vdsr.py:34,125: kernels 1, biases 0). */
+int srk_adam_step(srk_handle_t h, float* w, const float* g, float* m, float* v, size_t n, float lr,
+                  float beta1, float beta2, float eps, int64_t t, float weight_decay,
+                  const float* decay_mask, srk_stream_t stream);
+/* Momentum(0.9) with gradient clip +-cap/lr (vdsr/vdsr/model_vdsr.py:158-184). */
+int srk_momentum_clip_step(srk_handle_t h, float* w, const float* g, float* accum, size_t n, float lr,
+                           float momentum, float gradient_cap, float weight_decay, const float* decay_mask,
+                           srk_stream_t stream);
+/* FPA (bf16, C ch) <-> fp32 NHWC [n_img,H,W,C] converters (feature-map taps `conv.N:0`, tests). */
+int srk_fpa_to_nhwc(srk_handle_t h, const void* x_fpa, int C, int n_img, int H, int W, float* y,
+                    srk_stream_t stream);
+int srk_nhwc_to_fpa(srk_handle_t h, const float* x, int C, int n_img, int H, int W, void* y_fpa,
+                    srk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRK_H_ */

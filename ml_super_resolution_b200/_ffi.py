@@ -1,0 +1,72 @@
+"""ctypes binding of libsrk.so (include/srk.h).  No torch types cross this boundary: only raw
+device pointers, sizes and a cudaStream_t.  There is no CPU fallback -- a missing library or a
+failing call raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .build import LIB_PATH
+
+_lib = None
+
+
+class SrkError(RuntimeError):
+    pass
+
+
+class SrkPanel(C.Structure):
+    _fields_ = [("frame", C.c_int32), ("y0", C.c_int32), ("x0", C.c_int32), ("own_y0", C.c_int32),
+                ("own_y1", C.c_int32), ("own_x0", C.c_int32), ("own_x1", C.c_int32), ("reserved", C.c_int32)]
+
+
+_P, _I, _F, _SZ, _I64, _D = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_int64, C.c_double
+
+# name -> (restype, argtypes); mirrors include/srk.h declaration by declaration
+SIGNATURES = {
+    "srk_version": (_I, []),
+    "srk_last_error": (C.c_char_p, []),
+    "srk_create": (_I, [_I, C.POINTER(_P)]),
+    "srk_destroy": (_I, [_P]),
+    "srk_num_sms": (_I, [_P]),
+    "srk_fpa_rows": (_I64, [_I, _I, _I]),
+    "srk_pack_conv_weights": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "srk_conv_first": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P]),
+    "srk_conv_tc": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P]),
+    "srk_conv_tc_last": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "srk_conv_wgrad_tc": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "srk_conv_first_wgrad": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "srk_conv_last_wgrad": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "srk_pixel_shuffle": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "srk_pixel_unshuffle": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "srk_resize_bicubic_tf1": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "srk_degrade_gauss_bilinear": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "srk_fpa_upsample2": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    "srk_fpa_upsample2_bwd": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    "srk_mse_fwd_bwd": (_I, [_P, _P, _P, _SZ, _D, _P, _P, _P]),
+    "srk_l2norm_rows_mean_fwd_bwd": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
+    "srk_adam_step": (_I, [_P, _P, _P, _P, _P, _SZ, _F, _F, _F, _F, _I64, _F, _P, _P]),
+    "srk_momentum_clip_step": (_I, [_P, _P, _P, _P, _SZ, _F, _F, _F, _F, _P, _P]),
+    "srk_fpa_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
+    "srk_nhwc_to_fpa": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
+}
+
+
+def lib() -> C.CDLL:
+    """Load libsrk.so (built by `python -m ml_super_resolution_b200.build` / __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SrkError(f"{LIB_PATH} is missing: build it with __graft_entry__.build(); there is no CPU fallback")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        raise SrkError(f"{what} failed ({rc}): {lib().srk_last_error().decode()}")

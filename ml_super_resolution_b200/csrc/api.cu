@@ -1,0 +1,93 @@
+// Handle management, error text and tensor-map encoding for libsrk (include/srk.h).
+#include <cstring>
+#include <mutex>
+
+#include "srk_common.cuh"
+
+namespace srk {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tensor_map_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint32_t cols, uint32_t box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  SRK_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  const uint32_t row_bytes = cols * 2;
+  CUtensorMapSwizzle sw;
+  if (row_bytes == 128) sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  else if (row_bytes == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
+  else if (row_bytes == 32) sw = CU_TENSOR_MAP_SWIZZLE_32B;
+  else {
+    set_error("tensor map: unsupported row bytes %u", row_bytes);
+    return -1;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_bytes};
+  cuuint32_t box[2] = {cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SRK_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (ptr %p rows %llu cols %u)", int(r), gptr,
+              (unsigned long long)rows, cols);
+  return 0;
+}
+
+}  // namespace srk
+
+extern "C" {
+
+int srk_version(void) { return 100; }
+
+const char* srk_last_error(void) { return srk::g_err; }
+
+int srk_create(int device, srk_handle_t* out) {
+  SRK_REQUIRE(out != nullptr, "srk_create: out is NULL");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  SRK_REQUIRE(e == cudaSuccess && count > 0, "srk_create: no CUDA device (%s); libsrk has no CPU fallback",
+              cudaGetErrorString(e));
+  SRK_REQUIRE(device >= 0 && device < count, "srk_create: device %d out of range [0,%d)", device, count);
+  cudaDeviceProp prop;
+  SRK_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  SRK_REQUIRE(prop.major == 10, "srk_create: device %d is sm_%d%d; libsrk is built for sm_100a only", device, prop.major,
+              prop.minor);
+  srk_ctx* c = new srk_ctx;
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  c->smem_optin = int(prop.sharedMemPerBlockOptin);
+  *out = c;
+  return 0;
+}
+
+int srk_destroy(srk_handle_t h) {
+  delete h;
+  return 0;
+}
+
+int srk_num_sms(srk_handle_t h) { return h ? h->num_sms : -1; }
+
+int64_t srk_fpa_rows(int n_img, int H, int W) { return srk::fpa_geom(n_img, H, W).rows_alloc; }
+
+}  // extern "C"

@@ -1,0 +1,346 @@
+// CUDA-core kernels around the tensor-core conv: weight packing, the small-Cin first layer
+// (fp32 NHWC frame -> FPA), FPA <-> NHWC converters, and the first/last-layer weight gradients.
+// These layers carry <1% of the FLOPs and are HBM/L2-bound byte shuffles; they run on fp32 FMAs.
+#include <algorithm>
+
+#include "srk_common.cuh"
+
+namespace srk {
+
+// ------------------------------------------------------------------------------------ weight packing
+// packed[tap][n][kk] bf16, n < np, kk < cinp.  FWD: n=co, kk=ci, tap=(u,v).  DGRAD: n=ci, kk=co, tap=(k-1-u,k-1-v).
+__global__ void pack_weights_kernel(const float* __restrict__ w, int k, int cin, int cout, int mode, int np, int cinp,
+                                    __nv_bfloat16* __restrict__ out) {
+  const int total = k * k * np * cinp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int kk = i % cinp;
+    const int n = (i / cinp) % np;
+    const int tap = i / (cinp * np);
+    int u = tap / k, v = tap % k;
+    float val = 0.f;
+    if (mode == SRK_PACK_FWD) {
+      if (n < cout && kk < cin) val = w[((u * k + v) * cin + kk) * cout + n];
+    } else {
+      u = k - 1 - u;
+      v = k - 1 - v;
+      if (n < cin && kk < cout) val = w[((u * k + v) * cin + n) * cout + kk];
+    }
+    out[i] = __float2bfloat16_rn(val);
+  }
+}
+
+// ------------------------------------------------------------------------------------ first layer
+struct ConvFirstParams {
+  const float* x;
+  const float* w;     // HWIO [KS][KS][CIN][64]
+  const float* bias;  // [64] or null
+  __nv_bfloat16* y;   // FPA 64 ch
+  const __nv_bfloat16* relu_mask;
+  const srk_panel* panels;
+  int FH, FW;      // frame dims
+  int Hin, Win;    // panel-local input window (H + KS-1 for VALID, H for SAME)
+  int H, W, Wp;    // output FPA geometry
+  int64_t rows_valid;
+  int po;          // pad offset: KS/2 for SAME, 0 for VALID
+  int act;
+};
+
+template <int KS, int CIN>
+__global__ void __launch_bounds__(128) conv_first_kernel(const ConvFirstParams p) {
+  extern __shared__ float s_w[];  // [KS*KS*CIN][64]
+  constexpr int kW = KS * KS * CIN * 64;
+  for (int i = threadIdx.x; i < kW; i += blockDim.x) s_w[i] = p.w[i];
+  __syncthreads();
+  const int64_t prow = int64_t(blockIdx.x) * 128 + threadIdx.x;
+  if (prow >= p.rows_valid) return;
+  const uint32_t pr = uint32_t(prow);
+  const uint32_t q = pr / uint32_t(p.Wp);
+  const int x = int(pr - q * uint32_t(p.Wp));
+  const int n = int(q / uint32_t(p.H + 1));
+  const int yy = int(q - uint32_t(n) * uint32_t(p.H + 1));
+  const int y = yy - 1;
+  uint4* dst = reinterpret_cast<uint4*>(p.y + size_t(prow) * 64);
+  if (x >= p.W || yy == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[j] = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  int fn = n, y0 = 0, x0 = 0;
+  if (p.panels) {
+    const srk_panel e = p.panels[n];
+    fn = e.frame;
+    y0 = e.y0;
+    x0 = e.x0;
+  }
+  float acc[64];
+#pragma unroll
+  for (int c = 0; c < 64; ++c) acc[c] = p.bias ? __ldg(p.bias + c) : 0.f;
+  const float* frame = p.x + int64_t(fn) * p.FH * p.FW * CIN;
+#pragma unroll 1
+  for (int u = 0; u < KS; ++u) {
+    const int sy = y + u - p.po;
+    if (sy < 0 || sy >= p.Hin) continue;
+#pragma unroll 1
+    for (int v = 0; v < KS; ++v) {
+      const int sx = x + v - p.po;
+      if (sx < 0 || sx >= p.Win) continue;
+      const float* src = frame + (int64_t(y0 + sy) * p.FW + (x0 + sx)) * CIN;
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) {
+        const float val = __ldg(src + ci);
+        const float4* wr = reinterpret_cast<const float4*>(s_w + ((u * KS + v) * CIN + ci) * 64);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 w4 = wr[j];
+          acc[4 * j + 0] = fmaf(val, w4.x, acc[4 * j + 0]);
+          acc[4 * j + 1] = fmaf(val, w4.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(val, w4.z, acc[4 * j + 2]);
+          acc[4 * j + 3] = fmaf(val, w4.w, acc[4 * j + 3]);
+        }
+      }
+    }
+  }
+  if (p.act == SRK_ACT_RELU) {
+#pragma unroll
+    for (int c = 0; c < 64; ++c) acc[c] = fmaxf(acc[c], 0.f);
+  } else if (p.act == SRK_ACT_TANH) {
+#pragma unroll
+    for (int c = 0; c < 64; ++c) acc[c] = tanhf(acc[c]);
+  }
+  if (p.relu_mask) {
+    const uint4* m = reinterpret_cast<const uint4*>(p.relu_mask + size_t(prow) * 64);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint4 mv = __ldg(m + j);
+      const uint32_t w4[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e]));
+        if (!(f.x > 0.f)) acc[j * 8 + e * 2] = 0.f;
+        if (!(f.y > 0.f)) acc[j * 8 + e * 2 + 1] = 0.f;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint32_t r[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[j * 8 + e * 2], acc[j * 8 + e * 2 + 1]);
+      r[e] = *reinterpret_cast<uint32_t*>(&h2);
+    }
+    dst[j] = make_uint4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+template <int KS, int CIN>
+static int launch_conv_first(const ConvFirstParams& p, cudaStream_t s) {
+  const int smem = KS * KS * CIN * 64 * 4;
+  static bool attr_set = false;
+  if (!attr_set && smem > 48 * 1024) {
+    SRK_CHECK_CUDA(cudaFuncSetAttribute(conv_first_kernel<KS, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int grid = int((p.rows_valid + 127) / 128);
+  conv_first_kernel<KS, CIN><<<grid, 128, smem, s>>>(p);
+  SRK_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ converters
+__global__ void fpa_to_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int C, int n_img, int H, int W, float* __restrict__ y) {
+  const int64_t total = int64_t(n_img) * H * W * C;
+  const int Wp = W + 1;
+  const int64_t S = int64_t(H + 1) * Wp;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % C);
+    const int64_t pix = i / C;
+    const int xx = int(pix % W);
+    const int yy = int((pix / W) % H);
+    const int64_t n = pix / (int64_t(W) * H);
+    y[i] = __bfloat162float(x[(n * S + int64_t(yy + 1) * Wp + xx) * C + c]);
+  }
+}
+__global__ void nhwc_to_fpa_kernel(const float* __restrict__ x, int C, int n_img, int H, int W, int64_t rows_valid,
+                                   __nv_bfloat16* __restrict__ y) {
+  const int64_t total = rows_valid * C;
+  const int Wp = W + 1;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % C);
+    const int64_t prow = i / C;
+    const int64_t q = prow / Wp;
+    const int xx = int(prow - q * Wp);
+    const int64_t n = q / (H + 1);
+    const int yy = int(q - n * (H + 1));
+    float v = 0.f;
+    if (xx < W && yy > 0) v = x[((n * H + (yy - 1)) * int64_t(W) + xx) * C + c];
+    y[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------ first/last layer wgrad
+// First layer: dw[u][v][ci][co] = sum_{n,y,x} x[n, y+u-po, x+v-po, ci] * dy[n,y,x,co];  db[co] = sum dy.
+// One block per (tap, slice of pixels); 64 threads = co; fp32 atomics into dw/db (caller zeroes).
+__global__ void __launch_bounds__(64) conv_first_wgrad_kernel(const float* __restrict__ x, int n_img, int H, int W, int cin, int k,
+                                                              const __nv_bfloat16* __restrict__ dy, float* __restrict__ dw,
+                                                              float* __restrict__ db, int slices) {
+  const int tap = blockIdx.x / slices, slice = blockIdx.x % slices;
+  const bool do_bias = (tap == k * k);  // extra pseudo-tap accumulates the bias gradient
+  const int u = tap / k, v = tap % k, po = k / 2;
+  const int co = threadIdx.x;
+  const int Wp = W + 1;
+  const int64_t S = int64_t(H + 1) * Wp;
+  const int64_t npix = int64_t(n_img) * H * W;
+  const int64_t per = (npix + slices - 1) / slices;
+  const int64_t p0 = slice * per, p1 = min(npix, p0 + per);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t pix = p0; pix < p1; ++pix) {
+    const int xx = int(pix % W);
+    const int yy = int((pix / W) % H);
+    const int64_t n = pix / (int64_t(W) * H);
+    const float g = __bfloat162float(dy[(n * S + int64_t(yy + 1) * Wp + xx) * 64 + co]);
+    if (do_bias) {
+      acc[0] += g;
+      continue;
+    }
+    const int sy = yy + u - po, sx = xx + v - po;
+    if (sy < 0 || sy >= H || sx < 0 || sx >= W) continue;
+    const float* src = x + ((n * H + sy) * int64_t(W) + sx) * cin;
+    for (int ci = 0; ci < cin; ++ci) acc[ci] = fmaf(__ldg(src + ci), g, acc[ci]);
+  }
+  if (do_bias) {
+    atomicAdd(db + co, acc[0]);
+  } else {
+    for (int ci = 0; ci < cin; ++ci) atomicAdd(dw + (tap * cin + ci) * 64 + co, acc[ci]);
+  }
+}
+
+// Last layer: dw[u][v][ci][co] = sum_p x_fpa[p + (u-1)Wp + (v-1)][ci] * dy[p][co], co < cout <= 4; db[co] = sum dy.
+// One block per (tap, slice); 64 threads = ci.
+__global__ void __launch_bounds__(64) conv_last_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ dy,
+                                                             int n_img, int H, int W, int cout, float* __restrict__ dw,
+                                                             float* __restrict__ db, int slices) {
+  const int tap = blockIdx.x / slices, slice = blockIdx.x % slices;
+  const bool do_bias = (tap == 9);
+  const int u = tap / 3, v = tap % 3;
+  const int ci = threadIdx.x;
+  const int Wp = W + 1;
+  const int64_t S = int64_t(H + 1) * Wp;
+  const int64_t npix = int64_t(n_img) * H * W;
+  const int64_t per = (npix + slices - 1) / slices;
+  const int64_t p0 = slice * per, p1 = min(npix, p0 + per);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t pix = p0; pix < p1; ++pix) {
+    const int xx = int(pix % W);
+    const int yy = int((pix / W) % H);
+    const int64_t n = pix / (int64_t(W) * H);
+    const float* g = dy + pix * cout;
+    if (do_bias) {
+      if (ci < cout) acc[0] += __ldg(g + ci);
+      continue;
+    }
+    // FPA pads are zero, so out-of-image taps contribute nothing
+    const int64_t row = n * S + int64_t(yy + 1) * Wp + xx + int64_t(u - 1) * Wp + (v - 1);
+    if (row < 0 || row >= int64_t(n_img) * S) continue;  // outside the tensor: zero (TMA would zero-fill)
+    const float xv = __bfloat162float(x[row * 64 + ci]);
+    for (int co = 0; co < cout; ++co) acc[co] = fmaf(xv, __ldg(g + co), acc[co]);
+  }
+  if (do_bias) {
+    if (ci < cout) atomicAdd(db + ci, acc[0]);
+  } else {
+    for (int co = 0; co < cout; ++co) atomicAdd(dw + (tap * 64 + ci) * cout + co, acc[co]);
+  }
+}
+
+}  // namespace srk
+
+using namespace srk;
+
+extern "C" int srk_pack_conv_weights(srk_handle_t h, const float* w_hwio, int k, int cin, int cout, int mode, int np, int cinp,
+                                     void* packed_bf16, srk_stream_t stream) {
+  SRK_REQUIRE(h && w_hwio && packed_bf16, "srk_pack_conv_weights: null argument");
+  if (mode == SRK_PACK_FWD) SRK_REQUIRE(np >= cout && cinp >= cin, "srk_pack_conv_weights: padded dims too small");
+  else SRK_REQUIRE(np >= cin && cinp >= cout, "srk_pack_conv_weights: padded dims too small (dgrad)");
+  const int total = k * k * np * cinp;
+  pack_weights_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(w_hwio, k, cin, cout, mode, np, cinp,
+                                                                          static_cast<__nv_bfloat16*>(packed_bf16));
+  SRK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int srk_conv_first(srk_handle_t h, const float* x, int n_frames, int FH, int FW, int cin, const float* w_hwio,
+                              const float* bias, int k, int pad_mode, int act, const srk_panel* panels, int n_img, int H,
+                              int W, void* y_fpa, const void* relu_mask_src, srk_stream_t stream) {
+  SRK_REQUIRE(h && x && w_hwio && y_fpa, "srk_conv_first: null argument");
+  const int halo = (pad_mode == SRK_PAD_VALID) ? k - 1 : 0;
+  SRK_REQUIRE(panels || (n_frames == n_img && FH == H + halo && FW == W + halo),
+              "srk_conv_first: without panels the frame (%dx%d) must match the output geometry (%dx%d, k=%d)", FH, FW, H, W, k);
+  const FpaGeom g = fpa_geom(n_img, H, W);
+  SRK_REQUIRE(g.rows_valid < (int64_t(1) << 31), "srk_conv_first: too many rows");
+  ConvFirstParams p;
+  p.x = x;
+  p.w = w_hwio;
+  p.bias = bias;
+  p.y = static_cast<__nv_bfloat16*>(y_fpa);
+  p.relu_mask = static_cast<const __nv_bfloat16*>(relu_mask_src);
+  p.panels = panels;
+  p.FH = FH;
+  p.FW = FW;
+  p.Hin = H + halo;
+  p.Win = W + halo;
+  p.H = H;
+  p.W = W;
+  p.Wp = g.Wp;
+  p.rows_valid = g.rows_valid;
+  p.po = (pad_mode == SRK_PAD_VALID) ? 0 : k / 2;
+  p.act = act;
+  cudaStream_t s = as_stream(stream);
+#define SRK_CASE(KS, CIN) \
+  if (k == KS && cin == CIN) return launch_conv_first<KS, CIN>(p, s);
+  SRK_CASE(3, 1) SRK_CASE(3, 3) SRK_CASE(5, 1) SRK_CASE(5, 3) SRK_CASE(9, 1) SRK_CASE(9, 3)
+#undef SRK_CASE
+  set_error("srk_conv_first: unsupported (k=%d, cin=%d)", k, cin);
+  return -1;
+}
+
+extern "C" int srk_fpa_to_nhwc(srk_handle_t h, const void* x_fpa, int C, int n_img, int H, int W, float* y, srk_stream_t stream) {
+  SRK_REQUIRE(h && x_fpa && y, "srk_fpa_to_nhwc: null argument");
+  const int64_t total = int64_t(n_img) * H * W * C;
+  const int grid = int(std::min<int64_t>((total + 255) / 256, int64_t(h->num_sms) * 16));
+  fpa_to_nhwc_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(x_fpa), C, n_img, H, W, y);
+  SRK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int srk_nhwc_to_fpa(srk_handle_t h, const float* x, int C, int n_img, int H, int W, void* y_fpa, srk_stream_t stream) {
+  SRK_REQUIRE(h && x && y_fpa, "srk_nhwc_to_fpa: null argument");
+  const FpaGeom g = fpa_geom(n_img, H, W);
+  const int64_t total = g.rows_valid * C;
+  const int grid = int(std::min<int64_t>((total + 255) / 256, int64_t(h->num_sms) * 16));
+  nhwc_to_fpa_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, C, n_img, H, W, g.rows_valid, static_cast<__nv_bfloat16*>(y_fpa));
+  SRK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int srk_conv_first_wgrad(srk_handle_t h, const float* x, int n_img, int H, int W, int cin, int k, const void* dy_fpa,
+                                    float* dw_hwio, float* dbias, srk_stream_t stream) {
+  SRK_REQUIRE(h && x && dy_fpa && dw_hwio && dbias, "srk_conv_first_wgrad: null argument");
+  SRK_REQUIRE(cin >= 1 && cin <= 4, "srk_conv_first_wgrad: cin %d unsupported", cin);
+  const int slices = 64;
+  conv_first_wgrad_kernel<<<(k * k + 1) * slices, 64, 0, as_stream(stream)>>>(x, n_img, H, W, cin, k,
+                                                                            static_cast<const __nv_bfloat16*>(dy_fpa), dw_hwio,
+                                                                            dbias, slices);
+  SRK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int srk_conv_last_wgrad(srk_handle_t h, const void* x_fpa, const float* dy, int n_img, int H, int W, int cout,
+                                   float* dw_hwio, float* dbias, srk_stream_t stream) {
+  SRK_REQUIRE(h && x_fpa && dy && dw_hwio && dbias, "srk_conv_last_wgrad: null argument");
+  SRK_REQUIRE(cout >= 1 && cout <= 4, "srk_conv_last_wgrad: cout %d unsupported", cout);
+  const int slices = 64;
+  conv_last_wgrad_kernel<<<10 * slices, 64, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(x_fpa), dy, n_img, H, W, cout,
+                                                                    dw_hwio, dbias, slices);
+  SRK_LAUNCH_CHECK();
+  return 0;
+}

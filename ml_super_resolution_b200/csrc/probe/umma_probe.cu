@@ -331,14 +331,16 @@ int main() {
     place_sw128(img, X_OFF, X);
     place_sw128(img, Y_OFF, dY);
     struct Cfg { int s, d, swap; };
-    const Cfg cfgs[] = {{0, 8, 0}, {0, 1, 0}, {1, 1, 0}, {3, 42, 0}, {43, 84, 0}, {0, 8, 1}, {3, 42, 1}};
+    // negative d: second atom BEFORE the first one, LBO encoded modulo 2^18 bytes (14-bit field of 16 B units)
+    const Cfg cfgs[] = {{0, 8, 0}, {0, 1, 0}, {1, 1, 0}, {3, 42, 0}, {43, 84, 0}, {0, 8, 1}, {3, 42, 1},
+                        {50, -1, 0}, {50, -8, 0}, {300, -257, 0}, {131, -42, 0}};
     for (const Cfg& c : cfgs) {
       std::vector<MmaOp> ops;
       for (int k = 0; k < KTOT / 16; ++k) {
         MmaOp o{};
         o.a_off = X_OFF + (c.s + 16 * k) * 128;
         o.b_off = Y_OFF + (16 * k) * 128;
-        uint32_t lbo = c.d * 128, sbo = 1024;
+        uint32_t lbo = uint32_t(c.d * 128) & 0x3FFFFu, sbo = 1024;
         o.a_hi = c.swap ? umma_desc_hi(sbo, lbo, UMMA_LAYOUT_SW128) : umma_desc_hi(lbo, sbo, UMMA_LAYOUT_SW128);
         o.b_hi = c.swap ? umma_desc_hi(1024, 1024, UMMA_LAYOUT_SW128) : umma_desc_hi(1024, 1024, UMMA_LAYOUT_SW128);
         o.idesc = umma_idesc_bf16(128, 64, 1, 1);

@@ -3,6 +3,7 @@
 // (SRK_WAIT_BOUND polls) and traps instead of hanging the GPU box.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cuda.h>
 #include <cuda_runtime.h>
 

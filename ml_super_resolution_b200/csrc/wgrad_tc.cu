@@ -1,0 +1,216 @@
+// Tensor-core weight gradient of a 3x3 64->64 conv layer over FPAs (include/srk.h) for sm_100a.
+//
+//   dW[tap][ci][co] = sum_p X[p + off(tap)][ci] * dY[p][co],   off(u,v) = (u-1)*Wp + (v-1)
+//
+// is a GEMM whose contraction index is the pixel row p.  Both operands are "MN-major" in smem
+// exactly as TMA lands them ([pixel][channel] rows, SW128), so no transpose is ever materialised:
+// tcgen05.mma reads A = X^T and B = dY through MN-major descriptors (a_major = b_major = 1).
+// One M=128 instruction covers TWO taps: its two 64-row M atoms are two row-shifted windows of the
+// same X ring, LBO = (off_b - off_a) * 128 B apart (probe-verified; LBO must be positive, so the
+// ring keeps a mirror of its first chunks behind its last slot).  The ninth tap is paired with a
+// block of ones, which makes rows 64..127 of that accumulator the bias gradient sum_p dY[p][co].
+// Five fp32 accumulators (5 x 64 TMEM columns) persist over the CTA's whole pixel range (split-K
+// across CTAs); the epilogue adds them into dW / dbias with fp32 reductions.
+//
+//   warp 0: TMA producer for X chunks (+ mirrors)      warp 6: TMA producer for dY chunks
+//   warp 1: TMEM allocator + single-thread MMA issuer  warps 2..5: epilogue
+#include "sm100_ptx.cuh"
+#include "srk_common.cuh"
+
+namespace srk {
+
+constexpr int kXSlots = 10;  // ring + mirror slots (16 KB each)
+constexpr int kYRing = 3;
+constexpr int kWgThreads = 224;
+constexpr int kChunk = 128 * 128;  // bytes
+
+struct alignas(64) WgradParams {
+  CUtensorMap map_x;   // [rows_valid][64] box {64,128}
+  CUtensorMap map_dy;  // [rows_valid][64] box {64,128}
+  float* dw;           // [9][64][64] fp32 (HWIO), accumulated
+  float* dbias;        // [64]
+  int Wp;
+  int num_chunks;
+  int nb;      // look-behind/ahead chunks: ceil((Wp+1)/128)
+  int ring;    // X ring slots
+  int mirror;  // mirrored leading slots: ceil((Wp+16)/128)
+};
+
+struct WgSmem {
+  static constexpr int kOffX = 0;
+  static constexpr int kOffY = kXSlots * kChunk;
+  static constexpr int kOffOnes = kOffY + kYRing * kChunk;
+  static constexpr int kOffBars = kOffOnes + 2048;
+  static constexpr int kNumBars = 2 * kXSlots + 2 * kYRing + 1;
+  static constexpr int kOffTmemSlot = kOffBars + kNumBars * 8;
+  static constexpr int kTotal = kOffTmemSlot + 16 + 1024;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t s_x = s_base + WgSmem::kOffX;
+  const uint32_t s_y = s_base + WgSmem::kOffY;
+  const uint32_t s_ones = s_base + WgSmem::kOffOnes;
+  const uint32_t s_bars = s_base + WgSmem::kOffBars;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + WgSmem::kOffTmemSlot);
+  auto bar_xfull = [&](int s) { return s_bars + 8u * s; };
+  auto bar_xempty = [&](int s) { return s_bars + 8u * (kXSlots + s); };
+  auto bar_yfull = [&](int s) { return s_bars + 8u * (2 * kXSlots + s); };
+  auto bar_yempty = [&](int s) { return s_bars + 8u * (2 * kXSlots + kYRing + s); };
+  const uint32_t bar_done = s_bars + 8u * (2 * kXSlots + 2 * kYRing);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k_begin = int((int64_t(blockIdx.x) * p.num_chunks) / gridDim.x);
+  const int k_end = int((int64_t(blockIdx.x + 1) * p.num_chunks) / gridDim.x);
+  const int nb = p.nb, R = p.ring;
+  const int c0 = k_begin - nb, c_last = k_end - 1 + nb;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kXSlots; ++i) {
+      mbar_init(bar_xfull(i), 1);
+      mbar_init(bar_xempty(i), 1);
+    }
+    for (int i = 0; i < kYRing; ++i) {
+      mbar_init(bar_yfull(i), 1);
+      mbar_init(bar_yempty(i), 1);
+    }
+    mbar_init(bar_done, 1);
+    fence_mbar_init();
+  }
+  // 16 rows x 64 channels of bf16 1.0 (0x3F80): the swizzle of a constant block is the block itself
+  for (int i = threadIdx.x; i < 2048 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem + WgSmem::kOffOnes)[i] = 0x3F803F80u;
+  fence_proxy_async_smem();
+  if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.map_x);
+    tma_prefetch_desc(&p.map_dy);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (k_begin < k_end) {
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int c = c0; c <= c_last; ++c) {
+          const int i = c - c0, slot = i % R, gen = i / R;
+          mbar_wait(bar_xempty(slot), (gen & 1) ^ 1);
+          const bool mir = slot < p.mirror;
+          mbar_arrive_expect_tx(bar_xfull(slot), kChunk * (mir ? 2 : 1));
+          tma_load_2d(s_x + slot * kChunk, &p.map_x, 0, c * 128, bar_xfull(slot));
+          if (mir) tma_load_2d(s_x + (R + slot) * kChunk, &p.map_x, 0, c * 128, bar_xfull(slot));
+        }
+      }
+    } else if (warp == 6) {
+      if (lane == 0) {
+        for (int k = k_begin; k < k_end; ++k) {
+          const int j = k - k_begin, slot = j % kYRing, gen = j / kYRing;
+          mbar_wait(bar_yempty(slot), (gen & 1) ^ 1);
+          mbar_arrive_expect_tx(bar_yfull(slot), kChunk);
+          tma_load_2d(s_y + slot * kChunk, &p.map_dy, 0, k * 128, bar_yfull(slot));
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
+        constexpr uint64_t b_hi = umma_desc_hi(1024, 1024, UMMA_LAYOUT_SW128);
+        const int Wp = p.Wp;
+        // tap pairs (a, b): offsets of a, and distance d = off_b - off_a > 0 (rows)
+        const int off_a[5] = {-Wp - 1, -1, Wp - 1, -Wp + 1, Wp + 1};
+        const int dist[5] = {1, 1, 1, Wp, 0 /* ones block */};
+        int loaded = c0 - 1;
+        const int ring_rows = R * 128;
+        for (int k = k_begin; k < k_end; ++k) {
+          const int j = k - k_begin;
+          while (loaded < k + nb) {
+            ++loaded;
+            const int i = loaded - c0;
+            mbar_wait(bar_xfull(i % R), (i / R) & 1);
+          }
+          mbar_wait(bar_yfull(j % kYRing), (j / kYRing) & 1);
+          tc_fence_after();
+          const int row0 = (j + nb) * 128;
+          const uint32_t y_addr = s_y + (j % kYRing) * kChunk;
+#pragma unroll 1
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint64_t bdesc = umma_desc(b_hi, y_addr + kk * 2048);
+#pragma unroll
+            for (int pr = 0; pr < 5; ++pr) {
+              const int a0 = (row0 + off_a[pr] + 16 * kk) % ring_rows;
+              const uint32_t a_addr = s_x + uint32_t(a0) * 128u;
+              const uint32_t lbo = (pr == 4) ? (s_ones - a_addr) : uint32_t(dist[pr]) * 128u;
+              umma_bf16(tmem + pr * 64, umma_desc(umma_desc_hi(lbo, 1024, UMMA_LAYOUT_SW128), a_addr), bdesc, idesc,
+                        (j | kk) != 0);
+            }
+          }
+          umma_commit(bar_xempty(j % R));  // X chunk k-nb (= c0+j) is done
+          umma_commit(bar_yempty(j % kYRing));
+        }
+        umma_commit(bar_done);
+      }
+    } else {
+      // ---------------------------------------------------------------- epilogue: TMEM -> global reductions
+      const int quad = warp & 3;
+      const int m = quad * 32 + lane;  // accumulator row
+      mbar_wait(bar_done, 0);
+      tc_fence_after();
+      const int tap_of[5][2] = {{0, 1}, {3, 4}, {6, 7}, {2, 5}, {8, -1}};
+#pragma unroll 1
+      for (int pr = 0; pr < 5; ++pr) {
+        const int tap = tap_of[pr][m >> 6];
+        const int ci = m & 63;
+#pragma unroll
+        for (int c = 0; c < 64; c += 32) {
+          uint32_t u[32];
+          tmem_ld_32x32b_x32(tmem + pr * 64 + c + (uint32_t(quad * 32) << 16), u);
+          tmem_ld_wait();
+          if (tap >= 0) {
+            float* dst = p.dw + (size_t(tap) * 64 + ci) * 64 + c;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) atomicAdd(dst + q, __uint_as_float(u[q]));
+          } else if (m == 64) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) atomicAdd(p.dbias + c + q, __uint_as_float(u[q]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace srk
+
+using namespace srk;
+
+extern "C" int srk_conv_wgrad_tc(srk_handle_t h, const void* x_fpa, const void* dy_fpa, int n_img, int H, int W, float* dw_hwio,
+                                 float* dbias, srk_stream_t stream) {
+  SRK_REQUIRE(h && x_fpa && dy_fpa && dw_hwio && dbias, "srk_conv_wgrad_tc: null argument");
+  const FpaGeom g = fpa_geom(n_img, H, W);
+  SRK_REQUIRE(g.rows_valid < (int64_t(1) << 31), "srk_conv_wgrad_tc: too many rows");
+  WgradParams p{};
+  p.dw = dw_hwio;
+  p.dbias = dbias;
+  p.Wp = g.Wp;
+  p.num_chunks = int((g.rows_valid + 127) / 128);
+  p.nb = (g.Wp + 1 + 127) / 128;
+  p.mirror = (g.Wp + 16 + 127) / 128;
+  p.ring = kXSlots - p.mirror;
+  SRK_REQUIRE(p.ring >= 2 * p.nb + 2, "srk_conv_wgrad_tc: image width %d too large for the flat-stream kernel", W);
+  if (int rc = make_tensor_map_2d(&p.map_x, x_fpa, uint64_t(g.rows_valid), 64, 128)) return rc;
+  if (int rc = make_tensor_map_2d(&p.map_dy, dy_fpa, uint64_t(g.rows_valid), 64, 128)) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SRK_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem::kTotal));
+    attr_set = true;
+  }
+  const int grid = p.num_chunks < h->num_sms ? p.num_chunks : h->num_sms;
+  wgrad_tc_kernel<<<grid, kWgThreads, WgSmem::kTotal, as_stream(stream)>>>(p);
+  SRK_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,285 @@
+"""Host-side operator layer: one Python function per libsrk entry point (include/srk.h).
+
+torch is used only as the device allocator and stream provider (`.data_ptr()`,
+`torch.cuda.current_stream().cuda_stream`); all arithmetic happens in the hand-written sm_100a
+kernels.  Every function is asynchronous on torch's current stream and CUDA-graph capturable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _ffi
+from ._ffi import SrkPanel, check
+
+ACT = {None: 0, "none": 0, "linear": 0, "relu": 1, "tanh": 2}
+PAD = {"SAME": 0, "same": 0, "VALID": 1, "valid": 1}
+PACK_FWD, PACK_DGRAD = 0, 1
+
+_handles: dict[int, C.c_void_p] = {}
+
+
+def handle(device: int | None = None) -> C.c_void_p:
+    """Per-device libsrk handle (created on first use; fails loudly without an sm_100 GPU)."""
+    if device is None:
+        device = torch.cuda.current_device()
+    h = _handles.get(device)
+    if h is None:
+        h = C.c_void_p()
+        check(_ffi.lib().srk_create(device, C.byref(h)), "srk_create")
+        _handles[device] = h
+    return h
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: torch.Tensor | None) -> C.c_void_p:
+    if t is None:
+        return C.c_void_p(0)
+    assert t.is_cuda and t.is_contiguous(), "libsrk takes contiguous device tensors"
+    return C.c_void_p(t.data_ptr())
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    assert t.dtype == torch.float32, t.dtype
+    return t
+
+
+# ------------------------------------------------------------------------------------------
+# FPA buffers
+# ------------------------------------------------------------------------------------------
+
+
+@dataclass
+class Fpa:
+    """Flat padded activation (include/srk.h): bf16 [rows, C], pixel (n,y,x) at row n*S+(y+1)*Wp+x."""
+    data: torch.Tensor  # bf16 [rows_alloc, C]
+    n_img: int
+    H: int
+    W: int
+
+    @property
+    def C(self) -> int:
+        return self.data.shape[1]
+
+
+def fpa_rows(n_img: int, H: int, W: int) -> int:
+    return int(_ffi.lib().srk_fpa_rows(n_img, H, W))
+
+
+def fpa_empty(n_img: int, H: int, W: int, C_: int = 64, device=None) -> Fpa:
+    rows = fpa_rows(n_img, H, W)
+    return Fpa(torch.empty((rows, C_), dtype=torch.bfloat16, device=device or "cuda"), n_img, H, W)
+
+
+def fpa_from_nhwc(x: torch.Tensor, C_: int | None = None) -> Fpa:
+    n, h, w, c = x.shape
+    out = fpa_empty(n, h, w, C_ or c, x.device)
+    assert out.C == c, "channel padding not supported here"
+    check(_ffi.lib().srk_nhwc_to_fpa(handle(), _ptr(_f32(x)), c, n, h, w, _ptr(out.data), _stream()), "srk_nhwc_to_fpa")
+    return out
+
+
+def fpa_to_nhwc(a: Fpa) -> torch.Tensor:
+    y = torch.empty((a.n_img, a.H, a.W, a.C), dtype=torch.float32, device=a.data.device)
+    check(_ffi.lib().srk_fpa_to_nhwc(handle(), _ptr(a.data), a.C, a.n_img, a.H, a.W, _ptr(y), _stream()), "srk_fpa_to_nhwc")
+    return y
+
+
+def make_panels(entries, device="cuda") -> torch.Tensor:
+    """entries: iterable of (frame, y0, x0, own_y0, own_y1, own_x0, own_x1) -> int32 [n,8] device tensor."""
+    arr = np.zeros((len(entries), 8), np.int32)
+    for i, e in enumerate(entries):
+        arr[i, :7] = e
+    return torch.from_numpy(arr).to(device)
+
+
+# ------------------------------------------------------------------------------------------
+# conv family
+# ------------------------------------------------------------------------------------------
+
+
+def _round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+def pad_cout(cout: int) -> int:
+    return 16 if cout <= 16 else (32 if cout <= 32 else 64)
+
+
+def pack_conv_weights(w_hwio: torch.Tensor, mode: int = PACK_FWD, np_: int | None = None, cinp: int | None = None,
+                      out: torch.Tensor | None = None) -> torch.Tensor:
+    """fp32 HWIO [k,k,cin,cout] -> bf16 [k*k, np, cinp] GEMM-B blocks (see srk_pack_conv_weights)."""
+    k, k2, cin, cout = w_hwio.shape
+    assert k == k2
+    n_true, k_true = (cout, cin) if mode == PACK_FWD else (cin, cout)
+    np_ = np_ or pad_cout(n_true)
+    cinp = cinp or (32 if k_true <= 32 else 64)
+    if out is None:
+        out = torch.empty((k * k, np_, cinp), dtype=torch.bfloat16, device=w_hwio.device)
+    check(_ffi.lib().srk_pack_conv_weights(handle(), _ptr(_f32(w_hwio)), k, cin, cout, mode, np_, cinp, _ptr(out), _stream()),
+          "srk_pack_conv_weights")
+    return out
+
+
+def pad_bias(b: torch.Tensor | None, np_: int) -> torch.Tensor | None:
+    if b is None:
+        return None
+    if b.numel() == np_:
+        return b
+    out = torch.zeros(np_, dtype=torch.float32, device=b.device)
+    out[: b.numel()] = b
+    return out
+
+
+def conv_first(x: torch.Tensor, w_hwio: torch.Tensor, bias: torch.Tensor | None, padding="SAME", act=None,
+               panels: torch.Tensor | None = None, panel_hw: tuple[int, int] | None = None, out: Fpa | None = None,
+               relu_mask: Fpa | None = None) -> Fpa:
+    """Small-Cin first layer: fp32 NHWC frames -> FPA (srk_conv_first)."""
+    nf, fh, fw, cin = x.shape
+    k = w_hwio.shape[0]
+    assert w_hwio.shape[3] == 64
+    halo = k - 1 if PAD[padding] == 1 else 0
+    if panels is None:
+        n_img, H, W = nf, fh - halo, fw - halo
+    else:
+        n_img = panels.shape[0]
+        H, W = panel_hw[0] - halo, panel_hw[1] - halo
+    if out is None:
+        out = fpa_empty(n_img, H, W, 64, x.device)
+    check(_ffi.lib().srk_conv_first(handle(), _ptr(_f32(x)), nf, fh, fw, cin, _ptr(_f32(w_hwio)), _ptr(bias), k, PAD[padding],
+                                    ACT[act], _ptr(panels), n_img, H, W, _ptr(out.data),
+                                    _ptr(relu_mask.data if relu_mask is not None else None), _stream()), "srk_conv_first")
+    return out
+
+
+def conv_tc(x: Fpa, w_packed: torch.Tensor, bias: torch.Tensor | None, k: int, act=None, out: Fpa | None = None,
+            mask_src: Fpa | None = None, mask_kind=None, addend: Fpa | None = None, relu_after_add=False) -> Fpa:
+    """Tensor-core conv FPA -> FPA (srk_conv_tc).  w_packed: [k*k, cout_p, cin_p] bf16."""
+    cout_p, cin_p = w_packed.shape[1], w_packed.shape[2]
+    assert cin_p == x.C, (cin_p, x.C)
+    if out is None:
+        out = fpa_empty(x.n_img, x.H, x.W, cout_p, x.data.device)
+    check(_ffi.lib().srk_conv_tc(handle(), _ptr(x.data), cin_p, _ptr(w_packed), _ptr(bias), k, cout_p, ACT[act], x.n_img, x.H, x.W,
+                                 _ptr(out.data), _ptr(mask_src.data if mask_src is not None else None), ACT[mask_kind],
+                                 _ptr(addend.data if addend is not None else None), int(relu_after_add), _stream()), "srk_conv_tc")
+    return out
+
+
+def conv_tc_last(x: Fpa, w_packed: torch.Tensor, bias: torch.Tensor | None, k: int, cout: int, act=None,
+                 addend: torch.Tensor | None = None, shuffle_r: int = 1, panels: torch.Tensor | None = None,
+                 frame_shape: tuple[int, int, int] | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Last layer FPA -> fp32 NHWC with fused residual add / pixel shuffle / panel crop (srk_conv_tc_last)."""
+    cout_p, cin_p = w_packed.shape[1], w_packed.shape[2]
+    assert cin_p == x.C
+    if panels is None:
+        nf, fh, fw = x.n_img, x.H, x.W
+    else:
+        nf, fh, fw = frame_shape
+    r = shuffle_r
+    if out is None:
+        out = torch.empty((nf, fh * r, fw * r, cout // (r * r)), dtype=torch.float32, device=x.data.device)
+    check(_ffi.lib().srk_conv_tc_last(handle(), _ptr(x.data), cin_p, _ptr(w_packed), _ptr(bias), k, cout, cout_p, ACT[act], x.n_img,
+                                      x.H, x.W, _ptr(panels), nf, fh, fw, r, _ptr(addend), _ptr(out), _stream()), "srk_conv_tc_last")
+    return out
+
+
+def conv_wgrad_tc(x: Fpa, dy: Fpa, dw: torch.Tensor, dbias: torch.Tensor) -> None:
+    """dw [3,3,64,64] += X^T dY per tap, dbias [64] += sum dY (srk_conv_wgrad_tc)."""
+    check(_ffi.lib().srk_conv_wgrad_tc(handle(), _ptr(x.data), _ptr(dy.data), x.n_img, x.H, x.W, _ptr(_f32(dw)), _ptr(_f32(dbias)),
+                                       _stream()), "srk_conv_wgrad_tc")
+
+
+def conv_first_wgrad(x: torch.Tensor, dy: Fpa, k: int, dw: torch.Tensor, dbias: torch.Tensor) -> None:
+    n, h, w, cin = x.shape
+    check(_ffi.lib().srk_conv_first_wgrad(handle(), _ptr(_f32(x)), n, h, w, cin, k, _ptr(dy.data), _ptr(dw), _ptr(dbias), _stream()),
+          "srk_conv_first_wgrad")
+
+
+def conv_last_wgrad(x: Fpa, dy: torch.Tensor, dw: torch.Tensor, dbias: torch.Tensor) -> None:
+    cout = dy.shape[-1]
+    check(_ffi.lib().srk_conv_last_wgrad(handle(), _ptr(x.data), _ptr(_f32(dy)), x.n_img, x.H, x.W, cout, _ptr(dw), _ptr(dbias),
+                                         _stream()), "srk_conv_last_wgrad")
+
+
+# ------------------------------------------------------------------------------------------
+# bandwidth kernels
+# ------------------------------------------------------------------------------------------
+
+
+def pixel_shuffle(x: torch.Tensor, r: int) -> torch.Tensor:
+    n, h, w, k = x.shape
+    c = k // (r * r)
+    y = torch.empty((n, h * r, w * r, c), dtype=torch.float32, device=x.device)
+    check(_ffi.lib().srk_pixel_shuffle(handle(), _ptr(_f32(x)), n, h, w, c, r, _ptr(y), _stream()), "srk_pixel_shuffle")
+    return y
+
+
+def pixel_unshuffle(x: torch.Tensor, r: int) -> torch.Tensor:
+    n, hh, ww, c = x.shape
+    h, w = hh // r, ww // r
+    y = torch.empty((n, h, w, c * r * r), dtype=torch.float32, device=x.device)
+    check(_ffi.lib().srk_pixel_unshuffle(handle(), _ptr(_f32(x)), n, h, w, c, r, _ptr(y), _stream()), "srk_pixel_unshuffle")
+    return y
+
+
+def resize_bicubic_tf1(x: torch.Tensor, oh: int, ow: int) -> torch.Tensor:
+    n, h, w, c = x.shape
+    y = torch.empty((n, oh, ow, c), dtype=torch.float32, device=x.device)
+    check(_ffi.lib().srk_resize_bicubic_tf1(handle(), _ptr(_f32(x)), n, h, w, c, oh, ow, _ptr(y), _stream()), "srk_resize_bicubic_tf1")
+    return y
+
+
+def degrade_gauss_bilinear(hd: torch.Tensor, scales: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    n, h, w, c = hd.shape
+    if out is None:
+        out = torch.empty_like(hd)
+    check(_ffi.lib().srk_degrade_gauss_bilinear(handle(), _ptr(_f32(hd)), n, h, w, c, _ptr(_f32(scales)), _ptr(out), _stream()),
+          "srk_degrade_gauss_bilinear")
+    return out
+
+
+def fpa_upsample2(x: Fpa, out: Fpa | None = None) -> Fpa:
+    assert x.C == 64
+    if out is None:
+        out = fpa_empty(x.n_img, 2 * x.H, 2 * x.W, 64, x.data.device)
+    check(_ffi.lib().srk_fpa_upsample2(handle(), _ptr(x.data), x.n_img, x.H, x.W, _ptr(out.data), _stream()), "srk_fpa_upsample2")
+    return out
+
+
+def fpa_upsample2_bwd(dy: Fpa, out: Fpa | None = None) -> Fpa:
+    assert dy.C == 64
+    h, w = dy.H // 2, dy.W // 2
+    if out is None:
+        out = fpa_empty(dy.n_img, h, w, 64, dy.data.device)
+    check(_ffi.lib().srk_fpa_upsample2_bwd(handle(), _ptr(dy.data), dy.n_img, h, w, _ptr(out.data), _stream()), "srk_fpa_upsample2_bwd")
+    return out
+
+
+def mse_fwd_bwd(sr: torch.Tensor, hd: torch.Tensor, loss_accum: torch.Tensor, dsr: torch.Tensor | None = None,
+                numel_total: float | None = None) -> None:
+    n = sr.numel()
+    check(_ffi.lib().srk_mse_fwd_bwd(handle(), _ptr(_f32(sr)), _ptr(_f32(hd)), n, float(numel_total or n), _ptr(loss_accum), _ptr(dsr),
+                                     _stream()), "srk_mse_fwd_bwd")
+
+
+def l2norm_rows_mean_fwd_bwd(sr: torch.Tensor, hd: torch.Tensor, cols: int, loss_accum: torch.Tensor,
+                             dsr: torch.Tensor | None = None) -> None:
+    rows = sr.numel() // cols
+    check(_ffi.lib().srk_l2norm_rows_mean_fwd_bwd(handle(), _ptr(_f32(sr)), _ptr(_f32(hd)), rows, cols, _ptr(loss_accum), _ptr(dsr),
+                                                  _stream()), "srk_l2norm_rows_mean_fwd_bwd")
+
+
+def adam_step(w, g, m, v, lr: float, t: int, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, decay_mask=None) -> None:
+    check(_ffi.lib().srk_adam_step(handle(), _ptr(_f32(w)), _ptr(_f32(g)), _ptr(m), _ptr(v), w.numel(), lr, beta1, beta2, eps, t,
+                                   weight_decay, _ptr(decay_mask), _stream()), "srk_adam_step")
+
+
+def momentum_clip_step(w, g, accum, lr: float, momentum=0.9, gradient_cap=0.01, weight_decay=0.0, decay_mask=None) -> None:
+    check(_ffi.lib().srk_momentum_clip_step(handle(), _ptr(_f32(w)), _ptr(_f32(g)), _ptr(accum), w.numel(), lr, momentum, gradient_cap,
+                                            weight_decay, _ptr(decay_mask), _stream()), "srk_momentum_clip_step")

@@ -1,0 +1,16 @@
+"""CPU oracle for the convolutional hot path of imironhead/ml_super_resolution.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product package
+(`ml_super_resolution_b200/`) may import this; the only legal importers are
+`tests/`, `__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline` /
+`--impl reference` legs.
+
+PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures
+ and its arithmetic lives in un-vendored TensorFlow 1.8 /
+scikit-image 0.14 / PIL, none of which can be installed in this image.  The
+oracle restates the published semantics of those ops and
+is cross-validated internally (torch fp64 conv vs explicit numpy im2col GEMM vs
+finite differences; bilinear vs cv2.INTER_LINEAR; pixel-shuffle vs the
+reference's own numpy pack/unpack code paths restated verbatim).
+"""
+from . import ops, models  # noqa: F401

@@ -1,0 +1,192 @@
+"""Parity of the CUDA conv kernels (through the C ABI) against the CPU oracle.  Tolerances:
+north_star allows max-abs 2e-2 on [0,1] images in bf16 == 4e-2 on the reference's [-1,1] range;
+kernel-level checks here are much tighter (bf16 store rounding: 2^-8 relative)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ops as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _rng(seed):
+    return np.random.default_rng(seed)
+
+
+def _bf(x):
+    return O.bf16_round(np.asarray(x, np.float32))
+
+
+def _close_bf16(got, ref, rel=2.0 ** -7, abs_=2e-3):
+    got = np.asarray(got, np.float64)
+    ref = np.asarray(ref, np.float64)
+    err = np.abs(got - ref)
+    tol = rel * np.abs(ref) + abs_
+    bad = err > tol
+    assert not bad.any(), f"{bad.sum()} / {bad.size} mismatches, max err {err.max():.4g} (ref max {np.abs(ref).max():.4g})"
+
+
+def _dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+@pytest.mark.parametrize("k,cin,pad,act,shape", [
+    (3, 3, "SAME", "relu", (2, 9, 11)),
+    (3, 1, "SAME", "relu", (1, 16, 7)),
+    (5, 1, "SAME", "tanh", (2, 12, 13)),
+    (5, 3, "SAME", "tanh", (1, 17, 17)),
+    (9, 3, "VALID", "relu", (2, 21, 23)),
+    (9, 1, "VALID", "relu", (3, 33, 33)),
+    (3, 3, "SAME", "relu", (4, 41, 41)),
+])
+def test_conv_first(srk_ops, k, cin, pad, act, shape):
+    n, h, w = shape
+    r = _rng(k * 100 + cin)
+    x = r.uniform(-1, 1, (n, h, w, cin)).astype(np.float32)
+    wt = (r.standard_normal((k, k, cin, 64)) * 0.2).astype(np.float32)
+    b = (r.standard_normal(64) * 0.1).astype(np.float32)
+    y = srk_ops.conv_first(_dev(x), _dev(wt), _dev(b), pad, act)
+    got = srk_ops.fpa_to_nhwc(y).cpu().numpy()
+    ref = O.conv2d_nhwc(x, wt, b, pad, act)
+    assert got.shape == ref.shape
+    _close_bf16(got, ref)
+    # pad rows / columns of the FPA must be exactly zero
+    raw = y.data.float().cpu().numpy()
+    Wp, S = y.W + 1, (y.H + 1) * (y.W + 1)
+    rows = np.arange(y.n_img * S)
+    is_pad = ((rows % Wp) == y.W) | (((rows // Wp) % (y.H + 1)) == 0)
+    assert np.all(raw[: y.n_img * S][is_pad] == 0)
+
+
+@pytest.mark.parametrize("cin,cout,k,act,shape", [
+    (64, 64, 3, "relu", (2, 7, 9)),
+    (64, 64, 3, "relu", (64, 41, 41)),
+    (64, 64, 3, None, (1, 5, 130)),     # Wp > 127: two chunks of look-behind
+    (64, 64, 3, "relu", (1, 300, 254)),  # widest supported panel
+    (64, 32, 3, "tanh", (2, 17, 17)),
+    (64, 64, 1, None, (3, 32, 32)),
+    (64, 32, 1, "relu", (2, 25, 25)),
+    (32, 64, 3, None, (2, 17, 17)),
+])
+def test_conv_tc_fpa(srk_ops, cin, cout, k, act, shape):
+    n, h, w = shape
+    r = _rng(cin + cout + k + h)
+    x = _bf(r.uniform(-1, 1, (n, h, w, cin)))
+    wt = _bf(r.standard_normal((k, k, cin, cout)) * (1.0 / np.sqrt(k * k * cin)))
+    b = (r.standard_normal(cout) * 0.1).astype(np.float32)
+    xf = srk_ops.fpa_from_nhwc(_dev(x))
+    wp = srk_ops.pack_conv_weights(_dev(wt))
+    y = srk_ops.conv_tc(xf, wp, _dev(b), k, act)
+    got = srk_ops.fpa_to_nhwc(y).cpu().numpy()
+    ref = O.conv2d_nhwc(x, wt, b, "SAME", act)
+    _close_bf16(got, ref)
+    raw = y.data.float().cpu().numpy()
+    Wp, S = y.W + 1, (y.H + 1) * (y.W + 1)
+    rows = np.arange(y.n_img * S)
+    is_pad = ((rows % Wp) == y.W) | (((rows // Wp) % (y.H + 1)) == 0)
+    assert np.all(raw[: y.n_img * S][is_pad] == 0)
+
+
+def test_conv_tc_dgrad_mask_and_addend(srk_ops):
+    """dgrad form: rot180/transposed weights + ReLU' mask; and the ENet block form relu(x + conv1x1)."""
+    r = _rng(7)
+    n, h, w = 3, 19, 23
+    dy = _bf(r.standard_normal((n, h, w, 64)))
+    wt = _bf(r.standard_normal((3, 3, 64, 64)) / 24.0)
+    saved = _bf(r.standard_normal((n, h, w, 64)))
+    dyf = srk_ops.fpa_from_nhwc(_dev(dy))
+    sf = srk_ops.fpa_from_nhwc(_dev(saved))
+    wd = srk_ops.pack_conv_weights(_dev(wt), srk_ops.PACK_DGRAD)
+    dx = srk_ops.conv_tc(dyf, wd, None, 3, None, mask_src=sf, mask_kind="relu")
+    got = srk_ops.fpa_to_nhwc(dx).cpu().numpy()
+    # oracle: dL/dx of y = conv(x, w) given dy, times relu'(saved)
+    gx, _, _ = O.conv2d_backward(np.zeros((n, h, w, 64)), wt, np.zeros(64), dy, "SAME", None)
+    _close_bf16(got, gx * (saved > 0))
+    # tanh mask
+    dx2 = srk_ops.conv_tc(dyf, wd, None, 3, None, mask_src=sf, mask_kind="tanh")
+    _close_bf16(srk_ops.fpa_to_nhwc(dx2).cpu().numpy(), gx * (1 - saved.astype(np.float64) ** 2), rel=2.0 ** -6)
+    # relu(x + conv1x1(t) + b)
+    w1 = _bf(r.standard_normal((1, 1, 64, 64)) / 8.0)
+    b1 = (r.standard_normal(64) * 0.1).astype(np.float32)
+    y = srk_ops.conv_tc(dyf, srk_ops.pack_conv_weights(_dev(w1)), _dev(b1), 1, None, addend=sf, relu_after_add=True)
+    ref = np.maximum(O.conv2d_nhwc(dy, w1, b1, "SAME", None) + saved, 0)
+    _close_bf16(srk_ops.fpa_to_nhwc(y).cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("cin,cout,r,shape,act", [
+    (64, 3, 1, (2, 13, 15), None),
+    (64, 1, 1, (1, 9, 140), None),
+    (32, 27, 3, (2, 10, 12), None),
+    (32, 9, 3, (1, 24, 31), None),
+    (32, 12, 2, (1, 8, 8), None),
+])
+def test_conv_tc_last(srk_ops, cin, cout, r, shape, act):
+    n, h, w = shape
+    g = _rng(cin + cout + r)
+    x = _bf(g.uniform(-1, 1, (n, h, w, cin)))
+    wt = _bf(g.standard_normal((3, 3, cin, cout)) / np.sqrt(9 * cin))
+    b = (g.standard_normal(cout) * 0.1).astype(np.float32)
+    c = cout // (r * r)
+    addend = g.uniform(-1, 1, (n, h * r, w * r, c)).astype(np.float32)
+    xf = srk_ops.fpa_from_nhwc(_dev(x))
+    wp = srk_ops.pack_conv_weights(_dev(wt))
+    bp = srk_ops.pad_bias(_dev(b), wp.shape[1])
+    out = srk_ops.conv_tc_last(xf, wp, bp, 3, cout, act, addend=_dev(addend), shuffle_r=r).cpu().numpy()
+    ref = O.pixel_shuffle(O.conv2d_nhwc(x, wt, b, "SAME", act), r) + addend
+    assert out.shape == ref.shape
+    np.testing.assert_allclose(out, ref, rtol=1e-4, atol=2e-5)
+
+
+def test_conv_tc_last_valid_5x5_via_panel_crop(srk_ops):
+    """SRCNN reconstruction: 5x5 VALID 32->3 tanh == SAME over the FPA, cropped by 2 px."""
+    g = _rng(55)
+    n, h, w = 2, 25, 25
+    x = _bf(g.uniform(0, 1, (n, h, w, 32)))
+    wt = _bf(g.standard_normal((5, 5, 32, 3)) / np.sqrt(25 * 32))
+    b = (g.standard_normal(3) * 0.1).astype(np.float32)
+    xf = srk_ops.fpa_from_nhwc(_dev(x))
+    wp = srk_ops.pack_conv_weights(_dev(wt))
+    panels = srk_ops.make_panels([(i, -2, -2, 2, h - 2, 2, w - 2) for i in range(n)])
+    out = srk_ops.conv_tc_last(xf, wp, srk_ops.pad_bias(_dev(b), 16), 5, 3, "tanh", panels=panels,
+                               frame_shape=(n, h - 4, w - 4)).cpu().numpy()
+    ref = O.conv2d_nhwc(x, wt, b, "VALID", "tanh")
+    np.testing.assert_allclose(out, ref, rtol=2e-3, atol=2e-3)  # tanh.approx
+
+
+@pytest.mark.parametrize("shape", [(2, 7, 9), (64, 41, 41), (1, 20, 200), (3, 33, 120)])
+def test_wgrad_tc(srk_ops, shape):
+    n, h, w = shape
+    g = _rng(h * w)
+    x = _bf(g.uniform(-1, 1, (n, h, w, 64)))
+    dy = _bf(g.standard_normal((n, h, w, 64)) * 0.1)
+    xf = srk_ops.fpa_from_nhwc(_dev(x))
+    dyf = srk_ops.fpa_from_nhwc(_dev(dy))
+    dw = torch.zeros((3, 3, 64, 64), device="cuda")
+    db = torch.zeros(64, device="cuda")
+    srk_ops.conv_wgrad_tc(xf, dyf, dw, db)
+    _, gw, gb = O.conv2d_backward(x, np.zeros((3, 3, 64, 64)), np.zeros(64), dy, "SAME", None)
+    scale = np.abs(gw).max()
+    np.testing.assert_allclose(dw.cpu().numpy(), gw, rtol=1e-3, atol=1e-4 * scale)
+    np.testing.assert_allclose(db.cpu().numpy(), gb, rtol=1e-3, atol=1e-4 * np.abs(gb).max())
+
+
+def test_first_and_last_layer_wgrad(srk_ops):
+    g = _rng(3)
+    n, h, w = 3, 11, 13
+    x = g.uniform(-1, 1, (n, h, w, 3)).astype(np.float32)
+    dy = _bf(g.standard_normal((n, h, w, 64)) * 0.1)
+    dw = torch.zeros((3, 3, 3, 64), device="cuda")
+    db = torch.zeros(64, device="cuda")
+    srk_ops.conv_first_wgrad(_dev(x), srk_ops.fpa_from_nhwc(_dev(dy)), 3, dw, db)
+    _, gw, gb = O.conv2d_backward(x, np.zeros((3, 3, 3, 64)), np.zeros(64), dy, "SAME", None)
+    np.testing.assert_allclose(dw.cpu().numpy(), gw, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(db.cpu().numpy(), gb, rtol=1e-4, atol=1e-5)
+    x2 = _bf(g.uniform(-1, 1, (n, h, w, 64)))
+    dy2 = (g.standard_normal((n, h, w, 3)) * 0.1).astype(np.float32)
+    dw2 = torch.zeros((3, 3, 64, 3), device="cuda")
+    db2 = torch.zeros(3, device="cuda")
+    srk_ops.conv_last_wgrad(srk_ops.fpa_from_nhwc(_dev(x2)), _dev(dy2), dw2, db2)
+    _, gw2, gb2 = O.conv2d_backward(x2, np.zeros((3, 3, 64, 3)), np.zeros(3), dy2, "SAME", None)
+    np.testing.assert_allclose(dw2.cpu().numpy(), gw2, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(db2.cpu().numpy(), gb2, rtol=1e-4, atol=1e-5)
