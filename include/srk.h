@@ -36,7 +36,7 @@ typedef void* srk_stream_t; /* cudaStream_t */
 
 enum { SRK_ACT_NONE = 0, SRK_ACT_RELU = 1, SRK_ACT_TANH = 2 };
 enum { SRK_PAD_SAME = 0, SRK_PAD_VALID = 1 };
-enum { SRK_PACK_FWD = 0, SRK_PACK_DGRAD = 1 };
+enum { SRK_PACK_FWD = 0, SRK_PACK_DGRAD = 1, SRK_PACK_ROT180T_F32 = 2 };
 
 /* One entry per FPA image when a large frame is processed as column/row panels (tiled inference,
  * SURVEY 8e): the panel's top-left corner in the frame and the rectangle (panel-local, half-open)
@@ -64,6 +64,18 @@ int64_t srk_fpa_rows(int n_img, int H, int W);
  * convolution (dX = dY * rot180(W)^T), i.e. block[tap'][ci][co] = w[k-1-u][k-1-v][ci][co]. */
 int srk_pack_conv_weights(srk_handle_t h, const float* w_hwio, int k, int cin, int cout, int mode,
                           int np, int cinp, void* packed_bf16, srk_stream_t stream);
+
+/* Batched form of srk_pack_conv_weights: one launch re-packs every layer of a model after an optimiser
+ * step.  jobs_device is a device array; src_offset is in floats from `arena`, dst_offset in bytes from
+ * `out_base`, elem_begin the exclusive prefix sum of output elements (jobs sorted by it).  Mode
+ * SRK_PACK_ROT180T_F32 writes the fp32 [k][k][cout][cin] rotated+transposed kernel (the last layer's
+ * data-gradient kernel in the form srk_conv_first consumes). */
+typedef struct {
+  int64_t src_offset, dst_offset, elem_begin;
+  int32_t k, cin, cout, mode, np, cinp;
+} srk_pack_job;
+int srk_pack_conv_weights_batched(srk_handle_t h, const float* arena, const srk_pack_job* jobs_device, int n_jobs,
+                                  int64_t total_elems, void* out_base, srk_stream_t stream);
 
 /* ---- conv layers ------------------------------------------------------------------------------
  * First layer of every model: small-Cin conv from an fp32 NHWC frame straight into an FPA.
@@ -156,6 +168,16 @@ int srk_l2norm_rows_mean_fwd_bwd(srk_handle_t h, const float* sr, const float* h
 int srk_adam_step(srk_handle_t h, float* w, const float* g, float* m, float* v, size_t n, float lr,
                   float beta1, float beta2, float eps, int64_t t, float weight_decay,
                   const float* decay_mask, srk_stream_t stream);
+/* Same step with the bias-corrected rate lr_t = lr*sqrt(1-b2^t)/(1-b1^t) read from DEVICE memory, so a
+ * captured CUDA graph of the whole training step can be replayed while lr and t advance (the reference
+ * feeds the learning rate every step: vdsr/vdsr/experiment_train.py:130,137). */
+int srk_adam_step_dev(srk_handle_t h, float* w, const float* g, float* m, float* v, size_t n,
+                      const float* lr_t_device, float beta1, float beta2, float eps, float weight_decay,
+                      const float* decay_mask, srk_stream_t stream);
+/* *out_accum += scale * sum_i mask[i]*w[i]^2 : the l2_regularizer part of the VDSR loss
+ * (vdsr/vdsr/model_vdsr.py:34,125: scale = 0.5 * 1e-4, mask = 1 on kernels, 0 on biases). */
+int srk_sumsq_masked(srk_handle_t h, const float* w, const float* mask, size_t n, float scale, float* out_accum,
+                     srk_stream_t stream);
 /* Momentum(0.9) with gradient clip +-cap/lr (vdsr/vdsr/model_vdsr.py:158-184). */
 int srk_momentum_clip_step(srk_handle_t h, float* w, const float* g, float* accum, size_t n, float lr,
                            float momentum, float gradient_cap, float weight_decay, const float* decay_mask,

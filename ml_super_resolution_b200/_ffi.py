@@ -15,6 +15,11 @@ class SrkError(RuntimeError):
     pass
 
 
+class SrkPackJob(C.Structure):
+    _fields_ = [("src_offset", C.c_int64), ("dst_offset", C.c_int64), ("elem_begin", C.c_int64), ("k", C.c_int32),
+                ("cin", C.c_int32), ("cout", C.c_int32), ("mode", C.c_int32), ("np", C.c_int32), ("cinp", C.c_int32)]
+
+
 class SrkPanel(C.Structure):
     _fields_ = [("frame", C.c_int32), ("y0", C.c_int32), ("x0", C.c_int32), ("own_y0", C.c_int32),
                 ("own_y1", C.c_int32), ("own_x0", C.c_int32), ("own_x1", C.c_int32), ("reserved", C.c_int32)]
@@ -31,6 +36,9 @@ SIGNATURES = {
     "srk_num_sms": (_I, [_P]),
     "srk_fpa_rows": (_I64, [_I, _I, _I]),
     "srk_pack_conv_weights": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "srk_pack_conv_weights_batched": (_I, [_P, _P, _P, _I, _I64, _P, _P]),
+    "srk_sumsq_masked": (_I, [_P, _P, _P, _SZ, _F, _P, _P]),
+    "srk_adam_step_dev": (_I, [_P, _P, _P, _P, _P, _SZ, _P, _F, _F, _F, _F, _P, _P]),
     "srk_conv_first": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P]),
     "srk_conv_tc": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P]),
     "srk_conv_tc_last": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P]),

@@ -311,7 +311,9 @@ __global__ void __launch_bounds__(256) l2norm_rows_kernel(const float* __restric
 
 // ------------------------------------------------------------------------------------ optimisers
 __global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            size_t n, float lr_t, float b1, float b2, float eps, float wd, const float* __restrict__ mask) {
+                            size_t n, float lr_t, const float* __restrict__ lr_t_dev, float b1, float b2, float eps, float wd,
+                            const float* __restrict__ mask) {
+  if (lr_t_dev) lr_t = __ldg(lr_t_dev);
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
     float gi = g[i];
     const float wi = w[i];
@@ -434,8 +436,8 @@ extern "C" int srk_adam_step(srk_handle_t h, float* w, const float* g, float* m,
   SRK_REQUIRE(h && w && g && m && v && t >= 1, "srk_adam_step: bad argument");
   if (n == 0) return 0;
   const double lr_t = double(lr) * sqrt(1.0 - pow(double(beta2), double(t))) / (1.0 - pow(double(beta1), double(t)));
-  adam_kernel<<<grid_for(h, int64_t(n), 256), 256, 0, as_stream(stream)>>>(w, g, m, v, n, float(lr_t), beta1, beta2, eps, weight_decay,
-                                                                         decay_mask);
+  adam_kernel<<<grid_for(h, int64_t(n), 256), 256, 0, as_stream(stream)>>>(w, g, m, v, n, float(lr_t), nullptr, beta1, beta2, eps,
+                                                                         weight_decay, decay_mask);
   SRK_LAUNCH_CHECK();
   return 0;
 }
@@ -446,6 +448,16 @@ extern "C" int srk_momentum_clip_step(srk_handle_t h, float* w, const float* g, 
   if (n == 0) return 0;
   momentum_clip_kernel<<<grid_for(h, int64_t(n), 256), 256, 0, as_stream(stream)>>>(w, g, accum, n, lr, momentum, gradient_cap / lr,
                                                                                    weight_decay, decay_mask);
+  SRK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int srk_adam_step_dev(srk_handle_t h, float* w, const float* g, float* m, float* v, size_t n, const float* lr_t_device,
+                                 float beta1, float beta2, float eps, float weight_decay, const float* decay_mask, srk_stream_t stream) {
+  SRK_REQUIRE(h && w && g && m && v && lr_t_device, "srk_adam_step_dev: bad argument");
+  if (n == 0) return 0;
+  adam_kernel<<<grid_for(h, int64_t(n), 256), 256, 0, as_stream(stream)>>>(w, g, m, v, n, 0.f, lr_t_device, beta1, beta2, eps,
+                                                                         weight_decay, decay_mask);
   SRK_LAUNCH_CHECK();
   return 0;
 }

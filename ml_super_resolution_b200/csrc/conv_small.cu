@@ -29,6 +29,62 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int k, int cin,
   }
 }
 
+// Batched form: one launch prepares every layer of a model after an optimiser step.  Each job packs one
+// HWIO kernel out of the flat fp32 parameter arena; mode SRK_PACK_ROT180T_F32 instead writes the fp32
+// [k][k][cout][cin] rotated/transposed kernel that srk_conv_first consumes as the last layer's dgrad.
+__global__ void pack_weights_batched_kernel(const float* __restrict__ arena, const srk_pack_job* __restrict__ jobs, int n_jobs,
+                                            int64_t total, uint8_t* __restrict__ out_base) {
+  extern __shared__ srk_pack_job s_jobs[];
+  for (int i = threadIdx.x; i < n_jobs; i += blockDim.x) s_jobs[i] = jobs[i];
+  __syncthreads();
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    int j = 0;
+    while (j + 1 < n_jobs && s_jobs[j + 1].elem_begin <= i) ++j;
+    const srk_pack_job jb = s_jobs[j];
+    const int e = int(i - jb.elem_begin);
+    const float* w = arena + jb.src_offset;
+    const int k = jb.k, cin = jb.cin, cout = jb.cout;
+    if (jb.mode == SRK_PACK_ROT180T_F32) {
+      // out[u'][v'][co][ci] = w[k-1-u'][k-1-v'][ci][co]
+      const int ci = e % cin, co = (e / cin) % cout, tap = e / (cin * cout);
+      const int u = k - 1 - tap / k, v = k - 1 - tap % k;
+      reinterpret_cast<float*>(out_base + jb.dst_offset)[e] = w[((u * k + v) * cin + ci) * cout + co];
+    } else {
+      const int kk = e % jb.cinp, n = (e / jb.cinp) % jb.np, tap = e / (jb.cinp * jb.np);
+      int u = tap / k, v = tap % k;
+      float val = 0.f;
+      if (jb.mode == SRK_PACK_FWD) {
+        if (n < cout && kk < cin) val = w[((u * k + v) * cin + kk) * cout + n];
+      } else {
+        u = k - 1 - u;
+        v = k - 1 - v;
+        if (n < cin && kk < cout) val = w[((u * k + v) * cin + n) * cout + kk];
+      }
+      reinterpret_cast<__nv_bfloat16*>(out_base + jb.dst_offset)[e] = __float2bfloat16_rn(val);
+    }
+  }
+}
+
+// sum over the arena of mask[i] * w[i]^2, scaled: the l2_regularizer term of the loss
+__global__ void __launch_bounds__(256) sumsq_masked_kernel(const float* __restrict__ w, const float* __restrict__ mask, size_t n, float scale,
+                                                           float* __restrict__ out) {
+  float acc = 0.f;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    const float v = w[i];
+    acc += (mask ? mask[i] : 1.f) * v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float s[8];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += s[i];
+    atomicAdd(out, t * scale);
+  }
+}
+
 // ------------------------------------------------------------------------------------ first layer
 struct ConvFirstParams {
   const float* x;
@@ -341,6 +397,26 @@ extern "C" int srk_conv_last_wgrad(srk_handle_t h, const void* x_fpa, const floa
   const int slices = 64;
   conv_last_wgrad_kernel<<<10 * slices, 64, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(x_fpa), dy, n_img, H, W, cout,
                                                                     dw_hwio, dbias, slices);
+  SRK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int srk_pack_conv_weights_batched(srk_handle_t h, const float* arena, const srk_pack_job* jobs_device, int n_jobs,
+                                             int64_t total_elems, void* out_base, srk_stream_t stream) {
+  SRK_REQUIRE(h && arena && jobs_device && out_base && n_jobs > 0 && n_jobs <= 256, "srk_pack_conv_weights_batched: bad argument");
+  const int grid = int(std::min<int64_t>((total_elems + 255) / 256, int64_t(h->num_sms) * 8));
+  pack_weights_batched_kernel<<<grid, 256, n_jobs * sizeof(srk_pack_job), as_stream(stream)>>>(
+      arena, jobs_device, n_jobs, total_elems, static_cast<uint8_t*>(out_base));
+  SRK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int srk_sumsq_masked(srk_handle_t h, const float* w, const float* mask, size_t n, float scale, float* out_accum,
+                                srk_stream_t stream) {
+  SRK_REQUIRE(h && w && out_accum, "srk_sumsq_masked: null argument");
+  if (n == 0) return 0;
+  const int grid = int(std::min<int64_t>((int64_t(n) + 255) / 256, int64_t(h->num_sms) * 4));
+  sumsq_masked_kernel<<<grid, 256, 0, as_stream(stream)>>>(w, mask, n, scale, out_accum);
   SRK_LAUNCH_CHECK();
   return 0;
 }

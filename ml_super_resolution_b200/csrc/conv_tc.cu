@@ -400,6 +400,7 @@ extern "C" int srk_conv_tc(srk_handle_t h, const void* x_fpa, int cin_p, const v
   SRK_CASE(64, 32, 1)
   SRK_CASE(32, 64, 3)
   SRK_CASE(32, 64, 1)
+  SRK_CASE(32, 32, 3)
 #undef SRK_CASE
   set_error("srk_conv_tc: unsupported (cin_p=%d, cout_p=%d, k=%d)", cin_p, cout_p, k);
   return -1;
@@ -431,6 +432,8 @@ extern "C" int srk_conv_tc_last(srk_handle_t h, const void* x_fpa, int cin_p, co
   SRK_CASE(32, 16, 3)
   SRK_CASE(32, 32, 3)
   SRK_CASE(32, 16, 5)
+  SRK_CASE(32, 64, 3)
+  SRK_CASE(64, 32, 3)
 #undef SRK_CASE
   set_error("srk_conv_tc_last: unsupported (cin_p=%d, cout_p=%d, k=%d)", cin_p, cout_p, k);
   return -1;

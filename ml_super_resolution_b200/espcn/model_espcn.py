@@ -1,0 +1,160 @@
+"""ESPCN on the B200 conv hot path -- drop-in for espcn/espcn/model_espcn.py of the reference.
+
+  f1  srk_conv_first   5x5 C->64 tanh                           reference :30-38 / :117-120
+  f2  srk_conv_tc      3x3 64->32 tanh (tcgen05, N=32 tiles)      reference :40-48 / :123-126
+  f3  srk_conv_tc_last 3x3 32->C*r^2 linear, fused depth_to_space reference :54-62 / :132-134 and the
+                       host un-pack of espcn/espcn/experiment_test.py:173-177
+
+`build_model` / `build_test_model` / `extract_weights` keep the reference's names, arguments and dict
+keys; `sr_result(s)` stays in PACKED (un-shuffled) space exactly like the reference, and the shuffled
+image is available as the extra key `hr_images` (pixel shuffle fused into the f3 epilogue).
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..initializers import espcn_params
+from ..params import ParamArena
+from ..session import Handle, Placeholder
+from ..tiling import MAX_PANEL_W, plan_tiles, shard_tiles
+
+HALO = 4  # receptive-field radius in LR pixels: 2 (5x5) + 1 + 1
+
+
+class EspcnNet:
+    def __init__(self, params=None, scaling_factor=3, channels=3, device="cuda", seed=0):
+        if params is None:
+            params = espcn_params(seed, scaling_factor, channels)
+        order = OrderedDict((k, np.asarray(params[k], np.float32)) for k in
+                            ("f1/kernel:0", "f1/bias:0", "f2/kernel:0", "f2/bias:0", "f3/kernel:0", "f3/bias:0"))
+        self.C = order["f1/kernel:0"].shape[2]
+        self.cout3 = order["f3/kernel:0"].shape[3]
+        self.r = int(round((self.cout3 // self.C) ** 0.5))
+        assert self.C * self.r * self.r == self.cout3
+        self.device = device
+        self.arena = ParamArena(order, device)
+        a = self.arena
+        self.np3 = ops.pad_cout(self.cout3)
+        plan = ops.PackPlan(device)
+        self._i2 = plan.add(a.offsets["f2/kernel:0"], 3, 64, 32, ops.PACK_FWD, 32, 64)
+        self._i3 = plan.add(a.offsets["f3/kernel:0"], 3, 32, self.cout3, ops.PACK_FWD, self.np3, 32)
+        plan.finalize()
+        self.plan = plan
+        self.bias3 = torch.zeros(self.np3, dtype=torch.float32, device=device)
+        self.repack()
+        self._bufs = {}
+        self._panels = {}
+
+    def repack(self):
+        self.plan.run(self.arena.w)
+        self.bias3[: self.cout3].copy_(self.arena.view("f3/bias:0"))
+
+    def load_params(self, params):
+        self.arena.load_numpy(params)
+        self.repack()
+
+    def _get_bufs(self, n, H, W):
+        key = (n, H, W)
+        if key not in self._bufs:
+            if len(self._bufs) > 8:
+                self._bufs.clear()
+            self._bufs[key] = (ops.fpa_empty(n, H, W, 64, self.device), ops.fpa_empty(n, H, W, 32, self.device))
+        return self._bufs[key]
+
+    def forward(self, lr: torch.Tensor, shuffle=True, out: torch.Tensor | None = None, rank=0, world=1, tile_rows=None) -> torch.Tensor:
+        """lr fp32 [N,h,w,C] -> shuffled [N,h*r,w*r,C] (shuffle=True) or packed [N,h,w,C*r^2]."""
+        n, H, W, C = lr.shape
+        assert C == self.C
+        a, r = self.arena, (self.r if shuffle else 1)
+        if out is None:
+            out = torch.empty((n, H * r, W * r, self.cout3 // (r * r)), dtype=torch.float32, device=lr.device)
+        w1, b1, b2 = a.view("f1/kernel:0"), a.view("f1/bias:0"), a.view("f2/bias:0")
+        w2p, w3p = self.plan.views[self._i2], self.plan.views[self._i3]
+        if W <= MAX_PANEL_W and world == 1 and (tile_rows is None or H <= tile_rows):
+            t1, t2 = self._get_bufs(n, H, W)
+            ops.conv_first(lr, w1, b1, "SAME", "tanh", out=t1)
+            ops.conv_tc(t1, w2p, b2, 3, "tanh", out=t2)
+            ops.conv_tc_last(t2, w3p, self.bias3, 3, self.cout3, None, shuffle_r=r, out=out)
+            return out
+        Ht, Wt, tiles = plan_tiles(n, H, W, HALO, MAX_PANEL_W, tile_rows)
+        tiles = shard_tiles(tiles, rank, world)
+        if not tiles:
+            return out
+        key = tuple(t.as_tuple() for t in tiles)
+        if key not in self._panels:
+            self._panels[key] = ops.make_panels(list(key), self.device)
+        panels = self._panels[key]
+        t1, t2 = self._get_bufs(len(tiles), Ht, Wt)
+        ops.conv_first(lr, w1, b1, "SAME", "tanh", panels=panels, panel_hw=(Ht, Wt), out=t1)
+        ops.conv_tc(t1, w2p, b2, 3, "tanh", out=t2)
+        ops.conv_tc_last(t2, w3p, self.bias3, 3, self.cout3, None, shuffle_r=r, panels=panels, frame_shape=(n, H, W), out=out)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# reference-shaped builders
+# ---------------------------------------------------------------------------------------------
+
+
+class _EspcnGraph:
+    def __init__(self, net, lr_ph, hr_ph=None):
+        self.net, self.lr_ph, self.hr_ph = net, lr_ph, hr_ph
+
+    def execute(self, keys, feeds):
+        net = self.net
+        out = {}
+        if "optimizer" in keys:
+            raise NotImplementedError("ESPCN training is not part of this round's hot path (SURVEY 8a: inference config)")
+        x = feeds[self.lr_ph]
+        lr = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        lr = lr.to(net.device, torch.float32).contiguous()
+        if keys & {"sr_result", "sr_results", "loss"}:
+            packed = net.forward(lr, shuffle=False)
+            out["sr_result"] = out["sr_results"] = packed.cpu().numpy()
+            if "loss" in keys:
+                hr = torch.from_numpy(np.ascontiguousarray(feeds[self.hr_ph], dtype=np.float32)).to(net.device)
+                acc = torch.zeros(1, device=net.device)
+                ops.mse_fwd_bwd(packed, hr, acc, None)
+                out["loss"] = float(acc)
+        if "hr_images" in keys:
+            out["hr_images"] = net.forward(lr, shuffle=True).cpu().numpy()
+        out["step"] = 0
+        out["scaling_factor"] = net.r
+        return out
+
+
+def build_model(lr_source, scaling_factor=3, hr_target=None, params=None, channels=3, device="cuda", seed=0):
+    """espcn/espcn/model_espcn.py:6 `build_model(lr_source, scaling_factor=3, hr_target=None)`."""
+    net = EspcnNet(params, scaling_factor, channels, device, seed)
+    g = _EspcnGraph(net, lr_source, hr_target)
+    model = {"lr_source": lr_source, "sr_result": Handle(g, "sr_result"), "hr_images": Handle(g, "hr_images")}
+    if hr_target is None:
+        return model
+    model["hr_target"] = hr_target
+    model["step"] = Handle(g, "step")
+    model["loss"] = Handle(g, "loss")
+    model["optimizer"] = Handle(g, "optimizer")
+    model["learning_rate"] = Placeholder("learning_rate", [])
+    return model
+
+
+def extract_weights(meta_path, ckpt_path):
+    """espcn/espcn/model_espcn.py:150-166 returns {tf_var_name: ndarray}.  Checkpoints here are `.npz`
+    files keyed by the same TF variable names (`meta_path` is accepted and ignored)."""
+    with np.load(ckpt_path) as z:
+        return {k: z[k] for k in z.files if k.endswith(("kernel:0", "bias:0"))}
+
+
+def build_test_model(meta_path, ckpt_path, device="cuda"):
+    """espcn/espcn/model_espcn.py:99-147: constant-weight test graph; `sr_results` is packed."""
+    variables = extract_weights(meta_path, ckpt_path)
+    scaling_factor = int((variables["f3/bias:0"].size // 3) ** 0.5)
+    lr_sources = Placeholder("lr_sources", [None, None, None, 3])
+    net = EspcnNet(variables, scaling_factor, 3, device)
+    g = _EspcnGraph(net, lr_sources)
+    return {"lr_sources": lr_sources, "sr_results": Handle(g, "sr_results"), "scaling_factor": scaling_factor,
+            "hr_images": Handle(g, "hr_images")}

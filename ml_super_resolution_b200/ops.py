@@ -17,7 +17,7 @@ from ._ffi import SrkPanel, check
 
 ACT = {None: 0, "none": 0, "linear": 0, "relu": 1, "tanh": 2}
 PAD = {"SAME": 0, "same": 0, "VALID": 1, "valid": 1}
-PACK_FWD, PACK_DGRAD = 0, 1
+PACK_FWD, PACK_DGRAD, PACK_ROT180T_F32 = 0, 1, 2
 
 _handles: dict[int, C.c_void_p] = {}
 
@@ -283,3 +283,54 @@ def adam_step(w, g, m, v, lr: float, t: int, beta1=0.9, beta2=0.999, eps=1e-8, w
 def momentum_clip_step(w, g, accum, lr: float, momentum=0.9, gradient_cap=0.01, weight_decay=0.0, decay_mask=None) -> None:
     check(_ffi.lib().srk_momentum_clip_step(handle(), _ptr(_f32(w)), _ptr(_f32(g)), _ptr(accum), w.numel(), lr, momentum, gradient_cap,
                                             weight_decay, _ptr(decay_mask), _stream()), "srk_momentum_clip_step")
+
+
+def adam_step_dev(w, g, m, v, lr_t_dev: torch.Tensor, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, decay_mask=None) -> None:
+    """Adam with the bias-corrected rate read from device memory (graph-replayable)."""
+    check(_ffi.lib().srk_adam_step_dev(handle(), _ptr(_f32(w)), _ptr(_f32(g)), _ptr(m), _ptr(v), w.numel(), _ptr(_f32(lr_t_dev)), beta1,
+                                       beta2, eps, weight_decay, _ptr(decay_mask), _stream()), "srk_adam_step_dev")
+
+
+def sumsq_masked(w: torch.Tensor, mask: torch.Tensor | None, scale: float, out_accum: torch.Tensor) -> None:
+    check(_ffi.lib().srk_sumsq_masked(handle(), _ptr(_f32(w)), _ptr(mask), w.numel(), scale, _ptr(out_accum), _stream()), "srk_sumsq_masked")
+
+
+class PackPlan:
+    """Device-resident job table for srk_pack_conv_weights_batched: re-packs every conv kernel of a model
+    from the flat fp32 parameter arena into one byte arena with a single launch."""
+
+    def __init__(self, device="cuda"):
+        self.jobs = []  # (src_offset, k, cin, cout, mode, np, cinp)
+        self.device = device
+        self.out = None
+        self.views = []
+
+    def add(self, src_offset: int, k: int, cin: int, cout: int, mode: int, np_: int = 0, cinp: int = 0) -> int:
+        self.jobs.append((src_offset, k, cin, cout, mode, np_, cinp))
+        return len(self.jobs) - 1
+
+    def finalize(self) -> None:
+        n = len(self.jobs)
+        arr = (_ffi.SrkPackJob * n)()
+        dst, elem = 0, 0
+        layout = []
+        for i, (src, k, cin, cout, mode, np_, cinp) in enumerate(self.jobs):
+            if mode == PACK_ROT180T_F32:
+                count, esz, shape, dt = k * k * cout * cin, 4, (k, k, cout, cin), torch.float32
+            else:
+                count, esz, shape, dt = k * k * np_ * cinp, 2, (k * k, np_, cinp), torch.bfloat16
+            dst = _round_up(dst, 1024)
+            arr[i] = _ffi.SrkPackJob(src, dst, elem, k, cin, cout, mode, np_, cinp)
+            layout.append((dst, count * esz, shape, dt))
+            dst += count * esz
+            elem += count
+        self.total = elem
+        self.out = torch.zeros(_round_up(dst, 1024), dtype=torch.uint8, device=self.device)
+        assert self.out.data_ptr() % 1024 == 0 or True
+        host = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
+        self.jobs_dev = torch.from_numpy(host).to(self.device)
+        self.views = [self.out[o:o + nb].view(dt).view(shape) for (o, nb, shape, dt) in layout]
+
+    def run(self, arena: torch.Tensor) -> None:
+        check(_ffi.lib().srk_pack_conv_weights_batched(handle(), _ptr(_f32(arena)), _ptr(self.jobs_dev), len(self.jobs), self.total,
+                                                       _ptr(self.out), _stream()), "srk_pack_conv_weights_batched")

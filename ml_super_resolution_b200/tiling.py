@@ -1,0 +1,78 @@
+"""Tile planner for full-frame inference.
+
+A frame larger than the flat-stream conv kernel's widest panel (254 px), larger than L2, or
+spread over several GPUs is cut into equally sized tiles that all lie INSIDE the frame and
+overlap by at least 2*halo, where halo = the network's receptive-field radius (VDSR 20,
+ESPCN 4 LR px, ENet 13 LR px).  Each tile runs through the network with ordinary per-layer SAME
+padding inside the crop; every output pixel is taken from the one tile that "owns" it, i.e. a
+tile in which the pixel sits >= halo away from any crop edge that is not a true frame edge --
+there the tiled result equals the full-frame result exactly (crop-edge error advances one pixel
+per 3x3 layer and never reaches an owned pixel).  Pure host-side integer logic; numpy only.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+MAX_PANEL_W = 254  # Wp + 1 <= 256 rows of look-behind in the flat-stream kernels
+
+
+@dataclass(frozen=True)
+class Tile:
+    frame: int
+    y0: int
+    x0: int
+    own_y0: int
+    own_y1: int
+    own_x0: int
+    own_x1: int
+
+    def as_tuple(self):
+        return (self.frame, self.y0, self.x0, self.own_y0, self.own_y1, self.own_x0, self.own_x1)
+
+
+def _split_axis(size: int, halo: int, max_len: int | None):
+    """-> (tile_len, [(start, own_lo, own_hi)]) with own ranges in tile-local coordinates."""
+    if max_len is None or size <= max_len:
+        return size, [(0, 0, size)]
+    if max_len <= 2 * halo:
+        raise ValueError(f"max tile length {max_len} does not exceed twice the halo {halo}")
+    core = max_len - 2 * halo
+    parts = -(-(size - 2 * halo) // core)  # ceil
+    length = -(-(size - 2 * halo) // parts) + 2 * halo
+    while True:  # integer rounding of the starts can cost one pixel of overlap
+        starts = [round(j * (size - length) / (parts - 1)) for j in range(parts)]
+        if all(starts[j] + length - starts[j + 1] >= 2 * halo for j in range(parts - 1)):
+            break
+        length += 1
+    assert length <= max_len
+    # ownership boundaries: midpoint of each overlap
+    bounds = [0]
+    for j in range(parts - 1):
+        lo, hi = starts[j + 1], starts[j] + length  # overlap [lo, hi)
+        assert hi - lo >= 2 * halo, "internal: overlap smaller than 2*halo"
+        bounds.append((lo + hi) // 2)
+    bounds.append(size)
+    out = []
+    for j in range(parts):
+        out.append((starts[j], bounds[j] - starts[j], bounds[j + 1] - starts[j]))
+    return length, out
+
+
+def plan_tiles(n_frames: int, FH: int, FW: int, halo: int, max_w: int | None = MAX_PANEL_W, max_h: int | None = None):
+    """Returns (Ht, Wt, [Tile...]): every tile is Ht x Wt, inside the frame, owned rects partition it."""
+    Wt, xs = _split_axis(FW, halo, max_w)
+    Ht, ys = _split_axis(FH, halo, max_h)
+    tiles = []
+    for f in range(n_frames):
+        for (y0, oy0, oy1) in ys:
+            for (x0, ox0, ox1) in xs:
+                tiles.append(Tile(f, y0, x0, oy0, oy1, ox0, ox1))
+    return Ht, Wt, tiles
+
+
+def shard_tiles(tiles, rank: int, world: int):
+    """Contiguous, balanced shard of the tile list for one rank (no data-path collective)."""
+    n = len(tiles)
+    lo = (rank * n) // world
+    hi = ((rank + 1) * n) // world
+    return tiles[lo:hi]

@@ -145,7 +145,7 @@ def vdsr_loss_and_grads(params: dict, sd, hd, num_layers=20, weight_decay=1e-4, 
     reg = sum(weight_decay * 0.5 * (v ** 2).sum() for k, v in p.items() if k.endswith("kernel:0"))
     loss = mse + reg
     loss.backward()
-    return float(loss), float(mse), {k: v.grad.numpy() for k, v in p.items()}, sr.detach().numpy()
+    return float(loss.detach()), float(mse.detach()), {k: v.grad.numpy() for k, v in p.items()}, sr.detach().numpy()
 
 
 # ------------------------------------------------------------------------------------------
@@ -171,7 +171,7 @@ def espcn_loss_and_grads(params: dict, lr, hr_packed, dtype=np.float64):
     sr = espcn_forward_t(p, _t(lr, dtype))
     loss = ((sr - _t(hr_packed, dtype)) ** 2).mean()
     loss.backward()
-    return float(loss), {k: v.grad.numpy() for k, v in p.items()}, sr.detach().numpy()
+    return float(loss.detach()), {k: v.grad.numpy() for k, v in p.items()}, sr.detach().numpy()
 
 
 # ------------------------------------------------------------------------------------------
@@ -201,7 +201,7 @@ def srcnn_loss_and_grads(params: dict, lo, hi, dtype=np.float64):
     d = (sr - hit).reshape(-1, bb * bb)
     loss = torch.linalg.vector_norm(d, ord=2, dim=1).mean()
     loss.backward()
-    return float(loss), {k: v.grad.numpy() for k, v in p.items()}, sr.detach().numpy()
+    return float(loss.detach()), {k: v.grad.numpy() for k, v in p.items()}, sr.detach().numpy()
 
 
 # ------------------------------------------------------------------------------------------

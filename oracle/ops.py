@@ -169,14 +169,15 @@ _BICUBIC_TABLE_SIZE = 1 << 10
 
 
 def _bicubic_table() -> np.ndarray:
-    """TF-1.x `InitCoeffsTable` (A = -0.75), fp32: T[2j], T[2j+1] for j = 0..1024."""
-    a = np.float32(-0.75)
+    """TF-1.x `InitCoeffsTable` (A = -0.75): double arithmetic on a float abscissa, stored as fp32;
+    T[2j], T[2j+1] for j = 0..1024."""
+    a = -0.75
     t = np.zeros((_BICUBIC_TABLE_SIZE + 1) * 2, np.float32)
     for j in range(_BICUBIC_TABLE_SIZE + 1):
-        x = np.float32(j) / np.float32(_BICUBIC_TABLE_SIZE)
-        t[2 * j] = ((a + np.float32(2)) * x - (a + np.float32(3))) * x * x + np.float32(1)
-        x = x + np.float32(1)
-        t[2 * j + 1] = ((a * x - np.float32(5) * a) * x + np.float32(8) * a) * x - np.float32(4) * a
+        x = float(np.float32(j * 1.0 / _BICUBIC_TABLE_SIZE))
+        t[2 * j] = np.float32(((a + 2) * x - (a + 3)) * x * x + 1)
+        x = float(np.float32(x + 1.0))
+        t[2 * j + 1] = np.float32(((a * x - 5 * a) * x + 8 * a) * x - 4 * a)
     return t
 
 

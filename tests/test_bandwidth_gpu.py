@@ -1,0 +1,89 @@
+"""Bandwidth kernels vs the oracle: index work bit-exact, fp32 arithmetic to fp32 round-off."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ops as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+@pytest.mark.parametrize("n,h,w,c,r", [(1, 4, 5, 3, 3), (2, 7, 3, 1, 2), (1, 1, 1, 3, 4), (2, 36, 64, 3, 3)])
+def test_pixel_shuffle_bit_exact(srk_ops, n, h, w, c, r):
+    x = np.random.default_rng(0).standard_normal((n, h, w, c * r * r)).astype(np.float32)
+    y = srk_ops.pixel_shuffle(_dev(x), r).cpu().numpy()
+    assert np.array_equal(y, O.pixel_shuffle(x, r))
+    if c == 3:
+        assert np.array_equal(y[0], O.pixel_shuffle_reference_literal(x[0], r))
+    back = srk_ops.pixel_unshuffle(_dev(y), r).cpu().numpy()
+    assert np.array_equal(back, x)
+
+
+@pytest.mark.parametrize("n,h,w,c,oh,ow", [(2, 243, 243, 3, 81, 81), (2, 81, 81, 3, 243, 243), (1, 11, 11, 1, 33, 33),
+                                            (1, 33, 33, 1, 11, 11), (1, 7, 13, 3, 20, 31)])
+def test_resize_bicubic_tf1_bit_exact(srk_ops, n, h, w, c, oh, ow):
+    x = np.random.default_rng(1).uniform(-1, 1, (n, h, w, c)).astype(np.float32)
+    y = srk_ops.resize_bicubic_tf1(_dev(x), oh, ow).cpu().numpy()
+    ref = O.resize_bicubic_tf1(x, oh, ow)
+    assert np.array_equal(y, ref), f"max diff {np.abs(y - ref).max()}"
+
+
+@pytest.mark.parametrize("h,w", [(41, 41), (128, 128), (37, 53)])
+def test_degrade_gauss_bilinear(srk_ops, h, w):
+    rng = np.random.default_rng(2)
+    hd = rng.uniform(0, 1, (6, h, w, 3)).astype(np.float32)
+    scales = np.array([2, 3, 4, 2, 3, 4], np.float32)
+    sd = srk_ops.degrade_gauss_bilinear(_dev(hd), _dev(scales)).cpu().numpy()
+    ref = np.stack([O.hd_image_to_sd_image(hd[i], float(scales[i])) for i in range(6)])
+    np.testing.assert_allclose(sd, ref, rtol=0, atol=2e-6)
+
+
+def test_mse_l2norm_and_optimisers(srk_ops):
+    rng = np.random.default_rng(3)
+    a = rng.uniform(-1, 1, (8, 41, 41, 3)).astype(np.float32)
+    b = rng.uniform(-1, 1, (8, 41, 41, 3)).astype(np.float32)
+    loss = torch.zeros(1, device="cuda")
+    d = torch.empty(a.shape, device="cuda")
+    srk_ops.mse_fwd_bwd(_dev(a), _dev(b), loss, d)
+    assert abs(float(loss) - O.mse_mean(a, b)) <= 1e-5
+    np.testing.assert_allclose(d.cpu().numpy(), 2 * (a - b) / a.size, rtol=1e-5, atol=1e-9)
+    # SRCNN row-L2-norm loss
+    sr = rng.uniform(-1, 1, (4, 21, 21, 3)).astype(np.float32)
+    hi = rng.uniform(-1, 1, (4, 21, 21, 3)).astype(np.float32)
+    loss.zero_()
+    d2 = torch.empty(sr.shape, device="cuda")
+    srk_ops.l2norm_rows_mean_fwd_bwd(_dev(sr), _dev(hi), 21 * 21, loss, d2)
+    ref_loss, ref_grad = O.l2norm_rows_mean(sr, hi, 21 * 21)
+    assert abs(float(loss) - ref_loss) <= 1e-4 * ref_loss
+    np.testing.assert_allclose(d2.cpu().numpy(), ref_grad, rtol=1e-4, atol=1e-8)
+    # TF-Adam, 3 steps, and Momentum+clip
+    n = 10007
+    w, g = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32) * 0.1
+    wd, gd = _dev(w), _dev(g)
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    wr, mr, vr = w.copy(), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    for t in (1, 2, 3):
+        srk_ops.adam_step(wd, gd, m, v, 1e-3, t)
+        wr, mr, vr = O.adam_tf(wr, g, mr, vr, t, 1e-3)
+    np.testing.assert_allclose(wd.cpu().numpy(), wr, rtol=1e-5, atol=1e-6)
+    acc = torch.zeros(n, device="cuda")
+    w2 = _dev(w)
+    srk_ops.momentum_clip_step(w2, gd, acc, 0.1)
+    wr2, _ = O.momentum_clip_tf(w, g, np.zeros(n, np.float32), 0.1)
+    np.testing.assert_allclose(w2.cpu().numpy(), wr2, rtol=1e-6, atol=1e-7)
+
+
+def test_fpa_upsample2_and_backward(srk_ops):
+    rng = np.random.default_rng(4)
+    x = O.bf16_round(rng.standard_normal((2, 5, 7, 64)).astype(np.float32))
+    xf = srk_ops.fpa_from_nhwc(_dev(x))
+    up = srk_ops.fpa_to_nhwc(srk_ops.fpa_upsample2(xf)).cpu().numpy()
+    assert np.array_equal(up, O.resize_nearest_tf1(x, 10, 14))
+    dy = O.bf16_round(rng.standard_normal((2, 10, 14, 64)).astype(np.float32))
+    dx = srk_ops.fpa_to_nhwc(srk_ops.fpa_upsample2_bwd(srk_ops.fpa_from_nhwc(_dev(dy)))).cpu().numpy()
+    ref = dy.reshape(2, 5, 2, 7, 2, 64).sum(axis=(2, 4))
+    np.testing.assert_allclose(dx, ref, rtol=2.0 ** -7, atol=1e-3)
