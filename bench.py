@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native super-resolution conv hot path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload espcn|vdsr_train|vdsr_infer] [--impl reference]
+
+Headline workload (BASELINE.json configs[1]): ESPCN 3x inference on synthetic 1920x1080 Y frames; metric
+"output Mpix/s".  One step = one batch of FRAMES_PER_STEP frames through f1 -> f2 -> f3(+pixel shuffle).
+`--workload vdsr_train` (configs[2]: VDSR-20 training, 64 patches of 41x41 per GPU, Adam, NCCL gradient
+all-reduce) and `--workload vdsr_infer` (configs[3]: VDSR 4K frame, tiles sharded over the GPUs) are the two
+other halves of BASELINE.json's metric; the default run appends their numbers under "also".
+Prints ONE JSON line on rank 0.  `--impl reference` times the CPU restatement of the reference graph
+(oracle/, torch-CPU fp32, all host threads) on the same workload instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAMES_PER_STEP = 4
+LR_H, LR_W, SCALE = 1080, 1920, 3
+VDSR_LAYERS = 20
+TRAIN_BATCH, TRAIN_PATCH = 64, 41
+FRAME_4K = (2160, 3840)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=float(d["hbm_gbs"]), tf_burst=float(d["bf16_tflops"]), tf_sust=float(d["bf16_tflops_sustained"]), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx, self.rows, self.proc = device_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def dist_info():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def timed_steps(step_fn, steps: int, warmup: int, world: int, sampler: ClockSampler | None):
+    """W warm-up steps, then exactly K steps between barrier+synchronize; device time via CUDA events on the
+    launching (current) stream; MAX over ranks."""
+    for _ in range(warmup):
+        step_fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step_fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t)
+    return ms, clocks
+
+
+def event_time(fn, iters=5):
+    """Average device time (ms) of one callable, CUDA events on the current stream, after one warm call."""
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def launches_of(fn) -> int:
+    from ml_super_resolution_b200 import _ffi
+    before = _ffi.launch_count
+    fn()
+    return _ffi.launch_count - before
+
+
+# ------------------------------------------------------------------------------------------------ ESPCN (headline)
+def espcn_workload(args, rank, world):
+    from ml_super_resolution_b200 import ops
+    from ml_super_resolution_b200.espcn.model_espcn import EspcnNet
+    from ml_super_resolution_b200.tiling import plan_tiles
+    C = 1
+    net = EspcnNet(None, SCALE, C, seed=42)
+    # trained-like magnitudes so tanh is exercised (reference init is sigma=0.02)
+    net.arena.w.mul_(5.0)
+    net.repack()
+    g = torch.Generator(device="cuda").manual_seed(1235 + rank)
+    lr = torch.rand((FRAMES_PER_STEP, LR_H, LR_W, C), device="cuda", generator=g) * 2 - 1
+    out = torch.empty((FRAMES_PER_STEP, LR_H * SCALE, LR_W * SCALE, C), device="cuda")
+    out_pix = FRAMES_PER_STEP * LR_H * SCALE * LR_W * SCALE
+
+    def step():
+        net.forward(lr, shuffle=True, out=out)
+
+    ms, clocks = timed_steps(step, args.steps, args.warmup, world, ClockSampler(torch.cuda.current_device()) if rank == 0 else None)
+    value = out_pix * world * args.steps / ms / 1e3  # Mpix/s, whole job
+    n_launch = launches_of(step) * args.steps
+
+    # ---- per-kernel device times for the roofline (same buffers, outside the timed region)
+    Ht, Wt, tiles = plan_tiles(FRAMES_PER_STEP, LR_H, LR_W, 4)
+    panels = ops.make_panels([t.as_tuple() for t in tiles])
+    t1, t2 = net._get_bufs(len(tiles), Ht, Wt)
+    a = net.arena
+    k_f1 = event_time(lambda: ops.conv_first(lr, a.view("f1/kernel:0"), a.view("f1/bias:0"), "SAME", "tanh", panels=panels, panel_hw=(Ht, Wt), out=t1))
+    k_f2 = event_time(lambda: ops.conv_tc(t1, net.plan.views[net._i2], a.view("f2/bias:0"), 3, "tanh", out=t2))
+    k_f3 = event_time(lambda: ops.conv_tc_last(t2, net.plan.views[net._i3], net.bias3, 3, net.cout3, None, shuffle_r=SCALE, panels=panels,
+                                               frame_shape=(FRAMES_PER_STEP, LR_H, LR_W), out=out))
+    lr_px = FRAMES_PER_STEP * LR_H * LR_W
+    # algorithmic bytes per LR pixel: f1 reads fp32 C, writes 64 bf16; f2 reads 64 bf16, writes 32 bf16;
+    # f3 reads 32 bf16, writes C*r^2 fp32
+    kernels = {
+        "espcn_f1_conv_first(5x5,C->64,tanh)": (k_f1, lr_px * (4 * C + 128)),
+        "espcn_f2_conv_tc(3x3,64->32,tanh)": (k_f2, lr_px * (128 + 64)),
+        "espcn_f3_conv_tc_last(3x3,32->9,shuffle)": (k_f3, lr_px * (64 + 4 * C * SCALE * SCALE)),
+    }
+    dom = max(kernels, key=lambda k: kernels[k][0])
+    pk = peaks()
+    ach = kernels[dom][1] / kernels[dom][0] / 1e6  # GB/s
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s", "frac": round(ach / pk["hbm"], 4),
+                "traffic": None, "peak_source": pk["src"], "kernel_ms": {k: round(v[0], 4) for k, v in kernels.items()},
+                "step_algorithmic_GB": round(sum(v[1] for v in kernels.values()) / 1e9, 3)}
+
+    # ---- end to end through the public call with HOST buffers (pinned in, pinned out, copies inside the timed region)
+    lr_host = lr.cpu().pin_memory()
+    out_host = torch.empty(out.shape, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        lr_d = lr_host.to("cuda", non_blocking=True)
+        net.forward(lr_d, shuffle=True, out=out)
+        out_host.copy_(out, non_blocking=True)
+
+    ms_e2e, _ = timed_steps(e2e_step, max(2, args.steps // 2), 2, world, None)
+    e2e_value = out_pix * world * max(2, args.steps // 2) / ms_e2e / 1e3
+    e2e = {"value": round(e2e_value, 1), "unit": "output Mpix/s", "h2d_bytes_per_step": lr_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4}
+    cfg = {"workload": f"ESPCN 3x (5x5-64 tanh, 3x3-32 tanh, 3x3-9 + fused pixel shuffle) inference, {FRAMES_PER_STEP} synthetic 1920x1080 Y frames/step/GPU",
+           "frames_per_step_per_gpu": FRAMES_PER_STEP, "lr_shape": [LR_H, LR_W, C], "scale": SCALE, "panels": len(tiles) // FRAMES_PER_STEP,
+           "l2_policy": "working set per step (activations ~1.7 GB + 0.3 GB output) >> 126 MB L2", "parallelism": f"frames x{world}"}
+    return dict(metric="ESPCN 3x output Mpix/s (fwd)", value=round(value, 1), unit="output Mpix/s", ms=ms, clocks=clocks, roofline=roofline,
+                e2e=e2e, gpu_launches=n_launch, config=cfg, scaling="weak")
+
+
+def espcn_cpu(frames: int, threads: int):
+    """CPU restatement (oracle, torch-CPU fp32 oneDNN) of the same ESPCN forward + pixel shuffle, `frames` frames."""
+    from oracle import models as OM
+    from oracle import ops as O
+    torch.set_num_threads(threads)
+    p = OM.espcn_init(seed=42, scaling_factor=SCALE, channels=1)
+    lr = OM.synthetic_images(1235, 1, LR_H, LR_W, 1)
+    OM.espcn_forward(p, lr[:, :64, :64], dtype=np.float32)  # warm
+    t0 = time.perf_counter()
+    for _ in range(frames):
+        y = OM.espcn_forward(p, lr, dtype=np.float32)
+        O.pixel_shuffle(y, SCALE)
+    dt = time.perf_counter() - t0
+    return frames * LR_H * SCALE * LR_W * SCALE / dt / 1e6, dt
+
+
+# ------------------------------------------------------------------------------------------------ VDSR training
+def vdsr_train_workload(args, rank, world):
+    from ml_super_resolution_b200.vdsr.model_vdsr import VdsrNet
+    net = VdsrNet(None, VDSR_LAYERS, 3, seed=42)
+    g = torch.Generator(device="cuda").manual_seed(1236 + rank)
+    hd = torch.rand((TRAIN_BATCH, TRAIN_PATCH, TRAIN_PATCH, 3), device="cuda", generator=g) * 2 - 1
+    from ml_super_resolution_b200 import ops
+    scales = torch.tensor([2.0, 3.0, 4.0], device="cuda")[torch.arange(TRAIN_BATCH, device="cuda") % 3]
+    sd = ((ops.degrade_gauss_bilinear(hd * 0.5 + 0.5, scales)) * 2 - 1).contiguous()
+
+    def step():
+        net.train_step(sd, hd, lr=5e-5, use_adam=True)
+
+    ms, clocks = timed_steps(step, args.steps, args.warmup, world, ClockSampler(torch.cuda.current_device()) if rank == 0 else None)
+    value = TRAIN_BATCH * world * args.steps / ms * 1e3
+    flops_per_patch = 6.7217e9
+    pk = peaks()
+    tf = value * flops_per_patch / 1e12 / world
+    roofline = {"bound": "tensor", "kernel": "whole training step (18x fwd/dgrad/wgrad tcgen05 convs dominate)", "achieved": round(tf, 1),
+                "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": round(tf / pk["tf_sust"], 4), "traffic": None, "peak_source": pk["src"]}
+    n_launch = launches_of(step) * args.steps
+    sd_h, hd_h = sd.cpu().pin_memory(), hd.cpu().pin_memory()
+
+    def e2e_step():
+        s, h = sd_h.to("cuda", non_blocking=True), hd_h.to("cuda", non_blocking=True)
+        loss = net.train_step(s, h, lr=5e-5, use_adam=True)
+        loss.item()  # device->host read of the step's loss
+
+    ms_e, _ = timed_steps(e2e_step, max(2, args.steps // 2), 2, world, None)
+    e2e = {"value": round(TRAIN_BATCH * world * max(2, args.steps // 2) / ms_e * 1e3, 1), "unit": "patches/s",
+           "h2d_bytes_per_step": 2 * sd_h.numel() * 4, "d2h_bytes_per_step": 4}
+    cfg = {"workload": f"VDSR-20 3x3-64 residual training, {TRAIN_BATCH} synthetic 41x41x3 patches/GPU, blur+bilinear 2/3/4x degrade, Adam",
+           "global_batch": TRAIN_BATCH * world, "parallelism": f"dp{world}", "l2_policy": "saved activations 19 x 14.5 MB = 275 MB per step > 126 MB L2"}
+    return dict(metric="VDSR-20 training patches/s", value=round(value, 1), unit="patches/s", ms=ms, clocks=clocks, roofline=roofline, e2e=e2e,
+                gpu_launches=n_launch, config=cfg, scaling="weak")
+
+
+def vdsr_train_cpu(steps: int, threads: int):
+    from oracle import models as OM
+    torch.set_num_threads(threads)
+    p = OM.vdsr_init(seed=42)
+    sd = OM.synthetic_images(1, TRAIN_BATCH, TRAIN_PATCH, TRAIN_PATCH, 3)
+    hd = OM.synthetic_images(2, TRAIN_BATCH, TRAIN_PATCH, TRAIN_PATCH, 3)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        OM.vdsr_loss_and_grads(p, sd, hd, dtype=np.float32)
+    dt = time.perf_counter() - t0
+    return steps * TRAIN_BATCH / dt, dt
+
+
+# ------------------------------------------------------------------------------------------------ VDSR 4K inference
+def vdsr_infer_workload(args, rank, world):
+    from ml_super_resolution_b200.vdsr.model_vdsr import VdsrNet
+    net = VdsrNet(None, VDSR_LAYERS, 3, seed=42)
+    H, W = FRAME_4K
+    g = torch.Generator(device="cuda").manual_seed(1237)
+    sd = torch.rand((1, H, W, 3), device="cuda", generator=g) * 2 - 1
+    out = torch.empty_like(sd)
+
+    def step():
+        net.forward(sd, out=out, rank=rank, world=world)
+
+    ms, clocks = timed_steps(step, args.steps, args.warmup, world, ClockSampler(torch.cuda.current_device()) if rank == 0 else None)
+    value = H * W * args.steps / ms / 1e3  # one frame per step for the whole job (strong scaling over tiles)
+    pk = peaks()
+    tf = value * 1e6 * 1334016 / 1e12 / world
+    roofline = {"bound": "tensor", "kernel": "conv_tc 3x3 64->64 (18 of 20 layers)", "achieved": round(tf, 1), "peak": pk["tf_sust"],
+                "unit": "TFLOP/s", "frac": round(tf / pk["tf_sust"], 4), "traffic": None, "peak_source": pk["src"]}
+    n_launch = launches_of(step) * args.steps
+    sd_h = sd.cpu().pin_memory()
+    out_h = torch.empty(sd.shape).pin_memory()
+
+    def e2e_step():
+        s = sd_h.to("cuda", non_blocking=True)
+        net.forward(s, out=out, rank=rank, world=world)
+        out_h.copy_(out, non_blocking=True)
+
+    ms_e, _ = timed_steps(e2e_step, max(2, args.steps // 2), 1, world, None)
+    e2e = {"value": round(H * W * max(2, args.steps // 2) / ms_e / 1e3, 1), "unit": "output Mpix/s", "h2d_bytes_per_step": sd_h.numel() * 4,
+           "d2h_bytes_per_step": out_h.numel() * 4}
+    cfg = {"workload": "VDSR-20 3x tiled inference, one synthetic 3840x2160x3 frame/step, 252-px column panels with 20-px halo sharded over the GPUs",
+           "parallelism": f"tiles x{world}", "l2_policy": "activations 2 x 1.26 GB ping-pong >> 126 MB L2"}
+    return dict(metric="VDSR 3x output Mpix/s (fwd)", value=round(value, 1), unit="output Mpix/s", ms=ms, clocks=clocks, roofline=roofline, e2e=e2e,
+                gpu_launches=n_launch, config=cfg, scaling="strong")
+
+
+def vdsr_infer_cpu(threads: int, rows: int = 270):
+    """Bounded sample: a 270-row x 3840 band of the 4K frame (1/8 of the pixels) through all 20 layers."""
+    from oracle import models as OM
+    torch.set_num_threads(threads)
+    p = OM.vdsr_init(seed=42)
+    sd = OM.synthetic_images(3, 1, rows, FRAME_4K[1], 3)
+    t0 = time.perf_counter()
+    OM.vdsr_forward_t(OM._to_t(p, np.float32), OM._t(sd, np.float32))
+    dt = time.perf_counter() - t0
+    return rows * FRAME_4K[1] / dt / 1e6, dt
+
+
+WORKLOADS = {"espcn": espcn_workload, "vdsr_train": vdsr_train_workload, "vdsr_infer": vdsr_infer_workload}
+
+
+def run_reference(args, rank, world):
+    """The reference's CPU path: oracle restatement of the TF-1.8 graph on torch-CPU fp32 with all host threads."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    t_all = time.perf_counter()
+    if args.workload == "espcn":
+        frames = max(1, min(args.steps, 8))
+        with torch.no_grad():
+            for _ in range(min(args.warmup, 1)):
+                espcn_cpu(1, threads)
+            v, dt = espcn_cpu(frames, threads)
+        unit, metric, steps, sample = "output Mpix/s", "ESPCN 3x output Mpix/s (fwd)", frames, f"{frames} step(s) of ONE 1920x1080 Y frame each (GPU arm: {FRAMES_PER_STEP}/step)"
+        cfg = {"workload": "ESPCN 3x inference on synthetic 1920x1080 Y frames (CPU restatement, torch-CPU fp32)"}
+    elif args.workload == "vdsr_train":
+        steps = max(1, min(args.steps, 5))
+        v, dt = vdsr_train_cpu(steps, threads)
+        unit, metric, sample = "patches/s", "VDSR-20 training patches/s", f"{steps} fwd+bwd step(s) of 64 41x41x3 patches (no optimiser step)"
+        cfg = {"workload": "VDSR-20 training, 64 synthetic 41x41x3 patches (CPU restatement, torch-CPU fp32 autograd)"}
+    else:
+        with torch.no_grad():
+            v, dt = vdsr_infer_cpu(threads)
+        unit, metric, steps, sample = "output Mpix/s", "VDSR 3x output Mpix/s (fwd)", 1, "one 270x3840 band (1/8 of a 4K frame)"
+        cfg = {"workload": "VDSR-20 inference on a synthetic 4K frame (CPU restatement, torch-CPU fp32)"}
+    line = {"impl": "reference", "metric": metric, "value": round(v, 3), "unit": unit, "n_gpus": world, "steps": steps, "warmup": min(args.warmup, 1),
+            "ms_per_step": round(dt * 1e3 / steps, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": round(v, 3), "unit": unit, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": round(v, 3), "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": round(time.perf_counter() - t_all, 1)}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="espcn", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads in the default run")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    rank, world, local = dist_info()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    assert torch.cuda.is_available(), "bench.py (native arm) needs a B200; there is no CPU fallback"
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch N>1 with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 bench.py --gpus N ...")
+    torch.cuda.set_device(local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    res = WORKLOADS[args.workload](args, rank, world)
+    also = {}
+    if args.workload == "espcn" and not args.no_also:
+        sub = argparse.Namespace(**vars(args))
+        sub.steps, sub.warmup = max(5, args.steps // 2), 3
+        for name in ("vdsr_train", "vdsr_infer"):
+            r = WORKLOADS[name](sub, rank, world)
+            also[name] = {"metric": r["metric"], "value": r["value"], "unit": r["unit"], "ms_per_step": round(r["ms"] / sub.steps, 4),
+                          "roofline": r["roofline"], "e2e": r["e2e"], "scaling": r["scaling"], "steps": sub.steps}
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            with torch.no_grad():
+                if args.workload == "espcn":
+                    v, dt = espcn_cpu(4, threads)
+                    cpu = {"value": round(v, 2), "unit": "output Mpix/s", "cores": threads, "kind": "port", "sample": f"4 frames of 1920x1080 Y, {dt:.1f} s"}
+                elif args.workload == "vdsr_infer":
+                    v, dt = vdsr_infer_cpu(threads)
+                    cpu = {"value": round(v, 3), "unit": "output Mpix/s", "cores": threads, "kind": "port", "sample": f"one 270x3840 band, {dt:.1f} s"}
+            if args.workload == "vdsr_train":
+                v, dt = vdsr_train_cpu(3, threads)
+                cpu = {"value": round(v, 2), "unit": "patches/s", "cores": threads, "kind": "port", "sample": f"3 fwd+bwd steps of 64 patches, {dt:.1f} s"}
+        line = {"metric": res["metric"], "value": res["value"], "unit": res["unit"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": round(res["ms"] / args.steps, 4), "higher_is_better": True, "scaling": res["scaling"], "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic", "config": res["config"], "clocks": res["clocks"], "e2e": res["e2e"],
+                "gpu_launches": res["gpu_launches"], "roofline": res["roofline"], "cpu_baseline": cpu}
+        if also:
+            line["also"] = also
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -122,11 +122,14 @@ int srk_conv_tc_last(srk_handle_t h, const void* x_fpa, int cin_p, const void* w
                      const float* addend, float* out, srk_stream_t stream);
 
 /* Weight gradient of a 3x3 64->64 layer on tensor cores: dW[u,v,ci,co] = sum_p x[p+(u-1)*Wp+(v-1)][ci]
- * * dy[p][co]; split over CTAs, accumulated with fp32 atomics into dw_hwio (caller zeroes it, or
- * pre-loads it with weight_decay*w); dbias[co] = sum_p dy[p][co].
+ * * dy[p][co], dbias[co] = sum_p dy[p][co].  Split over CTAs along the pixel axis; every CTA stores its
+ * partial [9*64*64+64] block into `workspace` and a second kernel sums the partials in a fixed order
+ * (deterministic).  accumulate != 0 adds to dw/dbias instead of overwriting.
  *   replaces the wgrad/bgrad ops autodiff adds for  vdsr/vdsr/model_vdsr.py:146-148 (minimize). */
+size_t srk_conv_wgrad_tc_workspace_bytes(srk_handle_t h, int n_img, int H, int W);
 int srk_conv_wgrad_tc(srk_handle_t h, const void* x_fpa, const void* dy_fpa, int n_img, int H, int W,
-                      float* dw_hwio, float* dbias, srk_stream_t stream);
+                      float* dw_hwio, float* dbias, int accumulate, void* workspace, size_t workspace_bytes,
+                      srk_stream_t stream);
 
 /* Weight gradient of the first layer (x fp32 NHWC cin<=4, dy FPA 64ch) -> dw [k,k,cin,64], db[64]. */
 int srk_conv_first_wgrad(srk_handle_t h, const float* x, int n_img, int H, int W, int cin, int k,

@@ -42,7 +42,8 @@ SIGNATURES = {
     "srk_conv_first": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P]),
     "srk_conv_tc": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P]),
     "srk_conv_tc_last": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P]),
-    "srk_conv_wgrad_tc": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "srk_conv_wgrad_tc_workspace_bytes": (_SZ, [_P, _I, _I, _I]),
+    "srk_conv_wgrad_tc": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _SZ, _P]),
     "srk_conv_first_wgrad": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "srk_conv_last_wgrad": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "srk_pixel_shuffle": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
@@ -71,8 +72,35 @@ def lib() -> C.CDLL:
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        _lib = l
+        _lib = _CountingLib(l)
     return _lib
+
+
+# kernels launched per C-ABI call (everything else: 0) -- feeds bench.py's `gpu_launches`
+KERNELS_PER_CALL = {name: 1 for name in SIGNATURES if name not in
+                    ("srk_version", "srk_last_error", "srk_create", "srk_destroy", "srk_num_sms", "srk_fpa_rows",
+                     "srk_conv_wgrad_tc_workspace_bytes")}
+KERNELS_PER_CALL["srk_conv_wgrad_tc"] = 2
+launch_count = 0
+
+
+class _CountingLib:
+    """Thin proxy over the CDLL that counts kernel launches issued through the C ABI."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+        for name in SIGNATURES:
+            fn = getattr(cdll, name)
+            k = KERNELS_PER_CALL.get(name, 0)
+            setattr(self, name, self._wrap(fn, k) if k else fn)
+
+    @staticmethod
+    def _wrap(fn, k):
+        def call(*args):
+            global launch_count
+            launch_count += k
+            return fn(*args)
+        return call
 
 
 def check(rc: int, what: str = "") -> None:

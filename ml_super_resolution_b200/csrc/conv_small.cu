@@ -235,76 +235,114 @@ __global__ void nhwc_to_fpa_kernel(const float* __restrict__ x, int C, int n_img
 }
 
 // ------------------------------------------------------------------------------------ first/last layer wgrad
+// Both are tiny contractions (k*k*cin*64 <= 15.5k outputs, reduction over every pixel).  256 threads =
+// 64 channels x 4 pixel lanes; each thread keeps its k*k*c partial sums in registers while the block walks
+// its pixel slice, then the 4 pixel lanes are folded through shared memory and one fp32 atomic per
+// output and block goes to global (caller zeroes dw/db).
+//
 // First layer: dw[u][v][ci][co] = sum_{n,y,x} x[n, y+u-po, x+v-po, ci] * dy[n,y,x,co];  db[co] = sum dy.
-// One block per (tap, slice of pixels); 64 threads = co; fp32 atomics into dw/db (caller zeroes).
-__global__ void __launch_bounds__(64) conv_first_wgrad_kernel(const float* __restrict__ x, int n_img, int H, int W, int cin, int k,
-                                                              const __nv_bfloat16* __restrict__ dy, float* __restrict__ dw,
-                                                              float* __restrict__ db, int slices) {
-  const int tap = blockIdx.x / slices, slice = blockIdx.x % slices;
-  const bool do_bias = (tap == k * k);  // extra pseudo-tap accumulates the bias gradient
-  const int u = tap / k, v = tap % k, po = k / 2;
-  const int co = threadIdx.x;
+template <int KS, int CIN>
+__global__ void __launch_bounds__(256) conv_first_wgrad_kernel(const float* __restrict__ x, int n_img, int H, int W,
+                                                               const __nv_bfloat16* __restrict__ dy, float* __restrict__ dw,
+                                                               float* __restrict__ db) {
+  constexpr int kAcc = KS * KS * CIN + 1;  // + bias
+  constexpr int po = KS / 2;
+  const int co = threadIdx.x & 63, pl = threadIdx.x >> 6;
   const int Wp = W + 1;
   const int64_t S = int64_t(H + 1) * Wp;
   const int64_t npix = int64_t(n_img) * H * W;
-  const int64_t per = (npix + slices - 1) / slices;
-  const int64_t p0 = slice * per, p1 = min(npix, p0 + per);
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int64_t pix = p0; pix < p1; ++pix) {
+  const int64_t per = (npix + gridDim.x - 1) / gridDim.x;
+  const int64_t p0 = blockIdx.x * per, p1 = min(npix, p0 + per);
+  float acc[kAcc];
+#pragma unroll
+  for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
+  for (int64_t pix = p0 + pl; pix < p1; pix += 4) {
     const int xx = int(pix % W);
     const int yy = int((pix / W) % H);
     const int64_t n = pix / (int64_t(W) * H);
     const float g = __bfloat162float(dy[(n * S + int64_t(yy + 1) * Wp + xx) * 64 + co]);
-    if (do_bias) {
-      acc[0] += g;
-      continue;
+    acc[kAcc - 1] += g;
+    const float* img = x + n * int64_t(H) * W * CIN;
+#pragma unroll
+    for (int u = 0; u < KS; ++u) {
+      const int sy = yy + u - po;
+#pragma unroll
+      for (int v = 0; v < KS; ++v) {
+        const int sx = xx + v - po;
+        if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
+          const float* src = img + (int64_t(sy) * W + sx) * CIN;
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci) acc[(u * KS + v) * CIN + ci] = fmaf(__ldg(src + ci), g, acc[(u * KS + v) * CIN + ci]);
+        }
+      }
     }
-    const int sy = yy + u - po, sx = xx + v - po;
-    if (sy < 0 || sy >= H || sx < 0 || sx >= W) continue;
-    const float* src = x + ((n * H + sy) * int64_t(W) + sx) * cin;
-    for (int ci = 0; ci < cin; ++ci) acc[ci] = fmaf(__ldg(src + ci), g, acc[ci]);
   }
-  if (do_bias) {
-    atomicAdd(db + co, acc[0]);
-  } else {
-    for (int ci = 0; ci < cin; ++ci) atomicAdd(dw + (tap * cin + ci) * 64 + co, acc[ci]);
+  __shared__ float red[4][64];
+#pragma unroll 1
+  for (int i = 0; i < kAcc; ++i) {
+    red[pl][co] = acc[i];
+    __syncthreads();
+    if (pl == 0) {
+      const float t = (red[0][co] + red[1][co]) + (red[2][co] + red[3][co]);
+      if (i == kAcc - 1) atomicAdd(db + co, t);
+      else atomicAdd(dw + i * 64 + co, t);
+    }
+    __syncthreads();
   }
 }
 
-// Last layer: dw[u][v][ci][co] = sum_p x_fpa[p + (u-1)Wp + (v-1)][ci] * dy[p][co], co < cout <= 4; db[co] = sum dy.
-// One block per (tap, slice); 64 threads = ci.
-__global__ void __launch_bounds__(64) conv_last_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ dy,
-                                                             int n_img, int H, int W, int cout, float* __restrict__ dw,
-                                                             float* __restrict__ db, int slices) {
-  const int tap = blockIdx.x / slices, slice = blockIdx.x % slices;
-  const bool do_bias = (tap == 9);
-  const int u = tap / 3, v = tap % 3;
-  const int ci = threadIdx.x;
+// Last layer: dw[u][v][ci][co] = sum_p x_fpa[p + (u-1)Wp + (v-1)][ci] * dy[p][co], co < COUT <= 4; db[co] = sum dy.
+template <int COUT>
+__global__ void __launch_bounds__(256) conv_last_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ dy,
+                                                              int n_img, int H, int W, float* __restrict__ dw, float* __restrict__ db) {
+  constexpr int kAcc = 9 * COUT;
+  const int ci = threadIdx.x & 63, pl = threadIdx.x >> 6;
   const int Wp = W + 1;
   const int64_t S = int64_t(H + 1) * Wp;
+  const int64_t rows_valid = int64_t(n_img) * S;
   const int64_t npix = int64_t(n_img) * H * W;
-  const int64_t per = (npix + slices - 1) / slices;
-  const int64_t p0 = slice * per, p1 = min(npix, p0 + per);
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int64_t pix = p0; pix < p1; ++pix) {
+  const int64_t per = (npix + gridDim.x - 1) / gridDim.x;
+  const int64_t p0 = blockIdx.x * per, p1 = min(npix, p0 + per);
+  float acc[kAcc], bacc[COUT];
+#pragma unroll
+  for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < COUT; ++i) bacc[i] = 0.f;
+  for (int64_t pix = p0 + pl; pix < p1; pix += 4) {
     const int xx = int(pix % W);
     const int yy = int((pix / W) % H);
     const int64_t n = pix / (int64_t(W) * H);
-    const float* g = dy + pix * cout;
-    if (do_bias) {
-      if (ci < cout) acc[0] += __ldg(g + ci);
-      continue;
+    float g[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) {
+      g[co] = __ldg(dy + pix * COUT + co);
+      bacc[co] += g[co];
     }
-    // FPA pads are zero, so out-of-image taps contribute nothing
-    const int64_t row = n * S + int64_t(yy + 1) * Wp + xx + int64_t(u - 1) * Wp + (v - 1);
-    if (row < 0 || row >= int64_t(n_img) * S) continue;  // outside the tensor: zero (TMA would zero-fill)
-    const float xv = __bfloat162float(x[row * 64 + ci]);
-    for (int co = 0; co < cout; ++co) acc[co] = fmaf(xv, __ldg(g + co), acc[co]);
+    const int64_t row = n * S + int64_t(yy + 1) * Wp + xx;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int64_t r = row + int64_t(tap / 3 - 1) * Wp + (tap % 3 - 1);
+      // FPA pads are zero, rows outside the tensor read as zero (TMA would zero-fill them)
+      const float xv = (r >= 0 && r < rows_valid) ? __bfloat162float(x[r * 64 + ci]) : 0.f;
+#pragma unroll
+      for (int co = 0; co < COUT; ++co) acc[tap * COUT + co] = fmaf(xv, g[co], acc[tap * COUT + co]);
+    }
   }
-  if (do_bias) {
-    if (ci < cout) atomicAdd(db + ci, acc[0]);
-  } else {
-    for (int co = 0; co < cout; ++co) atomicAdd(dw + (tap * 64 + ci) * cout + co, acc[co]);
+  __shared__ float red[4][64];
+#pragma unroll 1
+  for (int i = 0; i < kAcc; ++i) {
+    red[pl][ci] = acc[i];
+    __syncthreads();
+    if (pl == 0) {
+      const float t = (red[0][ci] + red[1][ci]) + (red[2][ci] + red[3][ci]);
+      const int tap = i / COUT, co = i % COUT;
+      atomicAdd(dw + (tap * 64 + ci) * COUT + co, t);
+    }
+    __syncthreads();
+  }
+  if (ci == 0) {  // every ci lane holds the same bias sums: one lane per pixel lane reports
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) atomicAdd(db + co, bacc[co]);
   }
 }
 
@@ -381,24 +419,39 @@ extern "C" int srk_nhwc_to_fpa(srk_handle_t h, const float* x, int C, int n_img,
 extern "C" int srk_conv_first_wgrad(srk_handle_t h, const float* x, int n_img, int H, int W, int cin, int k, const void* dy_fpa,
                                     float* dw_hwio, float* dbias, srk_stream_t stream) {
   SRK_REQUIRE(h && x && dy_fpa && dw_hwio && dbias, "srk_conv_first_wgrad: null argument");
-  SRK_REQUIRE(cin >= 1 && cin <= 4, "srk_conv_first_wgrad: cin %d unsupported", cin);
-  const int slices = 64;
-  conv_first_wgrad_kernel<<<(k * k + 1) * slices, 64, 0, as_stream(stream)>>>(x, n_img, H, W, cin, k,
-                                                                            static_cast<const __nv_bfloat16*>(dy_fpa), dw_hwio,
-                                                                            dbias, slices);
-  SRK_LAUNCH_CHECK();
-  return 0;
+  const int64_t npix = int64_t(n_img) * H * W;
+  const int grid = int(std::min<int64_t>((npix + 63) / 64, int64_t(h->num_sms) * 4));
+  const __nv_bfloat16* dy = static_cast<const __nv_bfloat16*>(dy_fpa);
+  cudaStream_t s = as_stream(stream);
+#define SRK_CASE(KS, CIN)                                                                           \
+  if (k == KS && cin == CIN) {                                                                      \
+    conv_first_wgrad_kernel<KS, CIN><<<grid, 256, 0, s>>>(x, n_img, H, W, dy, dw_hwio, dbias);      \
+    SRK_LAUNCH_CHECK();                                                                             \
+    return 0;                                                                                       \
+  }
+  SRK_CASE(3, 1) SRK_CASE(3, 3) SRK_CASE(5, 1) SRK_CASE(5, 3)
+#undef SRK_CASE
+  set_error("srk_conv_first_wgrad: unsupported (k=%d, cin=%d)", k, cin);
+  return -1;
 }
 
 extern "C" int srk_conv_last_wgrad(srk_handle_t h, const void* x_fpa, const float* dy, int n_img, int H, int W, int cout,
                                    float* dw_hwio, float* dbias, srk_stream_t stream) {
   SRK_REQUIRE(h && x_fpa && dy && dw_hwio && dbias, "srk_conv_last_wgrad: null argument");
-  SRK_REQUIRE(cout >= 1 && cout <= 4, "srk_conv_last_wgrad: cout %d unsupported", cout);
-  const int slices = 64;
-  conv_last_wgrad_kernel<<<10 * slices, 64, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(x_fpa), dy, n_img, H, W, cout,
-                                                                    dw_hwio, dbias, slices);
-  SRK_LAUNCH_CHECK();
-  return 0;
+  const int64_t npix = int64_t(n_img) * H * W;
+  const int grid = int(std::min<int64_t>((npix + 63) / 64, int64_t(h->num_sms) * 4));
+  const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(x_fpa);
+  cudaStream_t s = as_stream(stream);
+#define SRK_CASE(COUT)                                                                       \
+  if (cout == COUT) {                                                                        \
+    conv_last_wgrad_kernel<COUT><<<grid, 256, 0, s>>>(x, dy, n_img, H, W, dw_hwio, dbias);   \
+    SRK_LAUNCH_CHECK();                                                                      \
+    return 0;                                                                                \
+  }
+  SRK_CASE(1) SRK_CASE(2) SRK_CASE(3) SRK_CASE(4)
+#undef SRK_CASE
+  set_error("srk_conv_last_wgrad: unsupported cout=%d", cout);
+  return -1;
 }
 
 extern "C" int srk_pack_conv_weights_batched(srk_handle_t h, const float* arena, const srk_pack_job* jobs_device, int n_jobs,

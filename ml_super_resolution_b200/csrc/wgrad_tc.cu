@@ -10,7 +10,8 @@
 // ring keeps a mirror of its first chunks behind its last slot).  The ninth tap is paired with a
 // block of ones, which makes rows 64..127 of that accumulator the bias gradient sum_p dY[p][co].
 // Five fp32 accumulators (5 x 64 TMEM columns) persist over the CTA's whole pixel range (split-K
-// across CTAs); the epilogue adds them into dW / dbias with fp32 reductions.
+// across CTAs); each CTA stores its partial block to a workspace and a second, deterministic
+// kernel sums the partials into dW / dbias (fixed order: bit-reproducible gradients).
 //
 //   warp 0: TMA producer for X chunks (+ mirrors)      warp 6: TMA producer for dY chunks
 //   warp 1: TMEM allocator + single-thread MMA issuer  warps 2..5: epilogue
@@ -23,12 +24,12 @@ constexpr int kXSlots = 10;  // ring + mirror slots (16 KB each)
 constexpr int kYRing = 3;
 constexpr int kWgThreads = 224;
 constexpr int kChunk = 128 * 128;  // bytes
+constexpr int kPartialFloats = 9 * 64 * 64 + 64;  // dW[9][64][64] then dbias[64]
 
 struct alignas(64) WgradParams {
   CUtensorMap map_x;   // [rows_valid][64] box {64,128}
   CUtensorMap map_dy;  // [rows_valid][64] box {64,128}
-  float* dw;           // [9][64][64] fp32 (HWIO), accumulated
-  float* dbias;        // [64]
+  float* partial;      // workspace: [gridDim.x][kPartialFloats] per-CTA partial sums
   int Wp;
   int num_chunks;
   int nb;      // look-behind/ahead chunks: ceil((Wp+1)/128)
@@ -152,11 +153,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         umma_commit(bar_done);
       }
     } else {
-      // ---------------------------------------------------------------- epilogue: TMEM -> global reductions
+      // ---------------------------------------------------------------- epilogue: TMEM -> this CTA's partial block
       const int quad = warp & 3;
       const int m = quad * 32 + lane;  // accumulator row
       mbar_wait(bar_done, 0);
       tc_fence_after();
+      float* part = p.partial + size_t(blockIdx.x) * kPartialFloats;
       const int tap_of[5][2] = {{0, 1}, {3, 4}, {6, 7}, {2, 5}, {8, -1}};
 #pragma unroll 1
       for (int pr = 0; pr < 5; ++pr) {
@@ -167,13 +169,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
           uint32_t u[32];
           tmem_ld_32x32b_x32(tmem + pr * 64 + c + (uint32_t(quad * 32) << 16), u);
           tmem_ld_wait();
-          if (tap >= 0) {
-            float* dst = p.dw + (size_t(tap) * 64 + ci) * 64 + c;
+          float4* dst = nullptr;
+          if (tap >= 0) dst = reinterpret_cast<float4*>(part + (size_t(tap) * 64 + ci) * 64 + c);
+          else if (m == 64) dst = reinterpret_cast<float4*>(part + 9 * 64 * 64 + c);
+          if (dst) {
 #pragma unroll
-            for (int q = 0; q < 32; ++q) atomicAdd(dst + q, __uint_as_float(u[q]));
-          } else if (m == 64) {
-#pragma unroll
-            for (int q = 0; q < 32; ++q) atomicAdd(p.dbias + c + q, __uint_as_float(u[q]));
+            for (int q = 0; q < 8; ++q)
+              dst[q] = make_float4(__uint_as_float(u[4 * q]), __uint_as_float(u[4 * q + 1]), __uint_as_float(u[4 * q + 2]),
+                                   __uint_as_float(u[4 * q + 3]));
           }
         }
       }
@@ -184,24 +187,68 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
+// Deterministic second pass: dw/dbias = (accumulate ? dw : 0) + sum over CTA partials (fixed order).
+__global__ void __launch_bounds__(128) wgrad_reduce_kernel(const float4* __restrict__ partial, int n_part, float4* __restrict__ dw,
+                                                           float4* __restrict__ dbias, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // float4 index
+  constexpr int kN4 = kPartialFloats / 4;
+  if (i >= kN4) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int pidx = 0;
+  for (; pidx + 4 <= n_part; pidx += 4) {
+    const float4 a = __ldg(partial + size_t(pidx) * kN4 + i), b = __ldg(partial + size_t(pidx + 1) * kN4 + i);
+    const float4 c = __ldg(partial + size_t(pidx + 2) * kN4 + i), d = __ldg(partial + size_t(pidx + 3) * kN4 + i);
+    acc.x += (a.x + b.x) + (c.x + d.x);
+    acc.y += (a.y + b.y) + (c.y + d.y);
+    acc.z += (a.z + b.z) + (c.z + d.z);
+    acc.w += (a.w + b.w) + (c.w + d.w);
+  }
+  for (; pidx < n_part; ++pidx) {
+    const float4 a = __ldg(partial + size_t(pidx) * kN4 + i);
+    acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+  }
+  float4* dst = (i < 9 * 64 * 64 / 4) ? dw + i : dbias + (i - 9 * 64 * 64 / 4);
+  if (accumulate) {
+    const float4 o = *dst;
+    acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+  }
+  *dst = acc;
+}
+
+static int wgrad_grid(srk_ctx* h, int num_chunks) {
+  int g = (num_chunks + 7) / 8;  // >= 8 chunks of MMA work per partial block written
+  if (g > h->num_sms) g = h->num_sms;
+  if (g < 1) g = 1;
+  return g;
+}
+
 }  // namespace srk
 
 using namespace srk;
 
+extern "C" size_t srk_conv_wgrad_tc_workspace_bytes(srk_handle_t h, int n_img, int H, int W) {
+  if (!h) return 0;
+  const FpaGeom g = fpa_geom(n_img, H, W);
+  return size_t(wgrad_grid(h, int((g.rows_valid + 127) / 128))) * kPartialFloats * sizeof(float);
+}
+
 extern "C" int srk_conv_wgrad_tc(srk_handle_t h, const void* x_fpa, const void* dy_fpa, int n_img, int H, int W, float* dw_hwio,
-                                 float* dbias, srk_stream_t stream) {
-  SRK_REQUIRE(h && x_fpa && dy_fpa && dw_hwio && dbias, "srk_conv_wgrad_tc: null argument");
+                                 float* dbias, int accumulate, void* workspace, size_t workspace_bytes, srk_stream_t stream) {
+  SRK_REQUIRE(h && x_fpa && dy_fpa && dw_hwio && dbias && workspace, "srk_conv_wgrad_tc: null argument");
+  SRK_REQUIRE((reinterpret_cast<uintptr_t>(dw_hwio) | reinterpret_cast<uintptr_t>(dbias) | reinterpret_cast<uintptr_t>(workspace)) % 16 == 0,
+              "srk_conv_wgrad_tc: dw, dbias and workspace must be 16-byte aligned");
   const FpaGeom g = fpa_geom(n_img, H, W);
   SRK_REQUIRE(g.rows_valid < (int64_t(1) << 31), "srk_conv_wgrad_tc: too many rows");
   WgradParams p{};
-  p.dw = dw_hwio;
-  p.dbias = dbias;
+  p.partial = static_cast<float*>(workspace);
   p.Wp = g.Wp;
   p.num_chunks = int((g.rows_valid + 127) / 128);
   p.nb = (g.Wp + 1 + 127) / 128;
   p.mirror = (g.Wp + 16 + 127) / 128;
   p.ring = kXSlots - p.mirror;
   SRK_REQUIRE(p.ring >= 2 * p.nb + 2, "srk_conv_wgrad_tc: image width %d too large for the flat-stream kernel", W);
+  const int grid = wgrad_grid(h, p.num_chunks);
+  SRK_REQUIRE(workspace_bytes >= size_t(grid) * kPartialFloats * sizeof(float), "srk_conv_wgrad_tc: workspace too small (%zu B)", workspace_bytes);
   if (int rc = make_tensor_map_2d(&p.map_x, x_fpa, uint64_t(g.rows_valid), 64, 128)) return rc;
   if (int rc = make_tensor_map_2d(&p.map_dy, dy_fpa, uint64_t(g.rows_valid), 64, 128)) return rc;
   static bool attr_set = false;
@@ -209,8 +256,10 @@ extern "C" int srk_conv_wgrad_tc(srk_handle_t h, const void* x_fpa, const void* 
     SRK_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem::kTotal));
     attr_set = true;
   }
-  const int grid = p.num_chunks < h->num_sms ? p.num_chunks : h->num_sms;
   wgrad_tc_kernel<<<grid, kWgThreads, WgSmem::kTotal, as_stream(stream)>>>(p);
+  SRK_LAUNCH_CHECK();
+  wgrad_reduce_kernel<<<(kPartialFloats / 4 + 127) / 128, 128, 0, as_stream(stream)>>>(
+      static_cast<const float4*>(workspace), grid, reinterpret_cast<float4*>(dw_hwio), reinterpret_cast<float4*>(dbias), accumulate);
   SRK_LAUNCH_CHECK();
   return 0;
 }

@@ -189,10 +189,23 @@ def conv_tc_last(x: Fpa, w_packed: torch.Tensor, bias: torch.Tensor | None, k: i
     return out
 
 
-def conv_wgrad_tc(x: Fpa, dy: Fpa, dw: torch.Tensor, dbias: torch.Tensor) -> None:
-    """dw [3,3,64,64] += X^T dY per tap, dbias [64] += sum dY (srk_conv_wgrad_tc)."""
+_wgrad_ws: dict = {}
+
+
+def wgrad_workspace(n_img: int, H: int, W: int, device="cuda") -> torch.Tensor:
+    """Per-shape workspace for srk_conv_wgrad_tc's per-CTA partial blocks (allocated once, reused by every layer)."""
+    nbytes = int(_ffi.lib().srk_conv_wgrad_tc_workspace_bytes(handle(), n_img, H, W))
+    key = (str(device), nbytes)
+    if key not in _wgrad_ws:
+        _wgrad_ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    return _wgrad_ws[key]
+
+
+def conv_wgrad_tc(x: Fpa, dy: Fpa, dw: torch.Tensor, dbias: torch.Tensor, accumulate=False, workspace: torch.Tensor | None = None) -> None:
+    """dw [3,3,64,64] (=|+=) X^T dY per tap, dbias [64] (=|+=) sum dY (srk_conv_wgrad_tc, deterministic)."""
+    ws = workspace if workspace is not None else wgrad_workspace(x.n_img, x.H, x.W, x.data.device)
     check(_ffi.lib().srk_conv_wgrad_tc(handle(), _ptr(x.data), _ptr(dy.data), x.n_img, x.H, x.W, _ptr(_f32(dw)), _ptr(_f32(dbias)),
-                                       _stream()), "srk_conv_wgrad_tc")
+                                       int(accumulate), _ptr(ws), ws.numel(), _stream()), "srk_conv_wgrad_tc")
 
 
 def conv_first_wgrad(x: torch.Tensor, dy: Fpa, k: int, dw: torch.Tensor, dbias: torch.Tensor) -> None:
