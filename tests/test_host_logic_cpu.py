@@ -1,0 +1,113 @@
+"""CPU suite: host-side logic -- tile planner, parameter arena, session shim, and the data-parallel /
+tile-sharded math on a world_size-2 gloo group."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from ml_super_resolution_b200.tiling import MAX_PANEL_W, plan_tiles, shard_tiles
+
+
+@pytest.mark.parametrize("FH,FW,halo,max_h", [(2160, 3840, 20, None), (1080, 1920, 4, None), (41, 41, 20, None), (300, 255, 20, 100),
+                                             (96, 200, 8, 40), (2160, 3840, 20, 540), (17, 1000, 13, None)])
+def test_tiles_cover_frame_once_with_halo(FH, FW, halo, max_h):
+    Ht, Wt, tiles = plan_tiles(2, FH, FW, halo, MAX_PANEL_W, max_h)
+    assert Wt <= MAX_PANEL_W and (max_h is None or Ht <= max_h or FH <= max_h)
+    owner = np.zeros((2, FH, FW), np.int32)
+    for t in tiles:
+        assert 0 <= t.y0 and t.y0 + Ht <= FH and 0 <= t.x0 and t.x0 + Wt <= FW, "tile leaves the frame"
+        owner[t.frame, t.y0 + t.own_y0:t.y0 + t.own_y1, t.x0 + t.own_x0:t.x0 + t.own_x1] += 1
+        # owned pixels are >= halo away from every crop edge that is not a frame edge
+        if t.x0 > 0:
+            assert t.own_x0 >= halo
+        if t.x0 + Wt < FW:
+            assert Wt - t.own_x1 >= halo
+        if t.y0 > 0:
+            assert t.own_y0 >= halo
+        if t.y0 + Ht < FH:
+            assert Ht - t.own_y1 >= halo
+    assert np.all(owner == 1), "every output pixel must be owned by exactly one tile"
+    # sharding is a partition
+    parts = [shard_tiles(tiles, r, 3) for r in range(3)]
+    assert sum(len(p) for p in parts) == len(tiles) and [t for p in parts for t in p] == tiles
+
+
+def test_session_shim_fetch_structures():
+    from ml_super_resolution_b200.session import Handle, Session, placeholder
+
+    class G:
+        def execute(self, keys, feeds):
+            return {k: (k, feeds.get(ph)) for k in keys}
+
+    ph = placeholder([None, 3], "x")
+    g = G()
+    with Session() as s:
+        out = s.run({"a": Handle(g, "a"), "b": [Handle(g, "b"), None]}, feed_dict={ph: 5})
+    assert out == {"a": ("a", 5), "b": [("b", 5), None]}
+
+
+def test_param_arena_roundtrip_cpu():
+    from collections import OrderedDict
+    from ml_super_resolution_b200.params import ParamArena
+    p = OrderedDict([("conv2d/kernel:0", np.arange(54, dtype=np.float32).reshape(3, 3, 3, 2)), ("conv2d/bias:0", np.array([1, 2], np.float32))])
+    a = ParamArena(p, device="cpu")
+    assert a.size % 4 == 0 and all(o % 4 == 0 for o in a.offsets.values())
+    back = a.to_numpy()
+    assert all(np.array_equal(back[k], p[k]) for k in p)
+    assert a.decay_mask.sum() == 54 and a.view("conv2d/bias:0").tolist() == [1, 2]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _dp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import models as OM
+    torch.set_num_threads(1)
+    L = 3
+    params = OM.vdsr_init(seed=5, num_layers=L)
+    sd = OM.synthetic_images(1, 4, 9, 9, 3)
+    hd = OM.synthetic_images(2, 4, 9, 9, 3)
+    lo, hi = rank * 2, rank * 2 + 2
+    # per-rank loss scaled by the GLOBAL element count (what srk_mse_fwd_bwd's numel_total does), no l2 term
+    p = OM._to_t(params, np.float64, requires_grad=True)
+    sr = OM.vdsr_forward_t(p, OM._t(sd[lo:hi], np.float64), L)
+    loss = ((sr - OM._t(hd[lo:hi], np.float64)) ** 2).sum() / sd.size
+    loss.backward()
+    flat = torch.cat([p[k].grad.reshape(-1) for k in params])
+    torch.distributed.all_reduce(flat)  # the one exchange step of data-parallel training
+    ltot = loss.detach().clone()
+    torch.distributed.all_reduce(ltot)
+    if rank == 0:
+        q.put((flat.numpy(), float(ltot)))
+    torch.distributed.destroy_process_group()
+
+
+def test_data_parallel_gradients_equal_single_gpu_gloo():
+    import torch.multiprocessing as mp
+    from oracle import models as OM
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    flat, ltot = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    params = OM.vdsr_init(seed=5, num_layers=3)
+    sd = OM.synthetic_images(1, 4, 9, 9, 3)
+    hd = OM.synthetic_images(2, 4, 9, 9, 3)
+    _, mse, grads, _ = OM.vdsr_loss_and_grads(params, sd, hd, num_layers=3, weight_decay=0.0)
+    ref = np.concatenate([grads[k].reshape(-1) for k in params])
+    assert abs(ltot - mse) < 1e-12
+    assert np.abs(flat - ref).max() < 1e-12
