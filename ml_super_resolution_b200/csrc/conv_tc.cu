@@ -1,19 +1,34 @@
 // Tensor-core convolution between flat-padded activations (FPA, include/srk.h) for sm_100a.
 //
-// A KxK stride-1 SAME convolution over an FPA is K*K shifted GEMMs over ONE flat [rows][CIN] bf16
-// matrix: tap (dy,dx) of output row p reads input row p + dy*Wp + dx, and the zero row/column baked
-// into the layout supplies the padding.  Each persistent CTA owns a contiguous range of 128-row
-// tiles and streams the input through a shared-memory ring of 128-row chunks (one TMA load per
-// chunk => every activation byte crosses L2->SMEM once); the K*K taps are tcgen05.mma instructions
-// whose A descriptors point at row-shifted windows of that ring (probe-verified: SW128/SW64
-// descriptors accept any 128 B / 64 B row shift with base_offset 0).  The weights (K*K blocks of
-// [NP][CIN] bf16, K-major) stay resident in shared memory for the whole kernel.  Accumulators live
-// in TMEM (4 stages) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// A KxK stride-1 SAME convolution over an FPA is a sum of shifted GEMMs over ONE flat [rows][CIN] bf16
+// matrix: tap (dy,dx) of output row p reads input row p + dy*Wp + dx, and the zero row/column baked into
+// the layout supplies the padding.
 //
-//   warp 0     : TMA producer (weights once, then the chunk ring)
-//   warp 1     : TMEM allocator + single-thread tcgen05.mma issuer
-//   warps 2..5 : epilogue (tcgen05.ld -> bias/activation/mask -> bf16 -> swizzled smem -> TMA store,
-//                or fp32 NHWC scatter with residual add / pixel shuffle for the last layer)
+// tcgen05.mma (M=128, SS mode, bf16) costs >= 60 cycles per instruction for any N <= 64 on B200
+// (profiles/r1_mma_rate_vs_N.log), so one instruction per tap would cap the 64->64 layer at 53 % of the
+// tensor pipe.  Instead ONE instruction covers a whole kernel ROW: for each dy the A window starts at
+// p0 - h + dy*Wp (h = K/2) and the B operand is the K taps (dy, -h..h) stacked along N (N = K*NP, e.g. 192).
+// Column block dx of the accumulator then holds the contribution of input row i to output row i - dx, so
+// the epilogue adds the blocks with a LANE SHIFT:  y[j] = sum_dx D[j + dx][block dx]  (warp shuffles, edge
+// lanes exchanged through shared memory).  Tiles therefore advance by 128-(K-1) rows and the K-1 edge
+// lanes of each window are recomputed by the neighbouring tile (1.6 % redundancy for K=3).
+//
+// Each persistent CTA owns a contiguous range of tiles and streams the input through a shared-memory ring
+// of 64-row chunks (one TMA load per chunk: every activation byte crosses L2->SMEM once); the A descriptors
+// are row-shifted windows of that ring (probe-verified: SW128/SW64 descriptors accept any row shift with
+// base_offset 0; the ring's first 128 rows are mirrored behind its last slot so a window never wraps).  The
+// weights (K*K blocks of [NP][CIN] bf16, K-major) stay resident in shared memory.  Accumulators live in
+// TMEM (2-4 stages) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+//   warp 0      : TMA producer (weights once, then the chunk ring)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer
+//   warp 2      : TMA store issuer (waits for a full staging tile, stores it, frees the staging buffer)
+//   warps 4..   : epilogue, 4 warps (one per TMEM lane quadrant) for every 16 output channels, so each
+//                 SM sub-partition interleaves NP/16 epilogue warps and hides the tcgen05.ld / shuffle /
+//                 shared-memory latencies (a single warp per sub-partition left the tensor pipe 80 % idle:
+//                 profiles/r1_ncu_conv_tc_v2.txt): tcgen05.ld -> lane-shift add -> bias/activation/mask ->
+//                 bf16 -> swizzled smem -> TMA store, or fp32 NHWC scatter with residual add / panel crop /
+//                 pixel shuffle
 #include "sm100_ptx.cuh"
 #include "srk_common.cuh"
 
@@ -21,19 +36,18 @@ namespace srk {
 
 enum { EPI_FPA = 0, EPI_NHWC = 1 };
 
-constexpr int kRing = 7;       // chunk slots (plus one mirror slot)
-constexpr int kAccStages = 4;  // TMEM accumulator stages
-constexpr int kConvThreads = 192;
+constexpr int kChunkRows = 64;
+constexpr int kRingSlots = 14;   // ring of 64-row chunks ...
+constexpr int kMirrorSlots = 2;  // ... whose first 128 rows are duplicated behind the last slot
 
 struct alignas(64) ConvTcParams {
-  CUtensorMap map_in;   // [rows_valid][CIN]  box {CIN,128}
-  CUtensorMap map_w;    // [KS*KS*NP][CIN]    box {CIN,NP}
-  CUtensorMap map_out;  // [rows_valid][NP]   box {NP,128}   (EPI_FPA)
+  CUtensorMap map_in;   // [rows_valid][CIN]  box {CIN, 64}
+  CUtensorMap map_w;    // [KS*KS*NP][CIN]    box {CIN, NP}
+  CUtensorMap map_out;  // [rows_valid][NP]   box {NP, 128-(KS-1)}   (EPI_FPA)
   const float* bias;    // [NP] or null
   int n_img, H, W, Wp, S;
   int64_t rows_valid;
   int num_tiles;
-  int nb;  // chunks of look-behind / look-ahead a tile needs: ceil((KS/2)*(Wp+1)/128)
   int act;
   // EPI_FPA extras
   const __nv_bfloat16* mask_src;
@@ -48,22 +62,36 @@ struct alignas(64) ConvTcParams {
 };
 
 template <int CIN, int NP, int KS>
-struct ConvTcSmem {
+struct ConvTcCfg {
   static constexpr int kRowBytes = CIN * 2;
-  static constexpr int kChunkBytes = 128 * kRowBytes;
+  static constexpr int kChunkBytes = kChunkRows * kRowBytes;
   static constexpr int kTaps = KS * KS;
+  static constexpr int kHalo = KS / 2;
+  static constexpr int kTileStride = 128 - (KS - 1);  // output rows per tile
+  static constexpr int kN = KS * NP;                  // MMA N: one kernel row of taps
+  static constexpr int kAccStages = (kN > 128) ? 2 : 4;
+  static constexpr int kTmemColsRaw = kAccStages * kN;
+  static constexpr int kTmemCols = kTmemColsRaw <= 32 ? 32 : kTmemColsRaw <= 64 ? 64 : kTmemColsRaw <= 128 ? 128 : kTmemColsRaw <= 256 ? 256 : 512;
   static constexpr int kWTapBytes = NP * kRowBytes;
   static constexpr int kWBytes = ((kTaps * kWTapBytes + 1023) / 1024) * 1024;
-  static constexpr int kRingBytes = (kRing + 1) * kChunkBytes;
+  static constexpr int kRingBytes = (kRingSlots + kMirrorSlots) * kChunkBytes;
   static constexpr int kStageBytes = 128 * NP * 2;  // output staging (EPI_FPA)
+  static constexpr int kColPass = 16;               // accumulator columns per epilogue thread
+  static constexpr int kGroups = NP / kColPass;     // epilogue column groups (4 warps each)
+  static constexpr int kEpiThreads = 128 * kGroups;
+  static constexpr int kThreads = 128 + kEpiThreads;
+  static constexpr int kXchGroupFloats = 2 /*parity*/ * 4 /*quadrants*/ * (KS > 1 ? (KS - 1) * kHalo : 1) * kColPass;
+  static constexpr int kXchFloats = kXchGroupFloats * kGroups;
   static constexpr int kOffW = 0;
   static constexpr int kOffRing = kWBytes;
   static constexpr int kOffStage = kOffRing + kRingBytes;
   static constexpr int kOffBias = kOffStage + kStageBytes;
-  static constexpr int kOffBars = kOffBias + 256;
-  static constexpr int kNumBars = 2 * kRing + 1 + 2 * kAccStages;
+  static constexpr int kOffXch = kOffBias + 256;
+  static constexpr int kOffBars = kOffXch + ((kXchFloats * 4 + 15) / 16) * 16;
+  static constexpr int kNumBars = 2 * kRingSlots + 1 + 2 * kAccStages + 2;
   static constexpr int kOffTmemSlot = kOffBars + kNumBars * 8;
   static constexpr int kTotal = kOffTmemSlot + 16 + 1024;  // + alignment slack
+  static_assert(kN % 16 == 0 && kN <= 256, "invalid UMMA N");
 };
 
 __device__ __forceinline__ float act_apply(float v, int act) {
@@ -82,14 +110,31 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+// TMEM -> registers: kColPass fp32 columns of this thread's lane
+template <int NCOL>
+__device__ __forceinline__ void tmem_load_cols(uint32_t taddr, float (&v)[NCOL]) {
+  static_assert(NCOL == 32 || NCOL == 16, "column pass must be 16 or 32");
+  if constexpr (NCOL == 32) {
+    uint32_t u[32];
+    tmem_ld_32x32b_x32(taddr, u);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]);
+  } else {
+    uint32_t u[16];
+    tmem_ld_32x32b_x16(taddr, u);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(u[j]);
+  }
+}
 
 template <int CIN, int NP, int KS, int EPI>
-__global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
-  using L = ConvTcSmem<CIN, NP, KS>;
+__global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS>::kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
+  using L = ConvTcCfg<CIN, NP, KS>;
   constexpr uint32_t kLayout = (CIN == 64) ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW64;
   constexpr uint32_t kSbo = 8 * L::kRowBytes;
-  constexpr int kTmemCols = (kAccStages * NP < 32) ? 32 : kAccStages * NP;
-  static_assert((kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns must be a power of two");
+  constexpr int H_ = L::kHalo, TS = L::kTileStride, CP = L::kColPass, ACC = L::kAccStages;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -98,38 +143,45 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
   const uint32_t s_ring = s_base + L::kOffRing;
   uint8_t* stage_ptr = smem + L::kOffStage;
   float* s_bias = reinterpret_cast<float*>(smem + L::kOffBias);
+  float* s_xch = reinterpret_cast<float*>(smem + L::kOffXch);
   const uint32_t s_bars = s_base + L::kOffBars;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmemSlot);
   auto bar_full = [&](int s) { return s_bars + 8u * s; };
-  auto bar_empty = [&](int s) { return s_bars + 8u * (kRing + s); };
-  const uint32_t bar_wfull = s_bars + 8u * (2 * kRing);
-  auto bar_tfull = [&](int a) { return s_bars + 8u * (2 * kRing + 1 + a); };
-  auto bar_tempty = [&](int a) { return s_bars + 8u * (2 * kRing + 1 + kAccStages + a); };
+  auto bar_empty = [&](int s) { return s_bars + 8u * (kRingSlots + s); };
+  const uint32_t bar_wfull = s_bars + 8u * (2 * kRingSlots);
+  auto bar_tfull = [&](int a) { return s_bars + 8u * (2 * kRingSlots + 1 + a); };
+  auto bar_tempty = [&](int a) { return s_bars + 8u * (2 * kRingSlots + 1 + ACC + a); };
+  const uint32_t bar_sfull = s_bars + 8u * (2 * kRingSlots + 1 + 2 * ACC);      // staging tile complete
+  const uint32_t bar_sfree = s_bars + 8u * (2 * kRingSlots + 1 + 2 * ACC + 1);  // staging buffer reusable
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // contiguous tile range of this CTA
+  // contiguous tile range of this CTA; tile t produces output rows [TS*t, TS*t + TS)
   const int t_begin = int((int64_t(blockIdx.x) * p.num_tiles) / gridDim.x);
   const int t_end = int((int64_t(blockIdx.x + 1) * p.num_tiles) / gridDim.x);
-  const int nb = p.nb;
-  const int c0 = t_begin - nb;         // first chunk this CTA loads (may be negative: TMA zero-fills)
-  const int c_last = t_end - 1 + nb;
+  const int reach = H_ * p.Wp;  // rows of vertical reach
+  auto lo_chunk = [&](int t) { return floor_div(TS * t - H_ - reach, kChunkRows); };
+  auto hi_chunk = [&](int t) { return floor_div(TS * t - H_ + reach + 127, kChunkRows); };
+  const int c0 = lo_chunk(t_begin);  // first chunk this CTA loads (may be negative: TMA zero-fills)
+  const int c_last = hi_chunk(t_end - 1);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kRing; ++i) {
+    for (int i = 0; i < kRingSlots; ++i) {
       mbar_init(bar_full(i), 1);
       mbar_init(bar_empty(i), 1);
     }
     mbar_init(bar_wfull, 1);
-    for (int i = 0; i < kAccStages; ++i) {
+    for (int i = 0; i < ACC; ++i) {
       mbar_init(bar_tfull(i), 1);
-      mbar_init(bar_tempty(i), 128);
+      mbar_init(bar_tempty(i), L::kEpiThreads);
     }
+    mbar_init(bar_sfull, L::kEpiThreads);
+    mbar_init(bar_sfree, 1);
     fence_mbar_init();
   }
   if (threadIdx.x < NP) s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
-  if (warp == 1) tmem_alloc<kTmemCols>(smem_u32(tmem_slot));
+  if (warp == 1) tmem_alloc<L::kTmemCols>(smem_u32(tmem_slot));
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.map_in);
     tma_prefetch_desc(&p.map_w);
@@ -147,81 +199,153 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
         mbar_arrive_expect_tx(bar_wfull, L::kTaps * L::kWTapBytes);
         for (int tap = 0; tap < L::kTaps; ++tap) tma_load_2d(s_w + tap * L::kWTapBytes, &p.map_w, 0, tap * NP, bar_wfull);
         for (int c = c0; c <= c_last; ++c) {
-          const int i = c - c0, slot = i % kRing, gen = i / kRing;
+          const int i = c - c0, slot = i % kRingSlots, gen = i / kRingSlots;
           mbar_wait(bar_empty(slot), (gen & 1) ^ 1);
-          mbar_arrive_expect_tx(bar_full(slot), L::kChunkBytes * (slot == 0 ? 2 : 1));
-          tma_load_2d(s_ring + slot * L::kChunkBytes, &p.map_in, 0, c * 128, bar_full(slot));
-          // mirror of slot 0 behind the last slot: a 128-row window starting in slot kRing-1 stays contiguous
-          if (slot == 0) tma_load_2d(s_ring + kRing * L::kChunkBytes, &p.map_in, 0, c * 128, bar_full(slot));
+          const bool mir = slot < kMirrorSlots;
+          mbar_arrive_expect_tx(bar_full(slot), L::kChunkBytes * (mir ? 2 : 1));
+          tma_load_2d(s_ring + slot * L::kChunkBytes, &p.map_in, 0, c * kChunkRows, bar_full(slot));
+          if (mir) tma_load_2d(s_ring + (kRingSlots + slot) * L::kChunkBytes, &p.map_in, 0, c * kChunkRows, bar_full(slot));
         }
       }
     } else if (warp == 1) {
       // ------------------------------------------------------------------ MMA issuer (one thread)
       if (lane == 0) {
-        constexpr uint32_t idesc = umma_idesc_bf16(128, NP, 0, 0);
+        constexpr uint32_t idesc = umma_idesc_bf16(128, L::kN, 0, 0);
         constexpr uint64_t hi = umma_desc_hi(0, kSbo, kLayout);
         mbar_wait(bar_wfull, 0);
-        int loaded = c0 - 1;
+        int loaded = c0 - 1, released = c0;  // chunks <= loaded have landed; chunks < released were handed back
         for (int t = t_begin; t < t_end; ++t) {
-          const int it = t - t_begin, acc = it % kAccStages, accgen = it / kAccStages;
-          while (loaded < t + nb) {
+          const int it = t - t_begin, acc = it % ACC, accgen = it / ACC;
+          const int need = hi_chunk(t);
+          while (loaded < need) {
             ++loaded;
             const int i = loaded - c0;
-            mbar_wait(bar_full(i % kRing), (i / kRing) & 1);
+            mbar_wait(bar_full(i % kRingSlots), (i / kRingSlots) & 1);
           }
           mbar_wait(bar_tempty(acc), (accgen & 1) ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem + acc * NP;
-          const int row0 = (t - c0) * 128;
-#pragma unroll 1
-          for (int tap = 0; tap < L::kTaps; ++tap) {
-            const int dy = tap / KS - KS / 2, dx = tap % KS - KS / 2;
-            const int rr = (row0 + dy * p.Wp + dx) % (kRing * 128);
+          const uint32_t d_tmem = tmem + acc * L::kN;
+          const int row0 = TS * t - H_ - c0 * kChunkRows;  // window start of dy = 0, relative to the ring origin
+#pragma unroll
+          for (int r = 0; r < KS; ++r) {
+            const int rr = (row0 + (r - H_) * p.Wp) % (kRingSlots * kChunkRows);
             const uint32_t a_addr = s_ring + rr * L::kRowBytes;
-            const uint32_t b_addr = s_w + tap * L::kWTapBytes;
+            const uint32_t b_addr = s_w + r * KS * L::kWTapBytes;
 #pragma unroll
             for (int k = 0; k < CIN / 16; ++k)
-              umma_bf16(d_tmem, umma_desc(hi, a_addr + k * 32), umma_desc(hi, b_addr + k * 32), idesc, (tap | k) != 0);
+              umma_bf16(d_tmem, umma_desc(hi, a_addr + k * 32), umma_desc(hi, b_addr + k * 32), idesc, (r | k) != 0);
           }
           umma_commit(bar_tfull(acc));
-          umma_commit(bar_empty(it % kRing));  // chunk t-nb (= c0+it) is no longer needed by later tiles
-        }
-      }
-    } else {
-      // ------------------------------------------------------------------ epilogue (128 threads)
-      const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-      const int row = quad * 32 + lane;
-      const int etid = threadIdx.x - 64;
-      for (int t = t_begin; t < t_end; ++t) {
-        const int it = t - t_begin, acc = it % kAccStages, accgen = it / kAccStages;
-        mbar_wait(bar_tfull(acc), accgen & 1);
-        tc_fence_after();
-        float v[NP];
-        {
-          const uint32_t taddr = tmem + acc * NP + (uint32_t(quad * 32) << 16);
-          if constexpr (NP >= 32) {
-#pragma unroll
-            for (int c = 0; c < NP; c += 32) {
-              uint32_t u[32];
-              tmem_ld_32x32b_x32(taddr + c, u);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[c + j] = __uint_as_float(u[j]);
-            }
-          } else {
-            uint32_t u[16];
-            tmem_ld_32x32b_x16(taddr, u);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(u[j]);
+          // hand back the chunks no later tile needs
+          const int keep_from = (t + 1 < t_end) ? lo_chunk(t + 1) : released;
+          while (released < keep_from) {
+            umma_commit(bar_empty((released - c0) % kRingSlots));
+            ++released;
           }
         }
+      }
+    } else if (warp == 2) {
+      // ------------------------------------------------------------------ TMA store issuer (one thread)
+      if (EPI == EPI_FPA && lane == 0) {
+        for (int t = t_begin; t < t_end; ++t) {
+          const int it = t - t_begin;
+          mbar_wait(bar_sfull, it & 1);
+          tma_store_2d(&p.map_out, 0, TS * t, smem_u32(stage_ptr));
+          tma_store_commit();
+          tma_store_wait_read<0>();  // smem has been read: the staging buffer may be overwritten
+          mbar_arrive(bar_sfree);
+        }
+        tma_store_wait_all<0>();
+      }
+    } else if (warp >= 4) {
+      // ------------------------------------------------------------------ epilogue (128 threads per 16 channels)
+      const int quad = warp & 3;         // TMEM lane quadrant this warp may access
+      const int grp = (warp - 4) >> 2;   // column group: channels [16*grp, 16*grp + 16)
+      const int row = quad * 32 + lane;  // lane j of the accumulator <-> flat row TS*t - h + j
+      const int col0 = grp * CP;
+      const bool lane_valid = (row >= H_) && (row < H_ + TS);
+      float* xg = s_xch + grp * L::kXchGroupFloats;
+      constexpr int kXq = (KS > 1 ? (KS - 1) * H_ : 1) * CP;  // floats per (parity, quadrant)
+      float bias_r[CP];
+#pragma unroll
+      for (int c = 0; c < CP; ++c) bias_r[c] = s_bias[col0 + c];
+      int xpar = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int it = t - t_begin, acc = it % ACC, accgen = it / ACC;
+        mbar_wait(bar_tfull(acc), accgen & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem + acc * L::kN + col0 + (uint32_t(quad * 32) << 16);
+        float blk[KS][CP];
+#pragma unroll
+        for (int b = 0; b < KS; ++b) tmem_load_cols<CP>(taddr + b * NP, blk[b]);
+        tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(bar_tempty(acc));
+        float v[CP];
+        if constexpr (KS > 1) {
+          // ---- lane-shift add of the KS column blocks: y[j] = sum_dx D[j + dx][block dx]
+          // edge lanes publish what the neighbouring quadrants need: block dx<0 from the top lanes, dx>0 from the bottom lanes
+          float* xq = xg + (xpar * 4 + quad) * kXq;
+#pragma unroll
+          for (int b = 0; b < KS; ++b) {
+            const int dx = b - H_;
+            const int bi = (dx < 0) ? b : b - 1;  // index among the KS-1 shifted blocks
+            if (dx < 0 && lane >= 32 + dx) {
+              float4* dst = reinterpret_cast<float4*>(xq + (bi * H_ + (lane - (32 + dx))) * CP);
+#pragma unroll
+              for (int c = 0; c < CP / 4; ++c) dst[c] = make_float4(blk[b][4 * c], blk[b][4 * c + 1], blk[b][4 * c + 2], blk[b][4 * c + 3]);
+            }
+            if (dx > 0 && lane < dx) {
+              float4* dst = reinterpret_cast<float4*>(xq + (bi * H_ + lane) * CP);
+#pragma unroll
+              for (int c = 0; c < CP / 4; ++c) dst[c] = make_float4(blk[b][4 * c], blk[b][4 * c + 1], blk[b][4 * c + 2], blk[b][4 * c + 3]);
+            }
+          }
+          named_bar_sync(1 + grp, 128);
+#pragma unroll
+          for (int c = 0; c < CP; ++c) v[c] = blk[H_][c];
+#pragma unroll
+          for (int b = 0; b < KS; ++b) {
+            const int dx = b - H_;
+            if (dx == 0) continue;
+            const int bi = (dx < 0) ? b : b - 1;
+            // lanes whose source row lives in the neighbouring quadrant take it from the exchange buffer; the
+            // value is SELECTED, not patched in, so every output sees the same fp32 addition order
+            // (tiled == un-tiled bit for bit)
+            const bool edge = (dx < 0) ? (lane < -dx) : (lane >= 32 - dx);
+            float ev[CP];
+#pragma unroll
+            for (int c = 0; c < CP; ++c) ev[c] = 0.f;
+            if (edge) {
+              const int nq = (dx < 0) ? quad - 1 : quad + 1;
+              const int li = (dx < 0) ? lane : lane - (32 - dx);
+              if (nq >= 0 && nq < 4) {
+                const float4* src = reinterpret_cast<const float4*>(xg + (xpar * 4 + nq) * kXq + (bi * H_ + li) * CP);
+#pragma unroll
+                for (int c = 0; c < CP / 4; ++c) {
+                  const float4 o = src[c];
+                  ev[4 * c] = o.x;
+                  ev[4 * c + 1] = o.y;
+                  ev[4 * c + 2] = o.z;
+                  ev[4 * c + 3] = o.w;
+                }
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < CP; ++c) {
+              const float sh = (dx < 0) ? __shfl_up_sync(0xffffffffu, blk[b][c], -dx) : __shfl_down_sync(0xffffffffu, blk[b][c], dx);
+              v[c] += edge ? ev[c] : sh;
+            }
+          }
+          xpar ^= 1;
+        } else {
+#pragma unroll
+          for (int c = 0; c < CP; ++c) v[c] = blk[0][c];
+        }
 
-        // decode the pixel this row holds
-        const int64_t prow = int64_t(t) * 128 + row;
-        bool valid = prow < p.rows_valid;
+        // decode the pixel this lane holds
+        const int64_t prow = int64_t(TS) * t - H_ + row;
+        bool valid = lane_valid && prow >= 0 && prow < p.rows_valid;
         int n = 0, y = 0, x = 0;
         if (valid) {
           const uint32_t pr = uint32_t(prow);
@@ -234,14 +358,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
         }
 
         if constexpr (EPI == EPI_FPA) {
-          uint32_t packed[NP / 2];
+          uint32_t packed[CP / 2];
           if (valid) {
 #pragma unroll
-            for (int c = 0; c < NP; ++c) v[c] = act_apply(v[c] + s_bias[c], p.act);
+            for (int c = 0; c < CP; ++c) v[c] = act_apply(v[c] + bias_r[c], p.act);
             if (p.mask_src) {
-              const uint4* m = reinterpret_cast<const uint4*>(p.mask_src + size_t(prow) * NP);
+              const uint4* m = reinterpret_cast<const uint4*>(p.mask_src + size_t(prow) * NP + col0);
 #pragma unroll
-              for (int j = 0; j < NP / 8; ++j) {
+              for (int j = 0; j < CP / 8; ++j) {
                 const uint4 mv = __ldg(m + j);
                 const uint32_t w4[4] = {mv.x, mv.y, mv.z, mv.w};
 #pragma unroll
@@ -258,9 +382,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
               }
             }
             if (p.addend_fpa) {
-              const uint4* a = reinterpret_cast<const uint4*>(p.addend_fpa + size_t(prow) * NP);
+              const uint4* a = reinterpret_cast<const uint4*>(p.addend_fpa + size_t(prow) * NP + col0);
 #pragma unroll
-              for (int j = 0; j < NP / 8; ++j) {
+              for (int j = 0; j < CP / 8; ++j) {
                 const uint4 av = __ldg(a + j);
                 const uint32_t w4[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
@@ -272,31 +396,30 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
               }
               if (p.relu_after_add) {
 #pragma unroll
-                for (int c = 0; c < NP; ++c) v[c] = fmaxf(v[c], 0.f);
+                for (int c = 0; c < CP; ++c) v[c] = fmaxf(v[c], 0.f);
               }
             }
 #pragma unroll
-            for (int c = 0; c < NP / 2; ++c) packed[c] = pack_bf16x2(v[2 * c], v[2 * c + 1]);
+            for (int c = 0; c < CP / 2; ++c) packed[c] = pack_bf16x2(v[2 * c], v[2 * c + 1]);
           } else {
 #pragma unroll
-            for (int c = 0; c < NP / 2; ++c) packed[c] = 0u;  // pad rows/columns stay exactly zero
+            for (int c = 0; c < CP / 2; ++c) packed[c] = 0u;  // pad rows/columns stay exactly zero
           }
-          // staging buffer free? (previous tile's TMA store finished reading it)
-          if (etid == 0) tma_store_wait_read<0>();
-          named_bar_sync(1, 128);
-          constexpr int kOutRowBytes = NP * 2;
-          const int sw = (NP == 64) ? (row & 7) : ((row >> 1) & 3);
+          // staging buffer free? (the store of the previous tile has finished reading it)
+          mbar_wait(bar_sfree, (it & 1) ^ 1);
+          if (lane_valid) {
+            constexpr int kOutRowBytes = NP * 2;
+            const int srow = row - H_;  // staging row = output row within the tile
+            const int sw = (NP == 64) ? (srow & 7) : ((srow >> 1) & 3);
 #pragma unroll
-          for (int j = 0; j < NP / 8; ++j) {
-            uint4 q4 = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-            *reinterpret_cast<uint4*>(stage_ptr + row * kOutRowBytes + ((j ^ sw) << 4)) = q4;
+            for (int j = 0; j < CP / 8; ++j) {
+              const int chunk = grp * (CP / 8) + j;  // 16-byte chunk index within the output row
+              uint4 q4 = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+              *reinterpret_cast<uint4*>(stage_ptr + srow * kOutRowBytes + ((chunk ^ sw) << 4)) = q4;
+            }
           }
           fence_proxy_async_smem();
-          named_bar_sync(2, 128);
-          if (etid == 0) {
-            tma_store_2d(&p.map_out, 0, t * 128, smem_u32(stage_ptr));
-            tma_store_commit();
-          }
+          mbar_arrive(bar_sfull);
         } else {
           // fp32 NHWC scatter: residual add, panel crop, depth_to_space
           if (valid) {
@@ -313,12 +436,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
               const int64_t OW = int64_t(p.FW) * r;
               const int64_t base = (int64_t(fn) * p.FH * r + int64_t(fy) * r) * OW + int64_t(fx) * r;
 #pragma unroll
-              for (int c = 0; c < NP; ++c) {
-                if (c < p.cout) {
-                  const int ch = c % C, sub = c / C;
+              for (int c = 0; c < CP; ++c) {
+                const int cc = col0 + c;
+                if (cc < p.cout) {
+                  const int ch = cc % C, sub = cc / C;
                   const int ddy = sub / r, ddx = sub - ddy * r;
                   const int64_t idx = (base + int64_t(ddy) * OW + ddx) * C + ch;
-                  float o = act_apply(v[c] + s_bias[c], p.act);
+                  float o = act_apply(v[c] + bias_r[c], p.act);
                   if (p.addend) o += __ldg(p.addend + idx);
                   p.out[idx] = o;
                 }
@@ -327,51 +451,49 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
           }
         }
       }
-      if (EPI == EPI_FPA && etid == 0) tma_store_wait_all<0>();
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<kTmemCols>(tmem);
+  if (warp == 1) tmem_dealloc<L::kTmemCols>(tmem);
 }
 
 // --------------------------------------------------------------------------------------- host side
 template <int CIN, int NP, int KS, int EPI>
-static int launch_conv_tc(srk_ctx* h, ConvTcParams& p, const void* x, const void* w_packed, void* y_fpa,
-                          cudaStream_t stream) {
-  using L = ConvTcSmem<CIN, NP, KS>;
+static int launch_conv_tc(srk_ctx* h, ConvTcParams& p, const void* x, const void* w_packed, void* y_fpa, cudaStream_t stream) {
+  using L = ConvTcCfg<CIN, NP, KS>;
   static bool attr_set = false;
+  SRK_REQUIRE(L::kTotal <= h->smem_optin, "conv_tc: needs %d B smem, device allows %d", L::kTotal, h->smem_optin);
   if (!attr_set) {
     SRK_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<CIN, NP, KS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     attr_set = true;
   }
-  SRK_REQUIRE(L::kTotal <= h->smem_optin, "conv_tc: needs %d B smem, device allows %d", L::kTotal, h->smem_optin);
-  if (int rc = make_tensor_map_2d(&p.map_in, x, uint64_t(p.rows_valid), CIN, 128)) return rc;
+  p.num_tiles = int((p.rows_valid + L::kTileStride - 1) / L::kTileStride);
+  const int span_chunks = (2 * L::kHalo * p.Wp + 128 + kChunkRows - 1) / kChunkRows + 1;
+  SRK_REQUIRE(span_chunks <= kRingSlots - 2,
+              "conv_tc: image width %d too large for the %dx%d flat-stream kernel (a tile needs %d chunks, ring holds %d); "
+              "split the frame into column panels", p.W, KS, KS, span_chunks, kRingSlots);
+  if (int rc = make_tensor_map_2d(&p.map_in, x, uint64_t(p.rows_valid), CIN, kChunkRows)) return rc;
   if (int rc = make_tensor_map_2d(&p.map_w, w_packed, uint64_t(KS * KS * NP), CIN, NP)) return rc;
   if (EPI == EPI_FPA) {
-    if (int rc = make_tensor_map_2d(&p.map_out, y_fpa, uint64_t(p.rows_valid), NP, 128)) return rc;
+    if (int rc = make_tensor_map_2d(&p.map_out, y_fpa, uint64_t(p.rows_valid), NP, L::kTileStride)) return rc;
   }
   const int grid = p.num_tiles < h->num_sms ? p.num_tiles : h->num_sms;
-  conv_tc_kernel<CIN, NP, KS, EPI><<<grid, kConvThreads, L::kTotal, stream>>>(p);
+  conv_tc_kernel<CIN, NP, KS, EPI><<<grid, L::kThreads, L::kTotal, stream>>>(p);
   SRK_LAUNCH_CHECK();
   return 0;
 }
 
-static int fill_geom(ConvTcParams& p, int n_img, int H, int W, int k) {
+static int fill_geom(ConvTcParams& p, int n_img, int H, int W) {
   SRK_REQUIRE(n_img > 0 && H > 0 && W > 0, "conv_tc: bad geometry n_img=%d H=%d W=%d", n_img, H, W);
   const FpaGeom g = fpa_geom(n_img, H, W);
-  SRK_REQUIRE(g.rows_valid < (int64_t(1) << 31), "conv_tc: %lld rows exceed the 2^31 row limit", (long long)g.rows_valid);
+  SRK_REQUIRE(g.rows_valid < (int64_t(1) << 30), "conv_tc: %lld rows exceed the 2^30 row limit", (long long)g.rows_valid);
   p.n_img = n_img;
   p.H = H;
   p.W = W;
   p.Wp = g.Wp;
   p.S = g.S;
   p.rows_valid = g.rows_valid;
-  p.num_tiles = int((g.rows_valid + 127) / 128);
-  const int reach = (k / 2) * (g.Wp + 1);
-  p.nb = (reach + 127) / 128;
-  SRK_REQUIRE(2 * p.nb + 2 <= kRing, "conv_tc: image width %d too large for the %dx%d flat-stream kernel (reach %d rows > %d); "
-              "split the frame into column panels", W, k, k, reach, ((kRing - 2) / 2) * 128);
   return 0;
 }
 
@@ -384,7 +506,7 @@ extern "C" int srk_conv_tc(srk_handle_t h, const void* x_fpa, int cin_p, const v
                            int mask_kind, const void* addend_fpa, int relu_after_add, srk_stream_t stream) {
   SRK_REQUIRE(h && x_fpa && w_packed && y_fpa, "srk_conv_tc: null argument");
   ConvTcParams p{};
-  if (int rc = fill_geom(p, n_img, H, W, k)) return rc;
+  if (int rc = fill_geom(p, n_img, H, W)) return rc;
   p.bias = bias;
   p.act = act;
   p.mask_src = static_cast<const __nv_bfloat16*>(mask_src);
@@ -415,7 +537,7 @@ extern "C" int srk_conv_tc_last(srk_handle_t h, const void* x_fpa, int cin_p, co
   SRK_REQUIRE(cout <= cout_p, "srk_conv_tc_last: cout %d > cout_p %d", cout, cout_p);
   SRK_REQUIRE(panels || (n_frames == n_img && FH == H && FW == W), "srk_conv_tc_last: without panels the frame must equal the FPA geometry");
   ConvTcParams p{};
-  if (int rc = fill_geom(p, n_img, H, W, k)) return rc;
+  if (int rc = fill_geom(p, n_img, H, W)) return rc;
   p.bias = bias;
   p.act = act;
   p.out = out;
