@@ -231,8 +231,10 @@ def vdsr_train_workload(args, rank, world):
     scales = torch.tensor([2.0, 3.0, 4.0], device="cuda")[torch.arange(TRAIN_BATCH, device="cuda") % 3]
     sd = ((ops.degrade_gauss_bilinear(hd * 0.5 + 0.5, scales)) * 2 - 1).contiguous()
 
+    gstep = net.make_graphed_step(sd, hd)  # CUDA-graph replay of the identical kernel sequence (fwd+loss+bwd | all-reduce | Adam+repack)
+
     def step():
-        net.train_step(sd, hd, lr=5e-5, use_adam=True)
+        gstep(5e-5)
 
     ms, clocks = timed_steps(step, args.steps, args.warmup, world, ClockSampler(torch.cuda.current_device()) if rank == 0 else None)
     value = TRAIN_BATCH * world * args.steps / ms * 1e3
@@ -241,13 +243,15 @@ def vdsr_train_workload(args, rank, world):
     tf = value * flops_per_patch / 1e12 / world
     roofline = {"bound": "tensor", "kernel": "whole training step (18x fwd/dgrad/wgrad tcgen05 convs dominate)", "achieved": round(tf, 1),
                 "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": round(tf / pk["tf_sust"], 4), "traffic": None, "peak_source": pk["src"]}
-    n_launch = launches_of(step) * args.steps
+    n_launch = launches_of(lambda: net.train_step(sd, hd, lr=5e-5, use_adam=True)) * args.steps  # same kernels the graphs replay
     sd_h, hd_h = sd.cpu().pin_memory(), hd.cpu().pin_memory()
+    loss_h = torch.zeros(2).pin_memory()
 
     def e2e_step():
-        s, h = sd_h.to("cuda", non_blocking=True), hd_h.to("cuda", non_blocking=True)
-        loss = net.train_step(s, h, lr=5e-5, use_adam=True)
-        loss.item()  # device->host read of the step's loss
+        sd.copy_(sd_h, non_blocking=True)  # host batch -> the graph's static input buffers
+        hd.copy_(hd_h, non_blocking=True)
+        loss_h.copy_(gstep(5e-5), non_blocking=True)  # device->host read of the step's loss
+        torch.cuda.current_stream().synchronize()
 
     ms_e, _ = timed_steps(e2e_step, max(2, args.steps // 2), 2, world, None)
     e2e = {"value": round(TRAIN_BATCH * world * max(2, args.steps // 2) / ms_e * 1e3, 1), "unit": "patches/s",

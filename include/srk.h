@@ -130,6 +130,12 @@ size_t srk_conv_wgrad_tc_workspace_bytes(srk_handle_t h, int n_img, int H, int W
 int srk_conv_wgrad_tc(srk_handle_t h, const void* x_fpa, const void* dy_fpa, int n_img, int H, int W,
                       float* dw_hwio, float* dbias, int accumulate, void* workspace, size_t workspace_bytes,
                       srk_stream_t stream);
+/* Deferred form: call srk_conv_wgrad_tc with dw_hwio = NULL for each of n_layers layers, each with its own
+ * workspace slice `workspace_base + l * layer_stride_bytes`, then fold all of them with ONE launch.
+ * dw_ptrs_device / db_ptrs_device: device arrays of n_layers destination pointers. */
+int srk_wgrad_reduce_many(srk_handle_t h, const void* workspace_base, size_t layer_stride_bytes, int n_layers,
+                          int n_img, int H, int W, float* const* dw_ptrs_device, float* const* db_ptrs_device,
+                          int accumulate, srk_stream_t stream);
 
 /* Weight gradient of the first layer (x fp32 NHWC cin<=4, dy FPA 64ch) -> dw [k,k,cin,64], db[64]. */
 int srk_conv_first_wgrad(srk_handle_t h, const float* x, int n_img, int H, int W, int cin, int k,

@@ -44,6 +44,7 @@ SIGNATURES = {
     "srk_conv_tc_last": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P]),
     "srk_conv_wgrad_tc_workspace_bytes": (_SZ, [_P, _I, _I, _I]),
     "srk_conv_wgrad_tc": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _SZ, _P]),
+    "srk_wgrad_reduce_many": (_I, [_P, _P, _SZ, _I, _I, _I, _I, _P, _P, _I, _P]),
     "srk_conv_first_wgrad": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "srk_conv_last_wgrad": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "srk_pixel_shuffle": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
@@ -80,7 +81,7 @@ def lib() -> C.CDLL:
 KERNELS_PER_CALL = {name: 1 for name in SIGNATURES if name not in
                     ("srk_version", "srk_last_error", "srk_create", "srk_destroy", "srk_num_sms", "srk_fpa_rows",
                      "srk_conv_wgrad_tc_workspace_bytes")}
-KERNELS_PER_CALL["srk_conv_wgrad_tc"] = 2
+KERNELS_PER_CALL["srk_conv_wgrad_tc"] = 1  # +1 when it also runs the reduce (counted as srk_wgrad_reduce_many otherwise)
 launch_count = 0
 
 

@@ -235,14 +235,14 @@ __global__ void nhwc_to_fpa_kernel(const float* __restrict__ x, int C, int n_img
 }
 
 // ------------------------------------------------------------------------------------ first/last layer wgrad
-// Both are tiny contractions (k*k*cin*64 <= 15.5k outputs, reduction over every pixel).  256 threads =
-// 64 channels x 4 pixel lanes; each thread keeps its k*k*c partial sums in registers while the block walks
-// its pixel slice, then the 4 pixel lanes are folded through shared memory and one fp32 atomic per
+// Both are tiny contractions (k*k*cin*64 <= 15.5k outputs, reduction over every pixel).  1024 threads =
+// 64 channels x 16 pixel lanes; each thread keeps its k*k*c partial sums in registers while the block walks
+// its pixel slice, then the 16 pixel lanes are folded through shared memory and one fp32 atomic per
 // output and block goes to global (caller zeroes dw/db).
 //
 // First layer: dw[u][v][ci][co] = sum_{n,y,x} x[n, y+u-po, x+v-po, ci] * dy[n,y,x,co];  db[co] = sum dy.
 template <int KS, int CIN>
-__global__ void __launch_bounds__(256) conv_first_wgrad_kernel(const float* __restrict__ x, int n_img, int H, int W,
+__global__ void __launch_bounds__(1024) conv_first_wgrad_kernel(const float* __restrict__ x, int n_img, int H, int W,
                                                                const __nv_bfloat16* __restrict__ dy, float* __restrict__ dw,
                                                                float* __restrict__ db) {
   constexpr int kAcc = KS * KS * CIN + 1;  // + bias
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(256) conv_first_wgrad_kernel(const float* __re
   float acc[kAcc];
 #pragma unroll
   for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
-  for (int64_t pix = p0 + pl; pix < p1; pix += 4) {
+  for (int64_t pix = p0 + pl; pix < p1; pix += 16) {
     const int xx = int(pix % W);
     const int yy = int((pix / W) % H);
     const int64_t n = pix / (int64_t(W) * H);
@@ -277,13 +277,15 @@ __global__ void __launch_bounds__(256) conv_first_wgrad_kernel(const float* __re
       }
     }
   }
-  __shared__ float red[4][64];
+  __shared__ float red[16][64];
 #pragma unroll 1
   for (int i = 0; i < kAcc; ++i) {
     red[pl][co] = acc[i];
     __syncthreads();
     if (pl == 0) {
-      const float t = (red[0][co] + red[1][co]) + (red[2][co] + red[3][co]);
+      float t = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) t += red[j][co];
       if (i == kAcc - 1) atomicAdd(db + co, t);
       else atomicAdd(dw + i * 64 + co, t);
     }
@@ -293,7 +295,7 @@ __global__ void __launch_bounds__(256) conv_first_wgrad_kernel(const float* __re
 
 // Last layer: dw[u][v][ci][co] = sum_p x_fpa[p + (u-1)Wp + (v-1)][ci] * dy[p][co], co < COUT <= 4; db[co] = sum dy.
 template <int COUT>
-__global__ void __launch_bounds__(256) conv_last_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ dy,
+__global__ void __launch_bounds__(1024) conv_last_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ dy,
                                                               int n_img, int H, int W, float* __restrict__ dw, float* __restrict__ db) {
   constexpr int kAcc = 9 * COUT;
   const int ci = threadIdx.x & 63, pl = threadIdx.x >> 6;
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(256) conv_last_wgrad_kernel(const __nv_bfloat1
   for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
 #pragma unroll
   for (int i = 0; i < COUT; ++i) bacc[i] = 0.f;
-  for (int64_t pix = p0 + pl; pix < p1; pix += 4) {
+  for (int64_t pix = p0 + pl; pix < p1; pix += 16) {
     const int xx = int(pix % W);
     const int yy = int((pix / W) % H);
     const int64_t n = pix / (int64_t(W) * H);
@@ -328,13 +330,15 @@ __global__ void __launch_bounds__(256) conv_last_wgrad_kernel(const __nv_bfloat1
       for (int co = 0; co < COUT; ++co) acc[tap * COUT + co] = fmaf(xv, g[co], acc[tap * COUT + co]);
     }
   }
-  __shared__ float red[4][64];
+  __shared__ float red[16][64];
 #pragma unroll 1
   for (int i = 0; i < kAcc; ++i) {
     red[pl][ci] = acc[i];
     __syncthreads();
     if (pl == 0) {
-      const float t = (red[0][ci] + red[1][ci]) + (red[2][ci] + red[3][ci]);
+      float t = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) t += red[j][ci];
       const int tap = i / COUT, co = i % COUT;
       atomicAdd(dw + (tap * 64 + ci) * COUT + co, t);
     }
@@ -420,12 +424,12 @@ extern "C" int srk_conv_first_wgrad(srk_handle_t h, const float* x, int n_img, i
                                     float* dw_hwio, float* dbias, srk_stream_t stream) {
   SRK_REQUIRE(h && x && dy_fpa && dw_hwio && dbias, "srk_conv_first_wgrad: null argument");
   const int64_t npix = int64_t(n_img) * H * W;
-  const int grid = int(std::min<int64_t>((npix + 63) / 64, int64_t(h->num_sms) * 4));
+  const int grid = int(std::min<int64_t>((npix + 63) / 64, int64_t(h->num_sms)));
   const __nv_bfloat16* dy = static_cast<const __nv_bfloat16*>(dy_fpa);
   cudaStream_t s = as_stream(stream);
 #define SRK_CASE(KS, CIN)                                                                           \
   if (k == KS && cin == CIN) {                                                                      \
-    conv_first_wgrad_kernel<KS, CIN><<<grid, 256, 0, s>>>(x, n_img, H, W, dy, dw_hwio, dbias);      \
+    conv_first_wgrad_kernel<KS, CIN><<<grid, 1024, 0, s>>>(x, n_img, H, W, dy, dw_hwio, dbias);      \
     SRK_LAUNCH_CHECK();                                                                             \
     return 0;                                                                                       \
   }
@@ -439,12 +443,12 @@ extern "C" int srk_conv_last_wgrad(srk_handle_t h, const void* x_fpa, const floa
                                    float* dw_hwio, float* dbias, srk_stream_t stream) {
   SRK_REQUIRE(h && x_fpa && dy && dw_hwio && dbias, "srk_conv_last_wgrad: null argument");
   const int64_t npix = int64_t(n_img) * H * W;
-  const int grid = int(std::min<int64_t>((npix + 63) / 64, int64_t(h->num_sms) * 4));
+  const int grid = int(std::min<int64_t>((npix + 63) / 64, int64_t(h->num_sms)));
   const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(x_fpa);
   cudaStream_t s = as_stream(stream);
 #define SRK_CASE(COUT)                                                                       \
   if (cout == COUT) {                                                                        \
-    conv_last_wgrad_kernel<COUT><<<grid, 256, 0, s>>>(x, dy, n_img, H, W, dw_hwio, dbias);   \
+    conv_last_wgrad_kernel<COUT><<<grid, 1024, 0, s>>>(x, dy, n_img, H, W, dw_hwio, dbias);   \
     SRK_LAUNCH_CHECK();                                                                      \
     return 0;                                                                                \
   }

@@ -76,8 +76,8 @@ struct ConvTcCfg {
   static constexpr int kWBytes = ((kTaps * kWTapBytes + 1023) / 1024) * 1024;
   static constexpr int kRingBytes = (kRingSlots + kMirrorSlots) * kChunkBytes;
   static constexpr int kStageBytes = 128 * NP * 2;  // output staging (EPI_FPA)
-  static constexpr int kColPass = 16;               // accumulator columns per epilogue thread
-  static constexpr int kGroups = NP / kColPass;     // epilogue column groups (4 warps each)
+  static constexpr int kGroups = 4;                 // epilogue column groups (4 warps each): 16 epilogue warps
+  static constexpr int kColPass = NP / kGroups;     // accumulator columns per epilogue thread (16 / 8 / 4)
   static constexpr int kEpiThreads = 128 * kGroups;
   static constexpr int kThreads = 128 + kEpiThreads;
   static constexpr int kXchGroupFloats = 2 /*parity*/ * 4 /*quadrants*/ * (KS > 1 ? (KS - 1) * kHalo : 1) * kColPass;
@@ -86,7 +86,8 @@ struct ConvTcCfg {
   static constexpr int kOffRing = kWBytes;
   static constexpr int kOffStage = kOffRing + kRingBytes;
   static constexpr int kOffBias = kOffStage + kStageBytes;
-  static constexpr int kOffXch = kOffBias + 256;
+  static constexpr int kOffTab = kOffBias + 256;    // NHWC epilogue: per-channel output offsets
+  static constexpr int kOffXch = kOffTab + 256;
   static constexpr int kOffBars = kOffXch + ((kXchFloats * 4 + 15) / 16) * 16;
   static constexpr int kNumBars = 2 * kRingSlots + 1 + 2 * kAccStages + 2;
   static constexpr int kOffTmemSlot = kOffBars + kNumBars * 8;
@@ -115,18 +116,13 @@ __device__ __forceinline__ int floor_div(int a, int b) { return (a >= 0) ? a / b
 // TMEM -> registers: kColPass fp32 columns of this thread's lane
 template <int NCOL>
 __device__ __forceinline__ void tmem_load_cols(uint32_t taddr, float (&v)[NCOL]) {
-  static_assert(NCOL == 32 || NCOL == 16, "column pass must be 16 or 32");
-  if constexpr (NCOL == 32) {
-    uint32_t u[32];
-    tmem_ld_32x32b_x32(taddr, u);
+  static_assert(NCOL == 16 || NCOL == 8 || NCOL == 4, "column pass must be 4, 8 or 16");
+  uint32_t u[NCOL];
+  if constexpr (NCOL == 16) tmem_ld_32x32b_x16(taddr, u);
+  else if constexpr (NCOL == 8) tmem_ld_32x32b_x8(taddr, u);
+  else tmem_ld_32x32b_x4(taddr, u);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]);
-  } else {
-    uint32_t u[16];
-    tmem_ld_32x32b_x16(taddr, u);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(u[j]);
-  }
+  for (int j = 0; j < NCOL; ++j) v[j] = __uint_as_float(u[j]);
 }
 
 template <int CIN, int NP, int KS, int EPI>
@@ -143,6 +139,7 @@ __global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS>::kThreads, 1) conv_tc_k
   const uint32_t s_ring = s_base + L::kOffRing;
   uint8_t* stage_ptr = smem + L::kOffStage;
   float* s_bias = reinterpret_cast<float*>(smem + L::kOffBias);
+  int* s_tab = reinterpret_cast<int*>(smem + L::kOffTab);
   float* s_xch = reinterpret_cast<float*>(smem + L::kOffXch);
   const uint32_t s_bars = s_base + L::kOffBars;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmemSlot);
@@ -181,6 +178,16 @@ __global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS>::kThreads, 1) conv_tc_k
     fence_mbar_init();
   }
   if (threadIdx.x < NP) s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
+  if (EPI == EPI_NHWC && threadIdx.x < NP) {
+    // output offset of packed channel c relative to pixel (Y*r, X*r, 0): depth_to_space index, -1 = padding channel
+    const int c = threadIdx.x, r = p.shuffle_r, C = p.cout / (r * r);
+    int off = -1;
+    if (c < p.cout) {
+      const int ch = c % C, sub = c / C, ddy = sub / r, ddx = sub - ddy * r;
+      off = (ddy * p.FW * r + ddx) * C + ch;
+    }
+    s_tab[c] = off;
+  }
   if (warp == 1) tmem_alloc<L::kTmemCols>(smem_u32(tmem_slot));
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.map_in);
@@ -267,9 +274,26 @@ __global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS>::kThreads, 1) conv_tc_k
       float* xg = s_xch + grp * L::kXchGroupFloats;
       constexpr int kXq = (KS > 1 ? (KS - 1) * H_ : 1) * CP;  // floats per (parity, quadrant)
       float bias_r[CP];
+      int tab_r[CP];
 #pragma unroll
-      for (int c = 0; c < CP; ++c) bias_r[c] = s_bias[col0 + c];
+      for (int c = 0; c < CP; ++c) {
+        bias_r[c] = s_bias[col0 + c];
+        tab_r[c] = (EPI == EPI_NHWC) ? s_tab[col0 + c] : 0;
+      }
       int xpar = 0;
+      // pixel coordinates of this lane's row in the first tile; lanes below the halo never hold a valid output
+      const int H1 = p.H + 1;
+      int px, pyy, pn;
+      {
+        const int64_t prow0 = int64_t(TS) * t_begin - H_ + row;
+        const uint32_t pr = uint32_t(prow0 < 0 ? 0 : prow0);
+        const uint32_t q = pr / uint32_t(p.Wp);
+        px = int(pr - q * uint32_t(p.Wp));
+        pn = int(q / uint32_t(H1));
+        pyy = int(q - uint32_t(pn) * uint32_t(H1));
+      }
+      const int adv_x = TS % p.Wp, adv_q = TS / p.Wp;
+      const int adv_y = adv_q % H1, adv_n = adv_q / H1;
       for (int t = t_begin; t < t_end; ++t) {
         const int it = t - t_begin, acc = it % ACC, accgen = it / ACC;
         mbar_wait(bar_tfull(acc), accgen & 1);
@@ -302,40 +326,38 @@ __global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS>::kThreads, 1) conv_tc_k
             }
           }
           named_bar_sync(1 + grp, 128);
+          // lanes whose shuffle would wrap around the warp first take over the neighbouring quadrant's row
+          // (their own value of that block is not needed any more), then ONE rotating shuffle per column
+          // serves every lane -- no per-element select, and every output sees the same fp32 addition order
+#pragma unroll
+          for (int b = 0; b < KS; ++b) {
+            const int dx = b - H_;
+            if (dx == 0) continue;
+            const int bi = (dx < 0) ? b : b - 1;
+            const bool edge = (dx < 0) ? (lane >= 32 + dx) : (lane < dx);
+            const int nq = (dx < 0) ? quad - 1 : quad + 1;
+            if (edge && nq >= 0 && nq < 4) {
+              const int li = (dx < 0) ? lane - (32 + dx) : lane;
+              const float4* src = reinterpret_cast<const float4*>(xg + (xpar * 4 + nq) * kXq + (bi * H_ + li) * CP);
+#pragma unroll
+              for (int c = 0; c < CP / 4; ++c) {
+                const float4 o = src[c];
+                blk[b][4 * c] = o.x;
+                blk[b][4 * c + 1] = o.y;
+                blk[b][4 * c + 2] = o.z;
+                blk[b][4 * c + 3] = o.w;
+              }
+            }
+          }
 #pragma unroll
           for (int c = 0; c < CP; ++c) v[c] = blk[H_][c];
 #pragma unroll
           for (int b = 0; b < KS; ++b) {
             const int dx = b - H_;
             if (dx == 0) continue;
-            const int bi = (dx < 0) ? b : b - 1;
-            // lanes whose source row lives in the neighbouring quadrant take it from the exchange buffer; the
-            // value is SELECTED, not patched in, so every output sees the same fp32 addition order
-            // (tiled == un-tiled bit for bit)
-            const bool edge = (dx < 0) ? (lane < -dx) : (lane >= 32 - dx);
-            float ev[CP];
+            const int src_lane = (lane + dx) & 31;  // y[j] += D[j + dx][block dx]
 #pragma unroll
-            for (int c = 0; c < CP; ++c) ev[c] = 0.f;
-            if (edge) {
-              const int nq = (dx < 0) ? quad - 1 : quad + 1;
-              const int li = (dx < 0) ? lane : lane - (32 - dx);
-              if (nq >= 0 && nq < 4) {
-                const float4* src = reinterpret_cast<const float4*>(xg + (xpar * 4 + nq) * kXq + (bi * H_ + li) * CP);
-#pragma unroll
-                for (int c = 0; c < CP / 4; ++c) {
-                  const float4 o = src[c];
-                  ev[4 * c] = o.x;
-                  ev[4 * c + 1] = o.y;
-                  ev[4 * c + 2] = o.z;
-                  ev[4 * c + 3] = o.w;
-                }
-              }
-            }
-#pragma unroll
-            for (int c = 0; c < CP; ++c) {
-              const float sh = (dx < 0) ? __shfl_up_sync(0xffffffffu, blk[b][c], -dx) : __shfl_down_sync(0xffffffffu, blk[b][c], dx);
-              v[c] += edge ? ev[c] : sh;
-            }
+            for (int c = 0; c < CP; ++c) v[c] += __shfl_sync(0xffffffffu, blk[b][c], src_lane);
           }
           xpar ^= 1;
         } else {
@@ -343,21 +365,23 @@ __global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS>::kThreads, 1) conv_tc_k
           for (int c = 0; c < CP; ++c) v[c] = blk[0][c];
         }
 
-        // decode the pixel this lane holds
+        // the pixel this lane holds (decoded once per CTA, then advanced by TS rows per tile)
         const int64_t prow = int64_t(TS) * t - H_ + row;
-        bool valid = lane_valid && prow >= 0 && prow < p.rows_valid;
-        int n = 0, y = 0, x = 0;
-        if (valid) {
-          const uint32_t pr = uint32_t(prow);
-          const uint32_t q = pr / uint32_t(p.Wp);
-          x = int(pr - q * uint32_t(p.Wp));
-          n = int(q / uint32_t(p.H + 1));
-          const int yy = int(q - uint32_t(n) * uint32_t(p.H + 1));
-          y = yy - 1;
-          valid = (x < p.W) && (yy > 0);
+        const bool valid_px = lane_valid && prow < p.rows_valid && (px < p.W) && (pyy > 0);
+        bool valid = valid_px;
+        const int n = pn, y = pyy - 1, x = px;
+        {
+          px += adv_x;
+          const int cx = px >= p.Wp;
+          px -= cx ? p.Wp : 0;
+          pyy += adv_y + cx;
+          const int cy = pyy >= H1;
+          pyy -= cy ? H1 : 0;
+          pn += adv_n + cy;
         }
 
         if constexpr (EPI == EPI_FPA) {
+          static_assert(CP >= 8, "FPA epilogue stores 16-byte chunks");
           uint32_t packed[CP / 2];
           if (valid) {
 #pragma unroll
@@ -434,14 +458,12 @@ __global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS>::kThreads, 1) conv_tc_k
             if (valid) {
               const int r = p.shuffle_r, C = p.cout / (r * r);
               const int64_t OW = int64_t(p.FW) * r;
-              const int64_t base = (int64_t(fn) * p.FH * r + int64_t(fy) * r) * OW + int64_t(fx) * r;
+              const int64_t base = ((int64_t(fn) * p.FH * r + int64_t(fy) * r) * OW + int64_t(fx) * r) * C;
 #pragma unroll
               for (int c = 0; c < CP; ++c) {
-                const int cc = col0 + c;
-                if (cc < p.cout) {
-                  const int ch = cc % C, sub = cc / C;
-                  const int ddy = sub / r, ddx = sub - ddy * r;
-                  const int64_t idx = (base + int64_t(ddy) * OW + ddx) * C + ch;
+                const int off = tab_r[c];
+                if (off >= 0) {
+                  const int64_t idx = base + off;
                   float o = act_apply(v[c] + bias_r[c], p.act);
                   if (p.addend) o += __ldg(p.addend + idx);
                   p.out[idx] = o;

@@ -188,20 +188,29 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
 }
 
 // Deterministic second pass: dw/dbias = (accumulate ? dw : 0) + sum over CTA partials (fixed order).
-__global__ void __launch_bounds__(128) wgrad_reduce_kernel(const float4* __restrict__ partial, int n_part, float4* __restrict__ dw,
-                                                           float4* __restrict__ dbias, int accumulate) {
+// blockIdx.y selects the layer: one launch can fold the partial blocks of every layer of a model.
+__global__ void __launch_bounds__(128) wgrad_reduce_kernel(const float4* __restrict__ partial_base, size_t layer_stride_f4, int n_part,
+                                                           float* const* __restrict__ dw_ptrs, float* const* __restrict__ db_ptrs,
+                                                           float4* dw_single, float4* db_single, int accumulate) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // float4 index
   constexpr int kN4 = kPartialFloats / 4;
   if (i >= kN4) return;
+  const float4* partial = partial_base + size_t(blockIdx.y) * layer_stride_f4;
+  float4* dw = dw_ptrs ? reinterpret_cast<float4*>(dw_ptrs[blockIdx.y]) : dw_single;
+  float4* dbias = db_ptrs ? reinterpret_cast<float4*>(db_ptrs[blockIdx.y]) : db_single;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   int pidx = 0;
-  for (; pidx + 4 <= n_part; pidx += 4) {
-    const float4 a = __ldg(partial + size_t(pidx) * kN4 + i), b = __ldg(partial + size_t(pidx + 1) * kN4 + i);
-    const float4 c = __ldg(partial + size_t(pidx + 2) * kN4 + i), d = __ldg(partial + size_t(pidx + 3) * kN4 + i);
-    acc.x += (a.x + b.x) + (c.x + d.x);
-    acc.y += (a.y + b.y) + (c.y + d.y);
-    acc.z += (a.z + b.z) + (c.z + d.z);
-    acc.w += (a.w + b.w) + (c.w + d.w);
+  for (; pidx + 8 <= n_part; pidx += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __ldg(partial + size_t(pidx + j) * kN4 + i);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc.x += v[j].x;
+      acc.y += v[j].y;
+      acc.z += v[j].z;
+      acc.w += v[j].w;
+    }
   }
   for (; pidx < n_part; ++pidx) {
     const float4 a = __ldg(partial + size_t(pidx) * kN4 + i);
@@ -234,7 +243,7 @@ extern "C" size_t srk_conv_wgrad_tc_workspace_bytes(srk_handle_t h, int n_img, i
 
 extern "C" int srk_conv_wgrad_tc(srk_handle_t h, const void* x_fpa, const void* dy_fpa, int n_img, int H, int W, float* dw_hwio,
                                  float* dbias, int accumulate, void* workspace, size_t workspace_bytes, srk_stream_t stream) {
-  SRK_REQUIRE(h && x_fpa && dy_fpa && dw_hwio && dbias && workspace, "srk_conv_wgrad_tc: null argument");
+  SRK_REQUIRE(h && x_fpa && dy_fpa && workspace && (dw_hwio == nullptr || dbias != nullptr), "srk_conv_wgrad_tc: null argument");
   SRK_REQUIRE((reinterpret_cast<uintptr_t>(dw_hwio) | reinterpret_cast<uintptr_t>(dbias) | reinterpret_cast<uintptr_t>(workspace)) % 16 == 0,
               "srk_conv_wgrad_tc: dw, dbias and workspace must be 16-byte aligned");
   const FpaGeom g = fpa_geom(n_img, H, W);
@@ -258,8 +267,25 @@ extern "C" int srk_conv_wgrad_tc(srk_handle_t h, const void* x_fpa, const void* 
   }
   wgrad_tc_kernel<<<grid, kWgThreads, WgSmem::kTotal, as_stream(stream)>>>(p);
   SRK_LAUNCH_CHECK();
-  wgrad_reduce_kernel<<<(kPartialFloats / 4 + 127) / 128, 128, 0, as_stream(stream)>>>(
-      static_cast<const float4*>(workspace), grid, reinterpret_cast<float4*>(dw_hwio), reinterpret_cast<float4*>(dbias), accumulate);
+  if (dw_hwio) {
+    wgrad_reduce_kernel<<<dim3((kPartialFloats / 4 + 127) / 128, 1), 128, 0, as_stream(stream)>>>(
+        static_cast<const float4*>(workspace), 0, grid, nullptr, nullptr, reinterpret_cast<float4*>(dw_hwio),
+        reinterpret_cast<float4*>(dbias), accumulate);
+    SRK_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int srk_wgrad_reduce_many(srk_handle_t h, const void* workspace_base, size_t layer_stride_bytes, int n_layers, int n_img, int H,
+                                     int W, float* const* dw_ptrs_device, float* const* db_ptrs_device, int accumulate,
+                                     srk_stream_t stream) {
+  SRK_REQUIRE(h && workspace_base && dw_ptrs_device && db_ptrs_device && n_layers > 0, "srk_wgrad_reduce_many: bad argument");
+  SRK_REQUIRE(layer_stride_bytes % 16 == 0, "srk_wgrad_reduce_many: layer stride must be a multiple of 16 bytes");
+  const FpaGeom g = fpa_geom(n_img, H, W);
+  const int n_part = wgrad_grid(h, int((g.rows_valid + 127) / 128));
+  SRK_REQUIRE(layer_stride_bytes >= size_t(n_part) * kPartialFloats * sizeof(float), "srk_wgrad_reduce_many: layer stride smaller than one layer's partials");
+  wgrad_reduce_kernel<<<dim3((kPartialFloats / 4 + 127) / 128, n_layers), 128, 0, as_stream(stream)>>>(
+      static_cast<const float4*>(workspace_base), layer_stride_bytes / 16, n_part, dw_ptrs_device, db_ptrs_device, nullptr, nullptr, accumulate);
   SRK_LAUNCH_CHECK();
   return 0;
 }

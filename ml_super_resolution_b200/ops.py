@@ -201,11 +201,26 @@ def wgrad_workspace(n_img: int, H: int, W: int, device="cuda") -> torch.Tensor:
     return _wgrad_ws[key]
 
 
-def conv_wgrad_tc(x: Fpa, dy: Fpa, dw: torch.Tensor, dbias: torch.Tensor, accumulate=False, workspace: torch.Tensor | None = None) -> None:
-    """dw [3,3,64,64] (=|+=) X^T dY per tap, dbias [64] (=|+=) sum dY (srk_conv_wgrad_tc, deterministic)."""
+def conv_wgrad_tc(x: Fpa, dy: Fpa, dw: torch.Tensor | None, dbias: torch.Tensor | None, accumulate=False,
+                  workspace: torch.Tensor | None = None) -> None:
+    """dw [3,3,64,64] (=|+=) X^T dY per tap, dbias [64] (=|+=) sum dY (srk_conv_wgrad_tc, deterministic).
+    dw=None leaves the per-CTA partials in `workspace` for a later `wgrad_reduce_many`."""
     ws = workspace if workspace is not None else wgrad_workspace(x.n_img, x.H, x.W, x.data.device)
-    check(_ffi.lib().srk_conv_wgrad_tc(handle(), _ptr(x.data), _ptr(dy.data), x.n_img, x.H, x.W, _ptr(_f32(dw)), _ptr(_f32(dbias)),
+    check(_ffi.lib().srk_conv_wgrad_tc(handle(), _ptr(x.data), _ptr(dy.data), x.n_img, x.H, x.W, _ptr(dw), _ptr(dbias),
                                        int(accumulate), _ptr(ws), ws.numel(), _stream()), "srk_conv_wgrad_tc")
+    if dw is not None:
+        _ffi.launch_count += 1  # the reduce kernel
+
+
+def wgrad_reduce_many(workspace: torch.Tensor, layer_stride_bytes: int, n_layers: int, n_img: int, H: int, W: int,
+                      dw_ptrs: torch.Tensor, db_ptrs: torch.Tensor, accumulate=False) -> None:
+    """Fold the deferred per-CTA partial blocks of n_layers layers into their dw/dbias with one launch."""
+    check(_ffi.lib().srk_wgrad_reduce_many(handle(), _ptr(workspace), layer_stride_bytes, n_layers, n_img, H, W, _ptr(dw_ptrs),
+                                           _ptr(db_ptrs), int(accumulate), _stream()), "srk_wgrad_reduce_many")
+
+
+def wgrad_workspace_bytes(n_img: int, H: int, W: int) -> int:
+    return int(_ffi.lib().srk_conv_wgrad_tc_workspace_bytes(handle(), n_img, H, W))
 
 
 def conv_first_wgrad(x: torch.Tensor, dy: Fpa, k: int, dw: torch.Tensor, dbias: torch.Tensor) -> None:

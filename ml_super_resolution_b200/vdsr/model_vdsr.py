@@ -162,8 +162,17 @@ class VdsrNet:
                 "sr": torch.empty((n, H, W, self.C), dtype=torch.float32, device=self.device),
                 "dsr": torch.empty((n, H, W, self.C), dtype=torch.float32, device=self.device),
                 "loss": torch.zeros(2, dtype=torch.float32, device=self.device),  # [mse, l2 regulariser]
+                "wg_stride": (ops.wgrad_workspace_bytes(n, H, W) + 1023) // 1024 * 1024,
                 "lr_t": torch.zeros(1, dtype=torch.float32, device=self.device),
             }
+            b = self._train_bufs
+            # one workspace slice per 64->64 layer so a single launch can fold all of their partial sums
+            b["wg_ws"] = torch.empty(b["wg_stride"] * (self.L - 2), dtype=torch.uint8, device=self.device)
+            a = self.arena
+            dw = [a.view(self._kname(i), "g").data_ptr() for i in range(1, self.L - 1)]
+            db = [a.view(self._bname(i), "g").data_ptr() for i in range(1, self.L - 1)]
+            b["wg_dw_ptrs"] = torch.tensor(dw, dtype=torch.int64, device=self.device)
+            b["wg_db_ptrs"] = torch.tensor(db, dtype=torch.int64, device=self.device)
         return self._train_bufs
 
     def forward_backward(self, sd: torch.Tensor, hd: torch.Tensor, numel_total: float | None = None):
@@ -188,9 +197,12 @@ class VdsrNet:
         # ---- backward
         ops.conv_last_wgrad(acts[L - 2], b["dsr"], a.view(self._kname(L - 1), "g"), a.view(self._bname(L - 1), "g"))
         d = ops.conv_first(b["dsr"], self.wd(L - 1), None, "SAME", None, out=dyb[0], relu_mask=acts[L - 2])
+        stride = b["wg_stride"]
         for i in range(L - 2, 0, -1):
-            ops.conv_wgrad_tc(acts[i - 1], d, a.view(self._kname(i), "g"), a.view(self._bname(i), "g"))
+            ws = b["wg_ws"][(i - 1) * stride:i * stride]
+            ops.conv_wgrad_tc(acts[i - 1], d, None, None, workspace=ws)  # partial sums only; folded below in one launch
             d = ops.conv_tc(d, self.wd(i), None, 3, None, out=dyb[(L - 1 - i) % 2], mask_src=acts[i - 1], mask_kind="relu")
+        ops.wgrad_reduce_many(b["wg_ws"], stride, L - 2, n, H, W, b["wg_dw_ptrs"], b["wg_db_ptrs"])
         ops.conv_first_wgrad(sd, d, 3, a.view(self._kname(0), "g"), a.view(self._bname(0), "g"))
         return b
 
@@ -217,6 +229,49 @@ class VdsrNet:
             torch.distributed.all_reduce(self.arena.g, group=group)  # NCCL sum over NVLink: the one exchange step
         self.apply_gradients(lr, use_adam)
         return b["loss"].sum()
+
+    def make_graphed_step(self, sd_static: torch.Tensor, hd_static: torch.Tensor, group=None):
+        """Capture the Adam training step into CUDA graphs (the ~85 launches of a step are latency-bound at
+        64 patches of 41x41).  Returns `step(lr) -> loss buffer [mse, reg]`; new batches are copied INTO
+        `sd_static` / `hd_static` before each call.  Graph A = forward + loss + backward, then (world > 1) the
+        NCCL gradient all-reduce runs eagerly, graph B = Adam (learning rate read from device memory, so the
+        same graph serves every step) + weight re-pack."""
+        world = 1
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            world = torch.distributed.get_world_size(group)
+        numel_total = float(sd_static.numel()) * world
+        a = self.arena
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up outside capture: allocates buffers, sets kernel attributes
+            self.forward_backward(sd_static, hd_static, numel_total)
+            b = self._train_bufs
+            ops.adam_step_dev(a.w, a.g, a.m, a.v, b["lr_t"], weight_decay=WEIGHT_DECAY, decay_mask=a.decay_mask)  # lr_t == 0: no-op update
+            self.repack()
+        torch.cuda.current_stream().wait_stream(side)
+        a.m.zero_()
+        a.v.zero_()
+        torch.cuda.synchronize()
+        g_fb, g_opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_fb):
+            self.forward_backward(sd_static, hd_static, numel_total)
+        with torch.cuda.graph(g_opt):
+            ops.adam_step_dev(a.w, a.g, a.m, a.v, b["lr_t"], weight_decay=WEIGHT_DECAY, decay_mask=a.decay_mask)
+            self.repack()
+        lr_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+
+        def step(lr: float):
+            g_fb.replay()
+            if world > 1:
+                torch.distributed.all_reduce(a.g, group=group)
+            self.step += 1
+            lr_host[0] = self.adam_lr_t(lr, self.step)
+            b["lr_t"].copy_(lr_host, non_blocking=True)
+            g_opt.replay()
+            return b["loss"]
+
+        step.graphs = (g_fb, g_opt)
+        return step
 
     @staticmethod
     def adam_lr_t(lr: float, t: int, beta1=0.9, beta2=0.999) -> float:

@@ -120,3 +120,22 @@ def test_espcn_forward_matches_oracle(srk_ops, channels, r, shape):
     # the fused depth_to_space is index-exact: shuffling our own packed output reproduces it bit for bit
     assert np.array_equal(shuffled, O.pixel_shuffle(packed, r))
     assert abs(_psnr(shuffled, O.pixel_shuffle(ref, r) + 0.1) - _psnr(O.pixel_shuffle(ref, r), O.pixel_shuffle(ref, r) + 0.1)) <= 0.02
+
+
+def test_vdsr_graphed_step_equals_eager(srk_ops):
+    """The CUDA-graph replay of the training step performs the same arithmetic as the eager step."""
+    from ml_super_resolution_b200.vdsr.model_vdsr import VdsrNet
+    L = 5
+    params = _trained_like(OM.vdsr_init(seed=4, num_layers=L))
+    hd = OM.synthetic_images(21, 8, 41, 41, 3)
+    sd = OM.synthetic_images(22, 8, 41, 41, 3)
+    sdt, hdt = torch.from_numpy(sd).cuda(), torch.from_numpy(hd).cuda()
+    eager, graphed = VdsrNet(params, num_layers=L), VdsrNet(params, num_layers=L)
+    gstep = graphed.make_graphed_step(sdt, hdt)
+    for _ in range(3):
+        le = float(eager.train_step(sdt, hdt, lr=1e-3))
+        lg = float(gstep(1e-3).sum())
+        assert le == pytest.approx(lg, rel=1e-6)
+    we, wg = eager.arena.to_numpy(), graphed.arena.to_numpy()
+    for k in we:
+        assert np.allclose(we[k], wg[k], rtol=1e-4, atol=1e-6), k  # (first/last-layer wgrad use fp32 atomics: order-dependent last bits)
