@@ -167,7 +167,7 @@ def espcn_workload(args, rank, world):
     panels = ops.make_panels([t.as_tuple() for t in tiles])
     t1, t2 = net._get_bufs(len(tiles), Ht, Wt)
     a = net.arena
-    k_f1 = event_time(lambda: ops.conv_first(lr, a.view("f1/kernel:0"), a.view("f1/bias:0"), "SAME", "tanh", panels=panels, panel_hw=(Ht, Wt), out=t1))
+    k_f1 = event_time(lambda: ops.conv_first_tc(lr, net.plan.views[net._i1], a.view("f1/bias:0"), 5, "SAME", "tanh", panels=panels, panel_hw=(Ht, Wt), out=t1))
     k_f2 = event_time(lambda: ops.conv_tc(t1, net.plan.views[net._i2], a.view("f2/bias:0"), 3, "tanh", out=t2))
     k_f3 = event_time(lambda: ops.conv_tc_last(t2, net.plan.views[net._i3], net.bias3, 3, net.cout3, None, shuffle_r=SCALE, panels=panels,
                                                frame_shape=(FRAMES_PER_STEP, LR_H, LR_W), out=out))
@@ -175,7 +175,7 @@ def espcn_workload(args, rank, world):
     # algorithmic bytes per LR pixel: f1 reads fp32 C, writes 64 bf16; f2 reads 64 bf16, writes 32 bf16;
     # f3 reads 32 bf16, writes C*r^2 fp32
     kernels = {
-        "espcn_f1_conv_first(5x5,C->64,tanh)": (k_f1, lr_px * (4 * C + 128)),
+        "espcn_f1_conv_first_tc(5x5,C->64,tanh)": (k_f1, lr_px * (4 * C + 128)),
         "espcn_f2_conv_tc(3x3,64->32,tanh)": (k_f2, lr_px * (128 + 64)),
         "espcn_f3_conv_tc_last(3x3,32->9,shuffle)": (k_f3, lr_px * (64 + 4 * C * SCALE * SCALE)),
     }

@@ -36,7 +36,7 @@ typedef void* srk_stream_t; /* cudaStream_t */
 
 enum { SRK_ACT_NONE = 0, SRK_ACT_RELU = 1, SRK_ACT_TANH = 2 };
 enum { SRK_PAD_SAME = 0, SRK_PAD_VALID = 1 };
-enum { SRK_PACK_FWD = 0, SRK_PACK_DGRAD = 1, SRK_PACK_ROT180T_F32 = 2 };
+enum { SRK_PACK_FWD = 0, SRK_PACK_DGRAD = 1, SRK_PACK_ROT180T_F32 = 2, SRK_PACK_FIRST = 3, SRK_PACK_FIRST_ROT180T = 4 };
 
 /* One entry per FPA image when a large frame is processed as column/row panels (tiled inference,
  * SURVEY 8e): the panel's top-left corner in the frame and the rectangle (panel-local, half-open)
@@ -93,6 +93,15 @@ int srk_conv_first(srk_handle_t h, const float* x, int n_frames, int FH, int FW,
                    const float* w_hwio, const float* bias, int k, int pad_mode, int act,
                    const srk_panel* panels, int n_img, int H, int W, void* y_fpa,
                    const void* relu_mask_src, srk_stream_t stream);
+
+/* Tensor-core form of srk_conv_first (same call sites): the im2col rows of each 128-pixel tile are gathered
+ * from the fp32 frame into shared memory (bf16) and multiplied by the packed kernel with tcgen05.mma.
+ * w_packed: srk_pack_conv_weights(..., mode = SRK_PACK_FIRST, ...) -> bf16 [ceil(k*k*cin/64)][64][64]; or mode
+ * SRK_PACK_FIRST_ROT180T of a [k,k,64,cout] kernel, which makes this call the LAST layer's data gradient
+ * (x = dY fp32 [.., cout], mask_src = saved activation, mask_kind = SRK_ACT_RELU). */
+int srk_conv_first_tc(srk_handle_t h, const float* x, int n_frames, int FH, int FW, int cin, const void* w_packed,
+                      const float* bias, int k, int pad_mode, int act, const srk_panel* panels, int n_img, int H, int W,
+                      void* y_fpa, const void* mask_src, int mask_kind, srk_stream_t stream);
 
 /* Tensor-core conv between FPA buffers (tcgen05 implicit GEMM, 9 shifted GEMMs, fp32 TMEM accum):
  *   y = act(conv_kxk(x) + bias) [* act'(mask_src)] [then relu(y + addend)]

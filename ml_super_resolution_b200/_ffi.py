@@ -40,6 +40,7 @@ SIGNATURES = {
     "srk_sumsq_masked": (_I, [_P, _P, _P, _SZ, _F, _P, _P]),
     "srk_adam_step_dev": (_I, [_P, _P, _P, _P, _P, _SZ, _P, _F, _F, _F, _F, _P, _P]),
     "srk_conv_first": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P]),
+    "srk_conv_first_tc": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P, _I, _I, _I, _P, _P, _I, _P]),
     "srk_conv_tc": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P]),
     "srk_conv_tc_last": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P]),
     "srk_conv_wgrad_tc_workspace_bytes": (_SZ, [_P, _I, _I, _I]),

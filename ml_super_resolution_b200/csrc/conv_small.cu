@@ -29,6 +29,30 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int k, int cin,
   }
 }
 
+// First-layer forms (srk_conv_first_tc): out[blk][n < 64][kk < 64] with GEMM-K index kg = blk*64 + kk.
+//   SRK_PACK_FIRST          : kg = (u*k + v)*cin + ci, n = co        -> w[u][v][ci][co]            (cout == 64)
+//   SRK_PACK_FIRST_ROT180T  : kg = (u*k + v)*cout + co, n = ci       -> w[k-1-u][k-1-v][ci][co]    (cin == 64): the last layer's
+//                             data gradient as a first-layer style conv over dY[..., cout]
+__device__ __forceinline__ float first_form_value(const float* __restrict__ w, int k, int cin, int cout, int mode, int n, int kg) {
+  if (mode == SRK_PACK_FIRST) {
+    if (kg >= k * k * cin) return 0.f;
+    const int ci = kg % cin, tap = kg / cin;
+    return w[(tap * cin + ci) * cout + n];
+  }
+  if (kg >= k * k * cout) return 0.f;
+  const int co = kg % cout, tap = kg / cout;
+  const int u = k - 1 - tap / k, v = k - 1 - tap % k;
+  return w[((u * k + v) * cin + n) * cout + co];
+}
+
+__global__ void pack_first_kernel(const float* __restrict__ w, int k, int cin, int cout, int mode, int blocks, __nv_bfloat16* __restrict__ out) {
+  const int total = blocks * 4096;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int kk = e % 64, n = (e / 64) % 64, blk = e / 4096;
+    out[e] = __float2bfloat16_rn(first_form_value(w, k, cin, cout, mode, n, blk * 64 + kk));
+  }
+}
+
 // Batched form: one launch prepares every layer of a model after an optimiser step.  Each job packs one
 // HWIO kernel out of the flat fp32 parameter arena; mode SRK_PACK_ROT180T_F32 instead writes the fp32
 // [k][k][cout][cin] rotated/transposed kernel that srk_conv_first consumes as the last layer's dgrad.
@@ -44,7 +68,10 @@ __global__ void pack_weights_batched_kernel(const float* __restrict__ arena, con
     const int e = int(i - jb.elem_begin);
     const float* w = arena + jb.src_offset;
     const int k = jb.k, cin = jb.cin, cout = jb.cout;
-    if (jb.mode == SRK_PACK_ROT180T_F32) {
+    if (jb.mode == SRK_PACK_FIRST || jb.mode == SRK_PACK_FIRST_ROT180T) {
+      const int kk = e % 64, n = (e / 64) % 64, blk = e / 4096;
+      reinterpret_cast<__nv_bfloat16*>(out_base + jb.dst_offset)[e] = __float2bfloat16_rn(first_form_value(w, k, cin, cout, jb.mode, n, blk * 64 + kk));
+    } else if (jb.mode == SRK_PACK_ROT180T_F32) {
       // out[u'][v'][co][ci] = w[k-1-u'][k-1-v'][ci][co]
       const int ci = e % cin, co = (e / cin) % cout, tap = e / (cin * cout);
       const int u = k - 1 - tap / k, v = k - 1 - tap % k;
@@ -357,6 +384,16 @@ using namespace srk;
 extern "C" int srk_pack_conv_weights(srk_handle_t h, const float* w_hwio, int k, int cin, int cout, int mode, int np, int cinp,
                                      void* packed_bf16, srk_stream_t stream) {
   SRK_REQUIRE(h && w_hwio && packed_bf16, "srk_pack_conv_weights: null argument");
+  if (mode == SRK_PACK_FIRST || mode == SRK_PACK_FIRST_ROT180T) {
+    // one job through the batched kernel (jobs array passed by value through a tiny device copy is avoided: use the single-job kernel)
+    const int kt = (mode == SRK_PACK_FIRST) ? k * k * cin : k * k * cout;
+    const int blocks = ((kt + 15) / 16 * 16 + 63) / 64;
+    SRK_REQUIRE((mode == SRK_PACK_FIRST ? cout : cin) == 64, "srk_pack_conv_weights: first-layer forms need 64 output channels");
+    pack_first_kernel<<<(blocks * 4096 + 255) / 256, 256, 0, as_stream(stream)>>>(w_hwio, k, cin, cout, mode, blocks,
+                                                                                 static_cast<__nv_bfloat16*>(packed_bf16));
+    SRK_LAUNCH_CHECK();
+    return 0;
+  }
   if (mode == SRK_PACK_FWD) SRK_REQUIRE(np >= cout && cinp >= cin, "srk_pack_conv_weights: padded dims too small");
   else SRK_REQUIRE(np >= cin && cinp >= cout, "srk_pack_conv_weights: padded dims too small (dgrad)");
   const int total = k * k * np * cinp;

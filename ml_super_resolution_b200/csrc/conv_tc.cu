@@ -37,7 +37,7 @@ namespace srk {
 enum { EPI_FPA = 0, EPI_NHWC = 1 };
 
 constexpr int kChunkRows = 64;
-constexpr int kRingSlots = 14;   // ring of 64-row chunks ...
+constexpr int kRingSlots = 12;   // ring of 64-row chunks ...
 constexpr int kMirrorSlots = 2;  // ... whose first 128 rows are duplicated behind the last slot
 
 struct alignas(64) ConvTcParams {
@@ -75,7 +75,7 @@ struct ConvTcCfg {
   static constexpr int kWTapBytes = NP * kRowBytes;
   static constexpr int kWBytes = ((kTaps * kWTapBytes + 1023) / 1024) * 1024;
   static constexpr int kRingBytes = (kRingSlots + kMirrorSlots) * kChunkBytes;
-  static constexpr int kStageBytes = 128 * NP * 2;  // output staging (EPI_FPA)
+  static constexpr int kStageBytes = 2 * 128 * NP * 2;  // output staging (EPI_FPA), double buffered
   static constexpr int kGroups = 4;                 // epilogue column groups (4 warps each): 16 epilogue warps
   static constexpr int kColPass = NP / kGroups;     // accumulator columns per epilogue thread (16 / 8 / 4)
   static constexpr int kEpiThreads = 128 * kGroups;
@@ -89,7 +89,7 @@ struct ConvTcCfg {
   static constexpr int kOffTab = kOffBias + 256;    // NHWC epilogue: per-channel output offsets
   static constexpr int kOffXch = kOffTab + 256;
   static constexpr int kOffBars = kOffXch + ((kXchFloats * 4 + 15) / 16) * 16;
-  static constexpr int kNumBars = 2 * kRingSlots + 1 + 2 * kAccStages + 2;
+  static constexpr int kNumBars = 2 * kRingSlots + 1 + 2 * kAccStages + 4;
   static constexpr int kOffTmemSlot = kOffBars + kNumBars * 8;
   static constexpr int kTotal = kOffTmemSlot + 16 + 1024;  // + alignment slack
   static_assert(kN % 16 == 0 && kN <= 256, "invalid UMMA N");
@@ -125,153 +125,52 @@ __device__ __forceinline__ void tmem_load_cols(uint32_t taddr, float (&v)[NCOL])
   for (int j = 0; j < NCOL; ++j) v[j] = __uint_as_float(u[j]);
 }
 
-template <int CIN, int NP, int KS, int EPI>
-__global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS>::kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
-  using L = ConvTcCfg<CIN, NP, KS>;
-  constexpr uint32_t kLayout = (CIN == 64) ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW64;
-  constexpr uint32_t kSbo = 8 * L::kRowBytes;
-  constexpr int H_ = L::kHalo, TS = L::kTileStride, CP = L::kColPass, ACC = L::kAccStages;
+// Shared-memory addresses the store warp and the epilogue warps work with.
+struct EpiCtx {
+  uint32_t tmem;
+  uint32_t bar_tfull0, bar_tempty0;  // + 8 * accumulator stage
+  uint32_t bar_sfull, bar_sfree;  // + 8 * staging buffer
+  uint8_t* stage_ptr;
+  int stage_stride;               // bytes between the two staging buffers
+  float* s_bias;
+  int* s_tab;
+  float* s_xch;
+};
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t s_base = smem_u32(smem);
-  const uint32_t s_w = s_base + L::kOffW;
-  const uint32_t s_ring = s_base + L::kOffRing;
-  uint8_t* stage_ptr = smem + L::kOffStage;
-  float* s_bias = reinterpret_cast<float*>(smem + L::kOffBias);
-  int* s_tab = reinterpret_cast<int*>(smem + L::kOffTab);
-  float* s_xch = reinterpret_cast<float*>(smem + L::kOffXch);
-  const uint32_t s_bars = s_base + L::kOffBars;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmemSlot);
-  auto bar_full = [&](int s) { return s_bars + 8u * s; };
-  auto bar_empty = [&](int s) { return s_bars + 8u * (kRingSlots + s); };
-  const uint32_t bar_wfull = s_bars + 8u * (2 * kRingSlots);
-  auto bar_tfull = [&](int a) { return s_bars + 8u * (2 * kRingSlots + 1 + a); };
-  auto bar_tempty = [&](int a) { return s_bars + 8u * (2 * kRingSlots + 1 + ACC + a); };
-  const uint32_t bar_sfull = s_bars + 8u * (2 * kRingSlots + 1 + 2 * ACC);      // staging tile complete
-  const uint32_t bar_sfree = s_bars + 8u * (2 * kRingSlots + 1 + 2 * ACC + 1);  // staging buffer reusable
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  // contiguous tile range of this CTA; tile t produces output rows [TS*t, TS*t + TS)
-  const int t_begin = int((int64_t(blockIdx.x) * p.num_tiles) / gridDim.x);
-  const int t_end = int((int64_t(blockIdx.x + 1) * p.num_tiles) / gridDim.x);
-  const int reach = H_ * p.Wp;  // rows of vertical reach
-  auto lo_chunk = [&](int t) { return floor_div(TS * t - H_ - reach, kChunkRows); };
-  auto hi_chunk = [&](int t) { return floor_div(TS * t - H_ + reach + 127, kChunkRows); };
-  const int c0 = lo_chunk(t_begin);  // first chunk this CTA loads (may be negative: TMA zero-fills)
-  const int c_last = hi_chunk(t_end - 1);
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kRingSlots; ++i) {
-      mbar_init(bar_full(i), 1);
-      mbar_init(bar_empty(i), 1);
+// One thread: wait for a complete staging tile, TMA-store it, hand the staging buffer back.
+template <int TS>
+__device__ __forceinline__ void conv_store_loop(const ConvTcParams& p, const EpiCtx& e, int t_begin, int t_end) {
+  for (int t = t_begin; t < t_end; ++t) {
+    const int it = t - t_begin, sb = it & 1, sgen = it >> 1;
+    mbar_wait(e.bar_sfull + 8u * sb, sgen & 1);
+    tma_store_2d(&p.map_out, 0, TS * t, smem_u32(e.stage_ptr + sb * e.stage_stride));
+    tma_store_commit();
+    if (it >= 1) {  // the store of tile it-1 has finished READING its staging buffer -> writers of tile it+1 may reuse it
+      tma_store_wait_read<1>();
+      mbar_arrive(e.bar_sfree + 8u * (sb ^ 1));
     }
-    mbar_init(bar_wfull, 1);
-    for (int i = 0; i < ACC; ++i) {
-      mbar_init(bar_tfull(i), 1);
-      mbar_init(bar_tempty(i), L::kEpiThreads);
-    }
-    mbar_init(bar_sfull, L::kEpiThreads);
-    mbar_init(bar_sfree, 1);
-    fence_mbar_init();
   }
-  if (threadIdx.x < NP) s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
-  if (EPI == EPI_NHWC && threadIdx.x < NP) {
-    // output offset of packed channel c relative to pixel (Y*r, X*r, 0): depth_to_space index, -1 = padding channel
-    const int c = threadIdx.x, r = p.shuffle_r, C = p.cout / (r * r);
-    int off = -1;
-    if (c < p.cout) {
-      const int ch = c % C, sub = c / C, ddy = sub / r, ddx = sub - ddy * r;
-      off = (ddy * p.FW * r + ddx) * C + ch;
-    }
-    s_tab[c] = off;
-  }
-  if (warp == 1) tmem_alloc<L::kTmemCols>(smem_u32(tmem_slot));
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.map_in);
-    tma_prefetch_desc(&p.map_w);
-    if (EPI == EPI_FPA) tma_prefetch_desc(&p.map_out);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  tma_store_wait_all<0>();
+}
 
-  if (t_begin < t_end) {
-    if (warp == 0) {
-      // ------------------------------------------------------------------ TMA producer
-      if (lane == 0) {
-        mbar_arrive_expect_tx(bar_wfull, L::kTaps * L::kWTapBytes);
-        for (int tap = 0; tap < L::kTaps; ++tap) tma_load_2d(s_w + tap * L::kWTapBytes, &p.map_w, 0, tap * NP, bar_wfull);
-        for (int c = c0; c <= c_last; ++c) {
-          const int i = c - c0, slot = i % kRingSlots, gen = i / kRingSlots;
-          mbar_wait(bar_empty(slot), (gen & 1) ^ 1);
-          const bool mir = slot < kMirrorSlots;
-          mbar_arrive_expect_tx(bar_full(slot), L::kChunkBytes * (mir ? 2 : 1));
-          tma_load_2d(s_ring + slot * L::kChunkBytes, &p.map_in, 0, c * kChunkRows, bar_full(slot));
-          if (mir) tma_load_2d(s_ring + (kRingSlots + slot) * L::kChunkBytes, &p.map_in, 0, c * kChunkRows, bar_full(slot));
-        }
-      }
-    } else if (warp == 1) {
-      // ------------------------------------------------------------------ MMA issuer (one thread)
-      if (lane == 0) {
-        constexpr uint32_t idesc = umma_idesc_bf16(128, L::kN, 0, 0);
-        constexpr uint64_t hi = umma_desc_hi(0, kSbo, kLayout);
-        mbar_wait(bar_wfull, 0);
-        int loaded = c0 - 1, released = c0;  // chunks <= loaded have landed; chunks < released were handed back
-        for (int t = t_begin; t < t_end; ++t) {
-          const int it = t - t_begin, acc = it % ACC, accgen = it / ACC;
-          const int need = hi_chunk(t);
-          while (loaded < need) {
-            ++loaded;
-            const int i = loaded - c0;
-            mbar_wait(bar_full(i % kRingSlots), (i / kRingSlots) & 1);
-          }
-          mbar_wait(bar_tempty(acc), (accgen & 1) ^ 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem + acc * L::kN;
-          const int row0 = TS * t - H_ - c0 * kChunkRows;  // window start of dy = 0, relative to the ring origin
-#pragma unroll
-          for (int r = 0; r < KS; ++r) {
-            const int rr = (row0 + (r - H_) * p.Wp) % (kRingSlots * kChunkRows);
-            const uint32_t a_addr = s_ring + rr * L::kRowBytes;
-            const uint32_t b_addr = s_w + r * KS * L::kWTapBytes;
-#pragma unroll
-            for (int k = 0; k < CIN / 16; ++k)
-              umma_bf16(d_tmem, umma_desc(hi, a_addr + k * 32), umma_desc(hi, b_addr + k * 32), idesc, (r | k) != 0);
-          }
-          umma_commit(bar_tfull(acc));
-          // hand back the chunks no later tile needs
-          const int keep_from = (t + 1 < t_end) ? lo_chunk(t + 1) : released;
-          while (released < keep_from) {
-            umma_commit(bar_empty((released - c0) % kRingSlots));
-            ++released;
-          }
-        }
-      }
-    } else if (warp == 2) {
-      // ------------------------------------------------------------------ TMA store issuer (one thread)
-      if (EPI == EPI_FPA && lane == 0) {
-        for (int t = t_begin; t < t_end; ++t) {
-          const int it = t - t_begin;
-          mbar_wait(bar_sfull, it & 1);
-          tma_store_2d(&p.map_out, 0, TS * t, smem_u32(stage_ptr));
-          tma_store_commit();
-          tma_store_wait_read<0>();  // smem has been read: the staging buffer may be overwritten
-          mbar_arrive(bar_sfree);
-        }
-        tma_store_wait_all<0>();
-      }
-    } else if (warp >= 4) {
-      // ------------------------------------------------------------------ epilogue (128 threads per 16 channels)
-      const int quad = warp & 3;         // TMEM lane quadrant this warp may access
-      const int grp = (warp - 4) >> 2;   // column group: channels [16*grp, 16*grp + 16)
+// Epilogue warp `ewarp` (0..15): TMEM lane quadrant ewarp & 3, column group ewarp >> 2.
+template <int NP, int KS, int EPI, int ACC, int KN>
+__device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCtx& e, int ewarp, int lane, int t_begin, int t_end) {
+  constexpr int H_ = KS / 2, TS = 128 - (KS - 1), CP = NP / 4;
+  constexpr int kXchGroupFloats = 2 * 4 * (KS > 1 ? (KS - 1) * H_ : 1) * CP;
+  const uint32_t tmem = e.tmem;
+  float* s_bias = e.s_bias;
+  int* s_tab = e.s_tab;
+  float* s_xch = e.s_xch;
+  auto bar_tfull = [&](int a) { return e.bar_tfull0 + 8u * a; };
+  auto bar_tempty = [&](int a) { return e.bar_tempty0 + 8u * a; };
+  {
+      const int quad = ewarp & 3;   // TMEM lane quadrant this warp may access (hardware: warp index % 4)
+      const int grp = ewarp >> 2;   // column group: channels [CP*grp, CP*grp + CP)
       const int row = quad * 32 + lane;  // lane j of the accumulator <-> flat row TS*t - h + j
       const int col0 = grp * CP;
       const bool lane_valid = (row >= H_) && (row < H_ + TS);
-      float* xg = s_xch + grp * L::kXchGroupFloats;
+      float* xg = s_xch + grp * kXchGroupFloats;
       constexpr int kXq = (KS > 1 ? (KS - 1) * H_ : 1) * CP;  // floats per (parity, quadrant)
       float bias_r[CP];
       int tab_r[CP];
@@ -298,7 +197,7 @@ __global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS>::kThreads, 1) conv_tc_k
         const int it = t - t_begin, acc = it % ACC, accgen = it / ACC;
         mbar_wait(bar_tfull(acc), accgen & 1);
         tc_fence_after();
-        const uint32_t taddr = tmem + acc * L::kN + col0 + (uint32_t(quad * 32) << 16);
+        const uint32_t taddr = tmem + acc * KN + col0 + (uint32_t(quad * 32) << 16);
         float blk[KS][CP];
 #pragma unroll
         for (int b = 0; b < KS; ++b) tmem_load_cols<CP>(taddr + b * NP, blk[b]);
@@ -429,8 +328,10 @@ __global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS>::kThreads, 1) conv_tc_k
 #pragma unroll
             for (int c = 0; c < CP / 2; ++c) packed[c] = 0u;  // pad rows/columns stay exactly zero
           }
-          // staging buffer free? (the store of the previous tile has finished reading it)
-          mbar_wait(bar_sfree, (it & 1) ^ 1);
+          // staging buffer free? (the store of tile it-2, which used the same buffer, has finished reading it)
+          const int sb = it & 1, sgen = it >> 1;
+          uint8_t* stage_ptr = e.stage_ptr + sb * e.stage_stride;
+          mbar_wait(e.bar_sfree + 8u * sb, (sgen & 1) ^ 1);
           if (lane_valid) {
             constexpr int kOutRowBytes = NP * 2;
             const int srow = row - H_;  // staging row = output row within the tile
@@ -443,7 +344,7 @@ __global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS>::kThreads, 1) conv_tc_k
             }
           }
           fence_proxy_async_smem();
-          mbar_arrive(bar_sfull);
+          mbar_arrive(e.bar_sfull + 8u * sb);
         } else {
           // fp32 NHWC scatter: residual add, panel crop, depth_to_space
           if (valid) {
@@ -473,11 +374,377 @@ __global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS>::kThreads, 1) conv_tc_k
           }
         }
       }
+  }
+}
+
+template <int CIN, int NP, int KS, int EPI>
+__global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS>::kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
+  using L = ConvTcCfg<CIN, NP, KS>;
+  constexpr uint32_t kLayout = (CIN == 64) ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW64;
+  constexpr uint32_t kSbo = 8 * L::kRowBytes;
+  constexpr int H_ = L::kHalo, TS = L::kTileStride, CP = L::kColPass, ACC = L::kAccStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t s_w = s_base + L::kOffW;
+  const uint32_t s_ring = s_base + L::kOffRing;
+  uint8_t* stage_ptr = smem + L::kOffStage;
+  float* s_bias = reinterpret_cast<float*>(smem + L::kOffBias);
+  int* s_tab = reinterpret_cast<int*>(smem + L::kOffTab);
+  float* s_xch = reinterpret_cast<float*>(smem + L::kOffXch);
+  const uint32_t s_bars = s_base + L::kOffBars;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmemSlot);
+  auto bar_full = [&](int s) { return s_bars + 8u * s; };
+  auto bar_empty = [&](int s) { return s_bars + 8u * (kRingSlots + s); };
+  const uint32_t bar_wfull = s_bars + 8u * (2 * kRingSlots);
+  auto bar_tfull = [&](int a) { return s_bars + 8u * (2 * kRingSlots + 1 + a); };
+  auto bar_tempty = [&](int a) { return s_bars + 8u * (2 * kRingSlots + 1 + ACC + a); };
+  const uint32_t bar_sfull = s_bars + 8u * (2 * kRingSlots + 1 + 2 * ACC);      // [2] staging tile complete
+  const uint32_t bar_sfree = s_bars + 8u * (2 * kRingSlots + 1 + 2 * ACC + 2);  // [2] staging buffer reusable
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // contiguous tile range of this CTA; tile t produces output rows [TS*t, TS*t + TS)
+  const int t_begin = int((int64_t(blockIdx.x) * p.num_tiles) / gridDim.x);
+  const int t_end = int((int64_t(blockIdx.x + 1) * p.num_tiles) / gridDim.x);
+  const int reach = H_ * p.Wp;  // rows of vertical reach
+  auto lo_chunk = [&](int t) { return floor_div(TS * t - H_ - reach, kChunkRows); };
+  auto hi_chunk = [&](int t) { return floor_div(TS * t - H_ + reach + 127, kChunkRows); };
+  const int c0 = lo_chunk(t_begin);  // first chunk this CTA loads (may be negative: TMA zero-fills)
+  const int c_last = hi_chunk(t_end - 1);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kRingSlots; ++i) {
+      mbar_init(bar_full(i), 1);
+      mbar_init(bar_empty(i), 1);
+    }
+    mbar_init(bar_wfull, 1);
+    for (int i = 0; i < ACC; ++i) {
+      mbar_init(bar_tfull(i), 1);
+      mbar_init(bar_tempty(i), L::kEpiThreads);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_sfull + 8u * i, L::kEpiThreads);
+      mbar_init(bar_sfree + 8u * i, 1);
+    }
+    fence_mbar_init();
+  }
+  if (threadIdx.x < NP) s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
+  if (EPI == EPI_NHWC && threadIdx.x < NP) {
+    // output offset of packed channel c relative to pixel (Y*r, X*r, 0): depth_to_space index, -1 = padding channel
+    const int c = threadIdx.x, r = p.shuffle_r, C = p.cout / (r * r);
+    int off = -1;
+    if (c < p.cout) {
+      const int ch = c % C, sub = c / C, ddy = sub / r, ddx = sub - ddy * r;
+      off = (ddy * p.FW * r + ddx) * C + ch;
+    }
+    s_tab[c] = off;
+  }
+  if (warp == 1) tmem_alloc<L::kTmemCols>(smem_u32(tmem_slot));
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.map_in);
+    tma_prefetch_desc(&p.map_w);
+    if (EPI == EPI_FPA) tma_prefetch_desc(&p.map_out);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  EpiCtx ec;
+  ec.tmem = tmem;
+  ec.bar_tfull0 = bar_tfull(0);
+  ec.bar_tempty0 = bar_tempty(0);
+  ec.bar_sfull = bar_sfull;
+  ec.bar_sfree = bar_sfree;
+  ec.stage_ptr = stage_ptr;
+  ec.stage_stride = L::kStageBytes / 2;
+  ec.s_bias = s_bias;
+  ec.s_tab = s_tab;
+  ec.s_xch = s_xch;
+
+  if (t_begin < t_end) {
+    if (warp == 0) {
+      // ------------------------------------------------------------------ TMA producer
+      if (lane == 0) {
+        mbar_arrive_expect_tx(bar_wfull, L::kTaps * L::kWTapBytes);
+        for (int tap = 0; tap < L::kTaps; ++tap) tma_load_2d(s_w + tap * L::kWTapBytes, &p.map_w, 0, tap * NP, bar_wfull);
+        for (int c = c0; c <= c_last; ++c) {
+          const int i = c - c0, slot = i % kRingSlots, gen = i / kRingSlots;
+          mbar_wait(bar_empty(slot), (gen & 1) ^ 1);
+          const bool mir = slot < kMirrorSlots;
+          mbar_arrive_expect_tx(bar_full(slot), L::kChunkBytes * (mir ? 2 : 1));
+          tma_load_2d(s_ring + slot * L::kChunkBytes, &p.map_in, 0, c * kChunkRows, bar_full(slot));
+          if (mir) tma_load_2d(s_ring + (kRingSlots + slot) * L::kChunkBytes, &p.map_in, 0, c * kChunkRows, bar_full(slot));
+        }
+      }
+    } else if (warp == 1) {
+      // ------------------------------------------------------------------ MMA issuer (one thread)
+      if (lane == 0) {
+        constexpr uint32_t idesc = umma_idesc_bf16(128, L::kN, 0, 0);
+        constexpr uint64_t hi = umma_desc_hi(0, kSbo, kLayout);
+        mbar_wait(bar_wfull, 0);
+        int loaded = c0 - 1, released = c0;  // chunks <= loaded have landed; chunks < released were handed back
+        for (int t = t_begin; t < t_end; ++t) {
+          const int it = t - t_begin, acc = it % ACC, accgen = it / ACC;
+          const int need = hi_chunk(t);
+          while (loaded < need) {
+            ++loaded;
+            const int i = loaded - c0;
+            mbar_wait(bar_full(i % kRingSlots), (i / kRingSlots) & 1);
+          }
+          mbar_wait(bar_tempty(acc), (accgen & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem + acc * L::kN;
+          const int row0 = TS * t - H_ - c0 * kChunkRows;  // window start of dy = 0, relative to the ring origin
+#pragma unroll
+          for (int r = 0; r < KS; ++r) {
+            const int rr = (row0 + (r - H_) * p.Wp) % (kRingSlots * kChunkRows);
+            const uint32_t a_addr = s_ring + rr * L::kRowBytes;
+            const uint32_t b_addr = s_w + r * KS * L::kWTapBytes;
+#pragma unroll
+            for (int k = 0; k < CIN / 16; ++k)
+              umma_bf16(d_tmem, umma_desc(hi, a_addr + k * 32), umma_desc(hi, b_addr + k * 32), idesc, (r | k) != 0);
+          }
+          umma_commit(bar_tfull(acc));
+          // hand back the chunks no later tile needs
+          const int keep_from = (t + 1 < t_end) ? lo_chunk(t + 1) : released;
+          while (released < keep_from) {
+            umma_commit(bar_empty((released - c0) % kRingSlots));
+            ++released;
+          }
+        }
+      }
+    } else if (warp == 2) {
+      // ------------------------------------------------------------------ TMA store issuer (one thread)
+      if (EPI == EPI_FPA && lane == 0) conv_store_loop<TS>(p, ec, t_begin, t_end);
+    } else if (warp >= 4) {
+      // ------------------------------------------------------------------ epilogue (128 threads per column group)
+      conv_epilogue<NP, KS, EPI, ACC, L::kN>(p, ec, warp - 4, lane, t_begin, t_end);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<L::kTmemCols>(tmem);
+}
+
+// ======================================================================================= first layer on tensor cores
+// Small-Cin first layer (KSxKS, CIN in {1,3} -> 64) as ONE GEMM per 128-pixel tile: K = KS*KS*CIN (padded to a
+// multiple of 16), A = im2col rows gathered from the fp32 NHWC frame by four producer warps (one pixel per
+// thread, bf16, written straight into the SW128 K-major layout the MMA reads), B = the packed kernel resident
+// in smem.  It is an HBM-bound layer (reads 4*CIN B, writes 128 B per pixel); the tensor core only removes the
+// 2*K*64 FMAs per pixel that made the CUDA-core version (conv_first_kernel) compute-bound.  Epilogue and store
+// path are shared with conv_tc_kernel (KS=1 form: no lane shift).
+struct alignas(64) ConvGatherParams {
+  ConvTcParams tc;  // map_w, map_out, bias, geometry, act, mask_src/mask_kind, panels
+  const float* x;   // fp32 NHWC frames
+  int FH, FW;       // frame dims
+  int Hin, Win;     // panel-local input window
+  int po;           // pad offset: KS/2 (SAME) or 0 (VALID)
+};
+
+template <int KS, int CIN>
+struct ConvGatherCfg {
+  static constexpr int kKT = KS * KS * CIN;
+  static constexpr int kKP = (kKT + 15) / 16 * 16;
+  static constexpr int kBlocks = (kKP + 63) / 64;       // 64-element K blocks (128-byte rows)
+  static constexpr int kABytes = kBlocks * 128 * 128;    // one A stage
+  static constexpr int kAStages = kBlocks <= 2 ? 4 : 2;
+  static constexpr int kWBytes = kBlocks * 64 * 128;
+  static constexpr int kAcc = 4;
+  static constexpr int kEpiThreads = 512, kGatherThreads = 128, kGatherGroups = 2;  // each group gathers every other tile
+  static constexpr int kThreads = 128 + kEpiThreads + kGatherGroups * kGatherThreads;
+  static constexpr int kOffW = 0;
+  static constexpr int kOffA = kWBytes;
+  static constexpr int kOffStage = kOffA + kAStages * kABytes;
+  static constexpr int kOffBias = kOffStage + 2 * 128 * 64 * 2;
+  static constexpr int kOffTab = kOffBias + 256;
+  static constexpr int kOffXch = kOffTab + 256;
+  static constexpr int kOffBars = kOffXch + 64;
+  static constexpr int kNumBars = 2 * kAStages + 1 + 2 * kAcc + 4;
+  static constexpr int kOffTmemSlot = kOffBars + kNumBars * 8;
+  static constexpr int kTotal = kOffTmemSlot + 16 + 1024;
+};
+
+template <int KS, int CIN>
+__global__ void __launch_bounds__(ConvGatherCfg<KS, CIN>::kThreads, 1) conv_gather_tc_kernel(const __grid_constant__ ConvGatherParams gp) {
+  using L = ConvGatherCfg<KS, CIN>;
+  constexpr int ACC = L::kAcc, AST = L::kAStages;
+  const ConvTcParams& p = gp.tc;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t s_w = s_base + L::kOffW;
+  uint8_t* a_ptr = smem + L::kOffA;
+  const uint32_t s_a = s_base + L::kOffA;
+  float* s_bias = reinterpret_cast<float*>(smem + L::kOffBias);
+  const uint32_t s_bars = s_base + L::kOffBars;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmemSlot);
+  auto bar_afull = [&](int s) { return s_bars + 8u * s; };
+  auto bar_aempty = [&](int s) { return s_bars + 8u * (AST + s); };
+  const uint32_t bar_wfull = s_bars + 8u * (2 * AST);
+  auto bar_tfull = [&](int a) { return s_bars + 8u * (2 * AST + 1 + a); };
+  auto bar_tempty = [&](int a) { return s_bars + 8u * (2 * AST + 1 + ACC + a); };
+  const uint32_t bar_sfull = s_bars + 8u * (2 * AST + 1 + 2 * ACC);
+  const uint32_t bar_sfree = s_bars + 8u * (2 * AST + 1 + 2 * ACC + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t_begin = int((int64_t(blockIdx.x) * p.num_tiles) / gridDim.x);
+  const int t_end = int((int64_t(blockIdx.x + 1) * p.num_tiles) / gridDim.x);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < AST; ++i) {
+      mbar_init(bar_afull(i), L::kGatherThreads);
+      mbar_init(bar_aempty(i), 1);
+    }
+    mbar_init(bar_wfull, 1);
+    for (int i = 0; i < ACC; ++i) {
+      mbar_init(bar_tfull(i), 1);
+      mbar_init(bar_tempty(i), L::kEpiThreads);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_sfull + 8u * i, L::kEpiThreads);
+      mbar_init(bar_sfree + 8u * i, 1);
+    }
+    fence_mbar_init();
+  }
+  if (threadIdx.x < 64) s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
+  if (warp == 1) tmem_alloc<256>(smem_u32(tmem_slot));
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.map_w);
+    tma_prefetch_desc(&p.map_out);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  EpiCtx ec;
+  ec.tmem = tmem;
+  ec.bar_tfull0 = bar_tfull(0);
+  ec.bar_tempty0 = bar_tempty(0);
+  ec.bar_sfull = bar_sfull;
+  ec.bar_sfree = bar_sfree;
+  ec.stage_ptr = smem + L::kOffStage;
+  ec.stage_stride = 128 * 64 * 2;
+  ec.s_bias = s_bias;
+  ec.s_tab = reinterpret_cast<int*>(smem + L::kOffTab);
+  ec.s_xch = reinterpret_cast<float*>(smem + L::kOffXch);
+
+  if (t_begin < t_end) {
+    if (warp == 0) {
+      if (lane == 0) {  // the packed kernel: kBlocks blocks of [64 co][64 k] bf16
+        mbar_arrive_expect_tx(bar_wfull, L::kWBytes);
+        for (int b = 0; b < L::kBlocks; ++b) tma_load_2d(s_w + b * 64 * 128, &p.map_w, 0, b * 64, bar_wfull);
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+        constexpr uint64_t hi = umma_desc_hi(0, 1024, UMMA_LAYOUT_SW128);
+        mbar_wait(bar_wfull, 0);
+        for (int t = t_begin; t < t_end; ++t) {
+          const int it = t - t_begin, acc = it % ACC, st = it % AST;
+          mbar_wait(bar_afull(st), (it / AST) & 1);
+          mbar_wait(bar_tempty(acc), ((it / ACC) & 1) ^ 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < L::kKP / 16; ++k) {
+            const uint32_t a_addr = s_a + st * L::kABytes + (k / 4) * (128 * 128) + (k % 4) * 32;
+            const uint32_t b_addr = s_w + (k / 4) * (64 * 128) + (k % 4) * 32;
+            umma_bf16(tmem + acc * 64, umma_desc(hi, a_addr), umma_desc(hi, b_addr), idesc, k != 0);
+          }
+          umma_commit(bar_tfull(acc));
+          umma_commit(bar_aempty(st));
+        }
+      }
+    } else if (warp == 2) {
+      if (lane == 0) conv_store_loop<128>(p, ec, t_begin, t_end);
+    } else if (warp >= 4 && warp < 20) {
+      conv_epilogue<64, 1, EPI_FPA, ACC, 64>(p, ec, warp - 4, lane, t_begin, t_end);
+    } else if (warp >= 20) {
+      // ------------------------------------------------------------------ im2col gather: one pixel row per thread
+      // Two groups of 128 threads take alternate tiles so two tiles' worth of loads are in flight.  Loads are
+      // unconditional from clamped coordinates and zeroed by a validity select afterwards, so the compiler can
+      // issue a whole chunk's loads back to back.
+      const int gg = (threadIdx.x - 640) >> 7;   // gather group
+      const int r = (threadIdx.x - 640) & 127;   // row of the A tile
+      const int H1 = p.H + 1;
+      for (int t = t_begin + gg; t < t_end; t += L::kGatherGroups) {
+        const int it = t - t_begin, st = it % AST;
+        const int64_t prow = int64_t(128) * t + r;
+        const uint32_t pr = uint32_t(prow);
+        const uint32_t q = pr / uint32_t(p.Wp);
+        const int px = int(pr - q * uint32_t(p.Wp));
+        const int pn = int(q / uint32_t(H1));
+        const int pyy = int(q - uint32_t(pn) * uint32_t(H1));
+        const bool valid = prow < p.rows_valid && px < p.W && pyy > 0;
+        mbar_wait(bar_aempty(st), ((it / AST) & 1) ^ 1);
+        if (valid) {
+          int fn = pn, y0 = 0, x0 = 0;
+          if (p.panels) {
+            const srk_panel e = p.panels[pn];
+            fn = e.frame;
+            y0 = e.y0;
+            x0 = e.x0;
+          }
+          const int y = pyy - 1 - gp.po, x = px - gp.po;  // top-left source pixel (panel-local)
+          const float* frame = gp.x + (int64_t(fn) * gp.FH + y0) * gp.FW * CIN + int64_t(x0) * CIN;
+          uint8_t* arow = a_ptr + st * L::kABytes + r * 128;
+          // per-tap row/column validity and clamped offsets (KS each)
+          int rofs[KS], cofs[KS];
+          bool rok[KS], cok[KS];
+#pragma unroll
+          for (int u = 0; u < KS; ++u) {
+            const int sy = y + u, sx = x + u;
+            rok[u] = sy >= 0 && sy < gp.Hin;
+            cok[u] = sx >= 0 && sx < gp.Win;
+            rofs[u] = min(max(sy, 0), gp.Hin - 1) * gp.FW * CIN;
+            cofs[u] = min(max(sx, 0), gp.Win - 1) * CIN;
+          }
+#pragma unroll
+          for (int c8 = 0; c8 < L::kKP / 8; ++c8) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int k = c8 * 8 + j;
+              f[j] = 0.f;
+              if (k < L::kKT) {
+                const int tap = k / CIN, ci = k % CIN, u = tap / KS, v = tap % KS;
+                const float val = __ldg(frame + rofs[u] + cofs[v] + ci);
+                f[j] = (rok[u] && cok[v]) ? val : 0.f;
+              }
+            }
+            const uint4 q4 = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            *reinterpret_cast<uint4*>(arow + (c8 / 8) * (128 * 128) + (((c8 % 8) ^ (r & 7)) << 4)) = q4;
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(bar_afull(st));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem);
+}
+
+template <int KS, int CIN>
+static int launch_conv_gather(srk_ctx* h, ConvGatherParams& gp, const void* w_packed, void* y_fpa, cudaStream_t stream) {
+  using L = ConvGatherCfg<KS, CIN>;
+  static bool attr_set = false;
+  SRK_REQUIRE(L::kTotal <= h->smem_optin, "conv_first_tc: needs %d B smem, device allows %d", L::kTotal, h->smem_optin);
+  if (!attr_set) {
+    SRK_CHECK_CUDA(cudaFuncSetAttribute(conv_gather_tc_kernel<KS, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_set = true;
+  }
+  ConvTcParams& p = gp.tc;
+  p.num_tiles = int((p.rows_valid + 127) / 128);
+  if (int rc = make_tensor_map_2d(&p.map_w, w_packed, uint64_t(L::kBlocks * 64), 64, 64)) return rc;
+  if (int rc = make_tensor_map_2d(&p.map_out, y_fpa, uint64_t(p.rows_valid), 64, 128)) return rc;
+  const int grid = p.num_tiles < h->num_sms ? p.num_tiles : h->num_sms;
+  conv_gather_tc_kernel<KS, CIN><<<grid, L::kThreads, L::kTotal, stream>>>(gp);
+  SRK_LAUNCH_CHECK();
+  return 0;
 }
 
 // --------------------------------------------------------------------------------------- host side
@@ -580,5 +847,34 @@ extern "C" int srk_conv_tc_last(srk_handle_t h, const void* x_fpa, int cin_p, co
   SRK_CASE(64, 32, 3)
 #undef SRK_CASE
   set_error("srk_conv_tc_last: unsupported (cin_p=%d, cout_p=%d, k=%d)", cin_p, cout_p, k);
+  return -1;
+}
+
+extern "C" int srk_conv_first_tc(srk_handle_t h, const float* x, int n_frames, int FH, int FW, int cin, const void* w_packed,
+                                 const float* bias, int k, int pad_mode, int act, const srk_panel* panels, int n_img, int H, int W,
+                                 void* y_fpa, const void* mask_src, int mask_kind, srk_stream_t stream) {
+  SRK_REQUIRE(h && x && w_packed && y_fpa, "srk_conv_first_tc: null argument");
+  const int halo = (pad_mode == SRK_PAD_VALID) ? k - 1 : 0;
+  SRK_REQUIRE(panels || (n_frames == n_img && FH == H + halo && FW == W + halo),
+              "srk_conv_first_tc: without panels the frame (%dx%d) must match the output geometry (%dx%d, k=%d)", FH, FW, H, W, k);
+  ConvGatherParams gp{};
+  if (int rc = fill_geom(gp.tc, n_img, H, W)) return rc;
+  gp.tc.bias = bias;
+  gp.tc.act = act;
+  gp.tc.mask_src = static_cast<const __nv_bfloat16*>(mask_src);
+  gp.tc.mask_kind = mask_kind;
+  gp.tc.panels = panels;
+  gp.x = x;
+  gp.FH = FH;
+  gp.FW = FW;
+  gp.Hin = H + halo;
+  gp.Win = W + halo;
+  gp.po = (pad_mode == SRK_PAD_VALID) ? 0 : k / 2;
+  cudaStream_t s = as_stream(stream);
+#define SRK_CASE(KS, CIN) \
+  if (k == KS && cin == CIN) return launch_conv_gather<KS, CIN>(h, gp, w_packed, y_fpa, s);
+  SRK_CASE(3, 1) SRK_CASE(3, 3) SRK_CASE(5, 1) SRK_CASE(5, 3) SRK_CASE(9, 1) SRK_CASE(9, 3)
+#undef SRK_CASE
+  set_error("srk_conv_first_tc: unsupported (k=%d, cin=%d)", k, cin);
   return -1;
 }

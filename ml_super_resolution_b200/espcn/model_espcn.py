@@ -1,6 +1,6 @@
 """ESPCN on the B200 conv hot path -- drop-in for espcn/espcn/model_espcn.py of the reference.
 
-  f1  srk_conv_first   5x5 C->64 tanh                           reference :30-38 / :117-120
+  f1  srk_conv_first_tc 5x5 C->64 tanh                          reference :30-38 / :117-120
   f2  srk_conv_tc      3x3 64->32 tanh (tcgen05, N=32 tiles)      reference :40-48 / :123-126
   f3  srk_conv_tc_last 3x3 32->C*r^2 linear, fused depth_to_space reference :54-62 / :132-134 and the
                        host un-pack of espcn/espcn/experiment_test.py:173-177
@@ -40,6 +40,7 @@ class EspcnNet:
         a = self.arena
         self.np3 = ops.pad_cout(self.cout3)
         plan = ops.PackPlan(device)
+        self._i1 = plan.add(a.offsets["f1/kernel:0"], 5, self.C, 64, ops.PACK_FIRST)
         self._i2 = plan.add(a.offsets["f2/kernel:0"], 3, 64, 32, ops.PACK_FWD, 32, 64)
         self._i3 = plan.add(a.offsets["f3/kernel:0"], 3, 32, self.cout3, ops.PACK_FWD, self.np3, 32)
         plan.finalize()
@@ -72,11 +73,11 @@ class EspcnNet:
         a, r = self.arena, (self.r if shuffle else 1)
         if out is None:
             out = torch.empty((n, H * r, W * r, self.cout3 // (r * r)), dtype=torch.float32, device=lr.device)
-        w1, b1, b2 = a.view("f1/kernel:0"), a.view("f1/bias:0"), a.view("f2/bias:0")
-        w2p, w3p = self.plan.views[self._i2], self.plan.views[self._i3]
+        b1, b2 = a.view("f1/bias:0"), a.view("f2/bias:0")
+        w1p, w2p, w3p = self.plan.views[self._i1], self.plan.views[self._i2], self.plan.views[self._i3]
         if W <= MAX_PANEL_W and world == 1 and (tile_rows is None or H <= tile_rows):
             t1, t2 = self._get_bufs(n, H, W)
-            ops.conv_first(lr, w1, b1, "SAME", "tanh", out=t1)
+            ops.conv_first_tc(lr, w1p, b1, 5, "SAME", "tanh", out=t1)
             ops.conv_tc(t1, w2p, b2, 3, "tanh", out=t2)
             ops.conv_tc_last(t2, w3p, self.bias3, 3, self.cout3, None, shuffle_r=r, out=out)
             return out
@@ -89,7 +90,7 @@ class EspcnNet:
             self._panels[key] = ops.make_panels(list(key), self.device)
         panels = self._panels[key]
         t1, t2 = self._get_bufs(len(tiles), Ht, Wt)
-        ops.conv_first(lr, w1, b1, "SAME", "tanh", panels=panels, panel_hw=(Ht, Wt), out=t1)
+        ops.conv_first_tc(lr, w1p, b1, 5, "SAME", "tanh", panels=panels, panel_hw=(Ht, Wt), out=t1)
         ops.conv_tc(t1, w2p, b2, 3, "tanh", out=t2)
         ops.conv_tc_last(t2, w3p, self.bias3, 3, self.cout3, None, shuffle_r=r, panels=panels, frame_shape=(n, H, W), out=out)
         return out

@@ -17,7 +17,7 @@ from ._ffi import SrkPanel, check
 
 ACT = {None: 0, "none": 0, "linear": 0, "relu": 1, "tanh": 2}
 PAD = {"SAME": 0, "same": 0, "VALID": 1, "valid": 1}
-PACK_FWD, PACK_DGRAD, PACK_ROT180T_F32 = 0, 1, 2
+PACK_FWD, PACK_DGRAD, PACK_ROT180T_F32, PACK_FIRST, PACK_FIRST_ROT180T = 0, 1, 2, 3, 4
 
 _handles: dict[int, C.c_void_p] = {}
 
@@ -155,6 +155,40 @@ def conv_first(x: torch.Tensor, w_hwio: torch.Tensor, bias: torch.Tensor | None,
     check(_ffi.lib().srk_conv_first(handle(), _ptr(_f32(x)), nf, fh, fw, cin, _ptr(_f32(w_hwio)), _ptr(bias), k, PAD[padding],
                                     ACT[act], _ptr(panels), n_img, H, W, _ptr(out.data),
                                     _ptr(relu_mask.data if relu_mask is not None else None), _stream()), "srk_conv_first")
+    return out
+
+
+def first_blocks(k: int, c: int) -> int:
+    """64-element K blocks of a first-layer GEMM with K = k*k*c (padded to 16)."""
+    return ((k * k * c + 15) // 16 * 16 + 63) // 64
+
+
+def pack_first_weights(w_hwio: torch.Tensor, mode: int = PACK_FIRST) -> torch.Tensor:
+    """fp32 HWIO -> bf16 [blocks, 64, 64] first-layer form (srk_conv_first_tc)."""
+    k, _, cin, cout = w_hwio.shape
+    c = cin if mode == PACK_FIRST else cout
+    out = torch.empty((first_blocks(k, c), 64, 64), dtype=torch.bfloat16, device=w_hwio.device)
+    check(_ffi.lib().srk_pack_conv_weights(handle(), _ptr(_f32(w_hwio)), k, cin, cout, mode, 64, 64, _ptr(out), _stream()),
+          "srk_pack_conv_weights")
+    return out
+
+
+def conv_first_tc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor | None, k: int, padding="SAME", act=None,
+                  panels: torch.Tensor | None = None, panel_hw: tuple[int, int] | None = None, out: Fpa | None = None,
+                  mask_src: Fpa | None = None, mask_kind=None) -> Fpa:
+    """Small-Cin first layer on tensor cores: fp32 NHWC frames -> FPA (srk_conv_first_tc)."""
+    nf, fh, fw, cin = x.shape
+    halo = k - 1 if PAD[padding] == 1 else 0
+    if panels is None:
+        n_img, H, W = nf, fh - halo, fw - halo
+    else:
+        n_img = panels.shape[0]
+        H, W = panel_hw[0] - halo, panel_hw[1] - halo
+    if out is None:
+        out = fpa_empty(n_img, H, W, 64, x.device)
+    check(_ffi.lib().srk_conv_first_tc(handle(), _ptr(_f32(x)), nf, fh, fw, cin, _ptr(w_packed), _ptr(bias), k, PAD[padding], ACT[act],
+                                       _ptr(panels), n_img, H, W, _ptr(out.data), _ptr(mask_src.data if mask_src is not None else None),
+                                       ACT[mask_kind], _stream()), "srk_conv_first_tc")
     return out
 
 
@@ -343,7 +377,10 @@ class PackPlan:
         dst, elem = 0, 0
         layout = []
         for i, (src, k, cin, cout, mode, np_, cinp) in enumerate(self.jobs):
-            if mode == PACK_ROT180T_F32:
+            if mode in (PACK_FIRST, PACK_FIRST_ROT180T):
+                nb = first_blocks(k, cin if mode == PACK_FIRST else cout)
+                count, esz, shape, dt = nb * 4096, 2, (nb, 64, 64), torch.bfloat16
+            elif mode == PACK_ROT180T_F32:
                 count, esz, shape, dt = k * k * cout * cin, 4, (k, k, cout, cin), torch.float32
             else:
                 count, esz, shape, dt = k * k * np_ * cinp, 2, (k * k, np_, cinp), torch.bfloat16

@@ -6,7 +6,7 @@ signature and dict keys (`conv.{i}`, `relu.{i}`, `sd_images`, `sr_images`, `step
 evaluated by `session.Session.run(fetches, feed_dict)` the way `tf.Session.run` evaluates tensors.
 Underneath, `VdsrNet` drives the libsrk kernels:
 
-  layer 1      srk_conv_first   (3x3, C->64, ReLU)                       reference :62-70 (i = 0)
+  layer 1      srk_conv_first_tc(3x3, C->64, ReLU)                       reference :62-70 (i = 0)
   layers 2..19 srk_conv_tc      (tcgen05 shift-GEMM, 64->64, ReLU)        reference :62-70
   layer 20     srk_conv_tc_last (64->C, fused `sd_images + residual`)     reference :85-104
   loss         srk_mse_fwd_bwd + srk_sumsq_masked (MSE mean + 1e-4*l2)    reference :120-125
@@ -62,11 +62,12 @@ class VdsrNet:
         a, L = self.arena, self.L
         plan = ops.PackPlan(self.device)
         self._fwd_idx, self._dg_idx = {}, {}
+        self._fwd_idx[0] = plan.add(a.offsets[self._kname(0)], 3, self.C, 64, ops.PACK_FIRST)
         for i in range(1, L - 1):
             self._fwd_idx[i] = plan.add(a.offsets[self._kname(i)], 3, 64, 64, ops.PACK_FWD, 64, 64)
             self._dg_idx[i] = plan.add(a.offsets[self._kname(i)], 3, 64, 64, ops.PACK_DGRAD, 64, 64)
         self._fwd_idx[L - 1] = plan.add(a.offsets[self._kname(L - 1)], 3, 64, self.C, ops.PACK_FWD, 16, 64)
-        self._dg_idx[L - 1] = plan.add(a.offsets[self._kname(L - 1)], 3, 64, self.C, ops.PACK_ROT180T_F32)
+        self._dg_idx[L - 1] = plan.add(a.offsets[self._kname(L - 1)], 3, 64, self.C, ops.PACK_FIRST_ROT180T)
         plan.finalize()
         self.plan = plan
         self.bias_last = torch.zeros(16, dtype=torch.float32, device=self.device)
@@ -89,7 +90,7 @@ class VdsrNet:
     # ------------------------------------------------------------------ inference
     def forward(self, sd: torch.Tensor, taps: dict | None = None, out: torch.Tensor | None = None, tile_rows: int | None = None,
                 rank: int = 0, world: int = 1) -> torch.Tensor:
-        """sd fp32 [N,H,W,C] on device -> sr.  Frames wider than 254 px (or taller than `tile_rows`) are
+        """sd fp32 [N,H,W,C] on device -> sr.  Frames wider than 223 px (or taller than `tile_rows`) are
         cut into halo-overlapped tiles; with world > 1 this rank computes only its shard of the tiles
         (tile-sharded multi-GPU inference, no collective; pixels it does not own are left untouched)."""
         n, H, W, C = sd.shape
@@ -100,7 +101,7 @@ class VdsrNet:
             out = torch.empty_like(sd)
         if not need_tiles:
             bufs = self._get_infer_bufs(n, H, W)
-            t = ops.conv_first(sd, a.view(self._kname(0)), a.view(self._bname(0)), "SAME", "relu", out=bufs[0])
+            t = ops.conv_first_tc(sd, self.wf(0), a.view(self._bname(0)), 3, "SAME", "relu", out=bufs[0])
             if taps is not None:
                 taps["conv.1"] = taps["relu.1"] = ops.fpa_to_nhwc(t)
             for i in range(1, self.L - 1):
@@ -122,8 +123,8 @@ class VdsrNet:
             key = (tuple(t.as_tuple() for t in chunk), str(sd.device))
             panels = self._panel_cache(key)
             bufs = self._get_infer_bufs(len(chunk), Ht, Wt)
-            t = ops.conv_first(sd, a.view(self._kname(0)), a.view(self._bname(0)), "SAME", "relu", panels=panels, panel_hw=(Ht, Wt),
-                               out=bufs[0])
+            t = ops.conv_first_tc(sd, self.wf(0), a.view(self._bname(0)), 3, "SAME", "relu", panels=panels, panel_hw=(Ht, Wt),
+                                  out=bufs[0])
             for i in range(1, self.L - 1):
                 t = ops.conv_tc(t, self.wf(i), a.view(self._bname(i)), 3, "relu", out=bufs[i % 2])
             ops.conv_tc_last(t, self.wf(self.L - 1), self.bias_last, 3, self.C, None, addend=sd, panels=panels, frame_shape=(n, H, W),
@@ -180,12 +181,12 @@ class VdsrNet:
         buffer dict (`loss` = [mse, reg], `sr`).  `numel_total` = GLOBAL element count under data
         parallelism so that summing rank gradients reproduces the single-GPU MEAN reduction."""
         n, H, W, C = sd.shape
-        assert W <= MAX_PANEL_W, "training patches wider than 254 px are not supported by the flat-stream kernels"
+        assert W <= MAX_PANEL_W, "training patches wider than 223 px are not supported by the flat-stream kernels"
         a, L = self.arena, self.L
         b = self._get_train_bufs(n, H, W)
         acts, dyb = b["acts"], b["dy"]
         # ---- forward, keeping every activation for the backward pass
-        ops.conv_first(sd, a.view(self._kname(0)), a.view(self._bname(0)), "SAME", "relu", out=acts[0])
+        ops.conv_first_tc(sd, self.wf(0), a.view(self._bname(0)), 3, "SAME", "relu", out=acts[0])
         for i in range(1, L - 1):
             ops.conv_tc(acts[i - 1], self.wf(i), a.view(self._bname(i)), 3, "relu", out=acts[i])
         ops.conv_tc_last(acts[L - 2], self.wf(L - 1), self.bias_last, 3, C, None, addend=sd, out=b["sr"])
@@ -196,7 +197,7 @@ class VdsrNet:
         ops.sumsq_masked(a.w, a.decay_mask, 0.5 * WEIGHT_DECAY, b["loss"][1:2])
         # ---- backward
         ops.conv_last_wgrad(acts[L - 2], b["dsr"], a.view(self._kname(L - 1), "g"), a.view(self._bname(L - 1), "g"))
-        d = ops.conv_first(b["dsr"], self.wd(L - 1), None, "SAME", None, out=dyb[0], relu_mask=acts[L - 2])
+        d = ops.conv_first_tc(b["dsr"], self.wd(L - 1), None, 3, "SAME", None, out=dyb[0], mask_src=acts[L - 2], mask_kind="relu")
         stride = b["wg_stride"]
         for i in range(L - 2, 0, -1):
             ws = b["wg_ws"][(i - 1) * stride:i * stride]

@@ -59,11 +59,56 @@ def test_conv_first(srk_ops, k, cin, pad, act, shape):
     assert np.all(raw[: y.n_img * S][is_pad] == 0)
 
 
+@pytest.mark.parametrize("k,cin,pad,act,shape", [
+    (3, 3, "SAME", "relu", (2, 9, 11)),
+    (3, 1, "SAME", None, (1, 16, 7)),
+    (5, 1, "SAME", "tanh", (2, 12, 13)),
+    (5, 3, "SAME", "tanh", (1, 17, 17)),
+    (9, 3, "VALID", "relu", (2, 21, 23)),
+    (9, 1, "VALID", "relu", (3, 33, 33)),
+    (3, 3, "SAME", "relu", (64, 41, 41)),
+    (5, 1, "SAME", "tanh", (1, 40, 250)),
+])
+def test_conv_first_tc(srk_ops, k, cin, pad, act, shape):
+    """Tensor-core first layer: inputs and weights are rounded to bf16 by the kernel, so the oracle gets the same."""
+    n, h, w = shape
+    r = _rng(k * 100 + cin + 7)
+    x = r.uniform(-1, 1, (n, h, w, cin)).astype(np.float32)
+    wt = (r.standard_normal((k, k, cin, 64)) * 0.2).astype(np.float32)
+    b = (r.standard_normal(64) * 0.1).astype(np.float32)
+    wp = srk_ops.pack_first_weights(_dev(wt))
+    y = srk_ops.conv_first_tc(_dev(x), wp, _dev(b), k, pad, act)
+    got = srk_ops.fpa_to_nhwc(y).cpu().numpy()
+    ref = O.conv2d_nhwc(_bf(x), _bf(wt), b, pad, act)
+    assert got.shape == ref.shape
+    _close_bf16(got, ref, abs_=3e-3)
+    # and against the un-rounded fp64 oracle within the model-level bf16 budget
+    assert np.abs(got - O.conv2d_nhwc(x, wt, b, pad, act)).max() <= 4e-2
+    raw = y.data.float().cpu().numpy()
+    Wp, S = y.W + 1, (y.H + 1) * (y.W + 1)
+    rows = np.arange(y.n_img * S)
+    is_pad = ((rows % Wp) == y.W) | (((rows // Wp) % (y.H + 1)) == 0)
+    assert np.all(raw[: y.n_img * S][is_pad] == 0)
+
+
+def test_last_layer_dgrad_via_first_tc(srk_ops):
+    """dX = conv(dY[...,3], rot180(W)^T) * relu'(saved): the first-layer kernel with SRK_PACK_FIRST_ROT180T weights."""
+    r = _rng(11)
+    n, h, w = 4, 19, 21
+    dy = (r.standard_normal((n, h, w, 3)) * 1e-3).astype(np.float32)
+    wt = (r.standard_normal((3, 3, 64, 3)) / 24).astype(np.float32)
+    saved = _bf(r.standard_normal((n, h, w, 64)))
+    wp = srk_ops.pack_first_weights(_dev(wt), srk_ops.PACK_FIRST_ROT180T)
+    dx = srk_ops.conv_first_tc(_dev(dy), wp, None, 3, "SAME", None, mask_src=srk_ops.fpa_from_nhwc(_dev(saved)), mask_kind="relu")
+    gx, _, _ = O.conv2d_backward(np.zeros((n, h, w, 64)), _bf(wt), np.zeros(3), _bf(dy), "SAME", None)
+    _close_bf16(srk_ops.fpa_to_nhwc(dx).cpu().numpy(), gx * (saved > 0), abs_=1e-6)
+
+
 @pytest.mark.parametrize("cin,cout,k,act,shape", [
     (64, 64, 3, "relu", (2, 7, 9)),
     (64, 64, 3, "relu", (64, 41, 41)),
     (64, 64, 3, None, (1, 5, 130)),     # Wp > 127: two chunks of look-behind
-    (64, 64, 3, "relu", (1, 300, 254)),  # widest supported panel
+    (64, 64, 3, "relu", (1, 300, 223)),  # widest supported panel
     (64, 32, 3, "tanh", (2, 17, 17)),
     (64, 64, 1, None, (3, 32, 32)),
     (64, 32, 1, "relu", (2, 25, 25)),

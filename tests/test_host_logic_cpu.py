@@ -10,7 +10,7 @@ import torch
 from ml_super_resolution_b200.tiling import MAX_PANEL_W, plan_tiles, shard_tiles
 
 
-@pytest.mark.parametrize("FH,FW,halo,max_h", [(2160, 3840, 20, None), (1080, 1920, 4, None), (41, 41, 20, None), (300, 255, 20, 100),
+@pytest.mark.parametrize("FH,FW,halo,max_h", [(2160, 3840, 20, None), (1080, 1920, 4, None), (41, 41, 20, None), (300, 255, 20, 100), (64, 224, 4, None),
                                              (96, 200, 8, 40), (2160, 3840, 20, 540), (17, 1000, 13, None)])
 def test_tiles_cover_frame_once_with_halo(FH, FW, halo, max_h):
     Ht, Wt, tiles = plan_tiles(2, FH, FW, halo, MAX_PANEL_W, max_h)

@@ -135,7 +135,10 @@ def test_vdsr_graphed_step_equals_eager(srk_ops):
     for _ in range(3):
         le = float(eager.train_step(sdt, hdt, lr=1e-3))
         lg = float(gstep(1e-3).sum())
-        assert le == pytest.approx(lg, rel=1e-6)
+        assert le == pytest.approx(lg, rel=2e-5)  # the MSE partial sums meet in an fp32 atomic: order-dependent last bits
     we, wg = eager.arena.to_numpy(), graphed.arena.to_numpy()
     for k in we:
-        assert np.allclose(we[k], wg[k], rtol=1e-4, atol=1e-6), k  # (first/last-layer wgrad use fp32 atomics: order-dependent last bits)
+        # first/last-layer wgrad and the MSE sum use fp32 atomics (order-dependent last bits); Adam's first steps act like
+        # sign(g), so a gradient element near zero may move the other way: bounded by 2*lr per step, and rare
+        d = np.abs(we[k] - wg[k])
+        assert d.max() <= 3 * 2e-3 and d.mean() <= 2e-5, (k, d.max(), d.mean())

@@ -35,8 +35,8 @@ def main():
     dev = "cuda"
     g = torch.Generator(device=dev).manual_seed(0)
     # ---- 64->64 3x3 layer on the VDSR training shape and on one inference panel group
-    for name, (n, h, w) in {"train_64x41x41": (64, 41, 41), "train_64x128x128": (64, 128, 128), "panel_18x2160x252": (18, 2160, 252),
-                            "panel_4x540x252": (4, 540, 252)}.items():
+    for name, (n, h, w) in {"train_64x41x41": (64, 41, 41), "train_64x128x128": (64, 128, 128), "panel_21x2160x223": (21, 2160, 223),
+                            "panel_4x540x223": (4, 540, 223)}.items():
         x = ops.fpa_empty(n, h, w, 64)
         x.data.normal_(generator=g)
         y = ops.fpa_empty(n, h, w, 64)
@@ -68,8 +68,8 @@ def main():
         panels = ops.make_panels([t.as_tuple() for t in tiles])
         t1, t2 = net._get_bufs(len(tiles), Ht, Wt)
         a = net.arena
-        med, mn = timeit(lambda: ops.conv_first(lr, a.view("f1/kernel:0"), a.view("f1/bias:0"), "SAME", "tanh", panels=panels,
-                                                 panel_hw=(Ht, Wt), out=t1))
+        med, mn = timeit(lambda: ops.conv_first_tc(lr, net.plan.views[net._i1], a.view("f1/bias:0"), 5, "SAME", "tanh", panels=panels,
+                                                    panel_hw=(Ht, Wt), out=t1))
         res[f"espcn_1080p_C{C}/f1_conv_first"] = dict(ms=med, ms_min=mn)
         med, mn = timeit(lambda: ops.conv_tc(t1, net.plan.views[net._i2], a.view("f2/bias:0"), 3, "tanh", out=t2))
         res[f"espcn_1080p_C{C}/f2_conv_tc"] = dict(ms=med, ms_min=mn)
