@@ -36,9 +36,10 @@ namespace srk {
 
 enum { EPI_FPA = 0, EPI_NHWC = 1 };
 
-constexpr int kChunkRows = 64;
-constexpr int kRingSlots = 12;   // ring of 64-row chunks ...
-constexpr int kMirrorSlots = 2;  // ... whose first 128 rows are duplicated behind the last slot
+constexpr int kChunkRows = 64;   // ring granularity (32-row chunks measured slower: per-TMA-op cost)
+constexpr int kMirrorSlots = 2;  // the ring's first 128 rows are duplicated behind its last slot
+constexpr int kMaxRingSlots = 40;
+constexpr int kSmemBudget = 227 * 1024;
 
 struct alignas(64) ConvTcParams {
   CUtensorMap map_in;   // [rows_valid][CIN]  box {CIN, 64}
@@ -74,24 +75,31 @@ struct ConvTcCfg {
   static constexpr int kTmemCols = kTmemColsRaw <= 32 ? 32 : kTmemColsRaw <= 64 ? 64 : kTmemColsRaw <= 128 ? 128 : kTmemColsRaw <= 256 ? 256 : 512;
   static constexpr int kWTapBytes = NP * kRowBytes;
   static constexpr int kWBytes = ((kTaps * kWTapBytes + 1023) / 1024) * 1024;
-  static constexpr int kRingBytes = (kRingSlots + kMirrorSlots) * kChunkBytes;
-  static constexpr int kStageBytes = 2 * 128 * NP * 2;  // output staging (EPI_FPA), double buffered
+  static constexpr int kStageBufs = (NP == 64 && CIN == 64 && KS == 3) ? 1 : 2;  // the widest config spends its smem on the ring
+  static constexpr int kStageBytes = kStageBufs * 128 * NP * 2;                  // output staging (EPI_FPA)
   static constexpr int kGroups = 4;                 // epilogue column groups (4 warps each): 16 epilogue warps
   static constexpr int kColPass = NP / kGroups;     // accumulator columns per epilogue thread (16 / 8 / 4)
   static constexpr int kEpiThreads = 128 * kGroups;
   static constexpr int kThreads = 128 + kEpiThreads;
-  static constexpr int kXchGroupFloats = 2 /*parity*/ * 4 /*quadrants*/ * (KS > 1 ? (KS - 1) * kHalo : 1) * kColPass;
+  static constexpr int kXchGroupFloats = 2 /*parity*/ * 4 /*quadrants*/ * (KS > 1 ? (KS - 1) * kHalo : 1) * kColPass;  // == kXgrp / 4 in conv_epilogue
   static constexpr int kXchFloats = kXchGroupFloats * kGroups;
+  static constexpr int kXchBytes = ((kXchFloats * 4 + 15) / 16) * 16;
+  // every byte left after weights / staging / bookkeeping goes to the input ring: look-ahead is what hides HBM latency
+  static constexpr int kFixedBytes = kWBytes + kStageBytes + 256 + 256 + kXchBytes + (2 * kMaxRingSlots + 16) * 8 + 16 + 1024;
+  static constexpr int kRingSlotsRaw = (kSmemBudget - kFixedBytes) / kChunkBytes - kMirrorSlots;
+  static constexpr int kRingSlots = kRingSlotsRaw > kMaxRingSlots ? kMaxRingSlots : kRingSlotsRaw;
+  static constexpr int kRingBytes = (kRingSlots + kMirrorSlots) * kChunkBytes;
   static constexpr int kOffW = 0;
   static constexpr int kOffRing = kWBytes;
   static constexpr int kOffStage = kOffRing + kRingBytes;
   static constexpr int kOffBias = kOffStage + kStageBytes;
   static constexpr int kOffTab = kOffBias + 256;    // NHWC epilogue: per-channel output offsets
   static constexpr int kOffXch = kOffTab + 256;
-  static constexpr int kOffBars = kOffXch + ((kXchFloats * 4 + 15) / 16) * 16;
+  static constexpr int kOffBars = kOffXch + kXchBytes;
   static constexpr int kNumBars = 2 * kRingSlots + 1 + 2 * kAccStages + 4;
   static constexpr int kOffTmemSlot = kOffBars + kNumBars * 8;
   static constexpr int kTotal = kOffTmemSlot + 16 + 1024;  // + alignment slack
+  static_assert(kTotal <= kSmemBudget && kRingSlots >= 10, "shared-memory plan does not fit");
   static_assert(kN % 16 == 0 && kN <= 256, "invalid UMMA N");
 };
 
@@ -129,23 +137,40 @@ __device__ __forceinline__ void tmem_load_cols(uint32_t taddr, float (&v)[NCOL])
 struct EpiCtx {
   uint32_t tmem;
   uint32_t bar_tfull0, bar_tempty0;  // + 8 * accumulator stage
-  uint32_t bar_sfull, bar_sfree;  // + 8 * staging buffer
-  uint8_t* stage_ptr;
-  int stage_stride;               // bytes between the two staging buffers
+  uint32_t bar_sfull, bar_sfree;     // + 8 * staging buffer
+  uint32_t stage_addr;               // shared-window address of staging buffer 0
+  int stage_stride;                  // bytes between the staging buffers
+  int stage_bufs;                    // 1 or 2
+  uint32_t xch_addr;                 // shared-window address of the lane-exchange area
   float* s_bias;
   int* s_tab;
-  float* s_xch;
 };
 
-// One thread: wait for a complete staging tile, TMA-store it, hand the staging buffer back.
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// One thread: wait for a complete staging tile, TMA-store it, hand the staging buffers back.
 template <int TS>
 __device__ __forceinline__ void conv_store_loop(const ConvTcParams& p, const EpiCtx& e, int t_begin, int t_end) {
+  const bool dbl = e.stage_bufs == 2;
   for (int t = t_begin; t < t_end; ++t) {
-    const int it = t - t_begin, sb = it & 1, sgen = it >> 1;
+    const int it = t - t_begin, sb = dbl ? (it & 1) : 0, sgen = dbl ? (it >> 1) : it;
     mbar_wait(e.bar_sfull + 8u * sb, sgen & 1);
-    tma_store_2d(&p.map_out, 0, TS * t, smem_u32(e.stage_ptr + sb * e.stage_stride));
+    tma_store_2d(&p.map_out, 0, TS * t, e.stage_addr + sb * e.stage_stride);
     tma_store_commit();
-    if (it >= 1) {  // the store of tile it-1 has finished READING its staging buffer -> writers of tile it+1 may reuse it
+    if (!dbl) {
+      tma_store_wait_read<0>();  // smem has been read: the staging buffer may be overwritten
+      mbar_arrive(e.bar_sfree);
+    } else if (it >= 1) {  // the store of tile it-1 has finished READING its buffer -> writers of tile it+1 may reuse it
       tma_store_wait_read<1>();
       mbar_arrive(e.bar_sfree + 8u * (sb ^ 1));
     }
@@ -153,233 +178,280 @@ __device__ __forceinline__ void conv_store_loop(const ConvTcParams& p, const Epi
   tma_store_wait_all<0>();
 }
 
-// Epilogue warp `ewarp` (0..15): TMEM lane quadrant ewarp & 3, column group ewarp >> 2.
+// Epilogue warp `ewarp` (0..15): TMEM lane quadrant ewarp & 3, column group ewarp >> 2 (CP = NP/4 channels).
+// Per tile and thread: KS tcgen05.ld of CP columns -> lane-shift add (rotating shuffles; the two edge lanes of a
+// warp first swap in the neighbouring quadrant's row through shared memory) -> packed fp32x2 bias add -> bf16x2
+// pack -> ReLU / ReLU' mask on the packed pairs -> two swizzled 16-byte stores into the staging tile.
 template <int NP, int KS, int EPI, int ACC, int KN>
 __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCtx& e, int ewarp, int lane, int t_begin, int t_end) {
   constexpr int H_ = KS / 2, TS = 128 - (KS - 1), CP = NP / 4;
-  constexpr int kXchGroupFloats = 2 * 4 * (KS > 1 ? (KS - 1) * H_ : 1) * CP;
+  constexpr int kNB = (KS > 1) ? KS - 1 : 1;           // shifted blocks
+  constexpr int kXq = kNB * (H_ > 0 ? H_ : 1) * CP * 4;  // bytes per (parity, quadrant)
+  constexpr int kXpar = 4 * kXq;                       // bytes per parity
+  constexpr int kXgrp = 2 * kXpar;                     // bytes per column group
   const uint32_t tmem = e.tmem;
-  float* s_bias = e.s_bias;
-  int* s_tab = e.s_tab;
-  float* s_xch = e.s_xch;
-  auto bar_tfull = [&](int a) { return e.bar_tfull0 + 8u * a; };
-  auto bar_tempty = [&](int a) { return e.bar_tempty0 + 8u * a; };
+  const int quad = ewarp & 3;   // TMEM lane quadrant this warp may access (hardware: warp index % 4)
+  const int grp = ewarp >> 2;   // column group: channels [CP*grp, CP*grp + CP)
+  const int row = quad * 32 + lane;  // lane j of the accumulator <-> flat row TS*t - h + j
+  const int col0 = grp * CP;
+  const bool lane_valid = (row >= H_) && (row < H_ + TS);
+  const uint32_t xg = e.xch_addr + grp * kXgrp;
+  float bias_r[CP];
+  int tab_r[CP];
+#pragma unroll
+  for (int c = 0; c < CP; ++c) {
+    bias_r[c] = e.s_bias[col0 + c];
+    tab_r[c] = (EPI == EPI_NHWC) ? e.s_tab[col0 + c] : 0;
+  }
+  // per-thread constant addresses of the lane exchange (parity 0) ...
+  uint32_t pub_addr[KS], sub_addr[KS];
+  bool do_pub[KS], do_sub[KS];
+#pragma unroll
+  for (int b = 0; b < KS; ++b) {
+    const int dx = b - H_;
+    const int bi = (dx < 0) ? b : b - 1;
+    const bool edge = (dx < 0) ? (lane >= 32 + dx) : (dx > 0 ? lane < dx : false);
+    const int li = (dx < 0) ? lane - (32 + dx) : lane;
+    const int nq = (dx < 0) ? quad - 1 : quad + 1;
+    do_pub[b] = edge;
+    do_sub[b] = edge && nq >= 0 && nq < 4;
+    pub_addr[b] = xg + quad * kXq + (bi * H_ + li) * CP * 4;
+    sub_addr[b] = xg + nq * kXq + (bi * H_ + li) * CP * 4;
+  }
+  // ... and of this thread's 16-byte chunks in staging buffer 0
+  uint32_t st_addr[CP >= 8 ? CP / 8 : 1];
+  if constexpr (EPI == EPI_FPA) {
+    const int srow = row - H_;
+    const int sw = (NP == 64) ? (srow & 7) : ((srow >> 1) & 3);
+#pragma unroll
+    for (int j = 0; j < CP / 8; ++j) st_addr[j] = e.stage_addr + srow * (NP * 2) + (((grp * (CP / 8) + j) ^ sw) << 4);
+  }
+  // pixel coordinates of this lane's row in the first tile, then advanced by TS rows per tile
+  const int H1 = p.H + 1;
+  int px, pyy, pn;
   {
-      const int quad = ewarp & 3;   // TMEM lane quadrant this warp may access (hardware: warp index % 4)
-      const int grp = ewarp >> 2;   // column group: channels [CP*grp, CP*grp + CP)
-      const int row = quad * 32 + lane;  // lane j of the accumulator <-> flat row TS*t - h + j
-      const int col0 = grp * CP;
-      const bool lane_valid = (row >= H_) && (row < H_ + TS);
-      float* xg = s_xch + grp * kXchGroupFloats;
-      constexpr int kXq = (KS > 1 ? (KS - 1) * H_ : 1) * CP;  // floats per (parity, quadrant)
-      float bias_r[CP];
-      int tab_r[CP];
-#pragma unroll
-      for (int c = 0; c < CP; ++c) {
-        bias_r[c] = s_bias[col0 + c];
-        tab_r[c] = (EPI == EPI_NHWC) ? s_tab[col0 + c] : 0;
-      }
-      int xpar = 0;
-      // pixel coordinates of this lane's row in the first tile; lanes below the halo never hold a valid output
-      const int H1 = p.H + 1;
-      int px, pyy, pn;
-      {
-        const int64_t prow0 = int64_t(TS) * t_begin - H_ + row;
-        const uint32_t pr = uint32_t(prow0 < 0 ? 0 : prow0);
-        const uint32_t q = pr / uint32_t(p.Wp);
-        px = int(pr - q * uint32_t(p.Wp));
-        pn = int(q / uint32_t(H1));
-        pyy = int(q - uint32_t(pn) * uint32_t(H1));
-      }
-      const int adv_x = TS % p.Wp, adv_q = TS / p.Wp;
-      const int adv_y = adv_q % H1, adv_n = adv_q / H1;
-      for (int t = t_begin; t < t_end; ++t) {
-        const int it = t - t_begin, acc = it % ACC, accgen = it / ACC;
-        mbar_wait(bar_tfull(acc), accgen & 1);
-        tc_fence_after();
-        const uint32_t taddr = tmem + acc * KN + col0 + (uint32_t(quad * 32) << 16);
-        float blk[KS][CP];
-#pragma unroll
-        for (int b = 0; b < KS; ++b) tmem_load_cols<CP>(taddr + b * NP, blk[b]);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(bar_tempty(acc));
-        float v[CP];
-        if constexpr (KS > 1) {
-          // ---- lane-shift add of the KS column blocks: y[j] = sum_dx D[j + dx][block dx]
-          // edge lanes publish what the neighbouring quadrants need: block dx<0 from the top lanes, dx>0 from the bottom lanes
-          float* xq = xg + (xpar * 4 + quad) * kXq;
-#pragma unroll
-          for (int b = 0; b < KS; ++b) {
-            const int dx = b - H_;
-            const int bi = (dx < 0) ? b : b - 1;  // index among the KS-1 shifted blocks
-            if (dx < 0 && lane >= 32 + dx) {
-              float4* dst = reinterpret_cast<float4*>(xq + (bi * H_ + (lane - (32 + dx))) * CP);
-#pragma unroll
-              for (int c = 0; c < CP / 4; ++c) dst[c] = make_float4(blk[b][4 * c], blk[b][4 * c + 1], blk[b][4 * c + 2], blk[b][4 * c + 3]);
-            }
-            if (dx > 0 && lane < dx) {
-              float4* dst = reinterpret_cast<float4*>(xq + (bi * H_ + lane) * CP);
-#pragma unroll
-              for (int c = 0; c < CP / 4; ++c) dst[c] = make_float4(blk[b][4 * c], blk[b][4 * c + 1], blk[b][4 * c + 2], blk[b][4 * c + 3]);
-            }
-          }
-          named_bar_sync(1 + grp, 128);
-          // lanes whose shuffle would wrap around the warp first take over the neighbouring quadrant's row
-          // (their own value of that block is not needed any more), then ONE rotating shuffle per column
-          // serves every lane -- no per-element select, and every output sees the same fp32 addition order
-#pragma unroll
-          for (int b = 0; b < KS; ++b) {
-            const int dx = b - H_;
-            if (dx == 0) continue;
-            const int bi = (dx < 0) ? b : b - 1;
-            const bool edge = (dx < 0) ? (lane >= 32 + dx) : (lane < dx);
-            const int nq = (dx < 0) ? quad - 1 : quad + 1;
-            if (edge && nq >= 0 && nq < 4) {
-              const int li = (dx < 0) ? lane - (32 + dx) : lane;
-              const float4* src = reinterpret_cast<const float4*>(xg + (xpar * 4 + nq) * kXq + (bi * H_ + li) * CP);
-#pragma unroll
-              for (int c = 0; c < CP / 4; ++c) {
-                const float4 o = src[c];
-                blk[b][4 * c] = o.x;
-                blk[b][4 * c + 1] = o.y;
-                blk[b][4 * c + 2] = o.z;
-                blk[b][4 * c + 3] = o.w;
-              }
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < CP; ++c) v[c] = blk[H_][c];
-#pragma unroll
-          for (int b = 0; b < KS; ++b) {
-            const int dx = b - H_;
-            if (dx == 0) continue;
-            const int src_lane = (lane + dx) & 31;  // y[j] += D[j + dx][block dx]
-#pragma unroll
-            for (int c = 0; c < CP; ++c) v[c] += __shfl_sync(0xffffffffu, blk[b][c], src_lane);
-          }
-          xpar ^= 1;
-        } else {
-#pragma unroll
-          for (int c = 0; c < CP; ++c) v[c] = blk[0][c];
-        }
+    const int64_t prow0 = int64_t(TS) * t_begin - H_ + row;
+    const uint32_t pr = uint32_t(prow0 < 0 ? 0 : prow0);
+    const uint32_t q = pr / uint32_t(p.Wp);
+    px = int(pr - q * uint32_t(p.Wp));
+    pn = int(q / uint32_t(H1));
+    pyy = int(q - uint32_t(pn) * uint32_t(H1));
+  }
+  const int adv_x = TS % p.Wp, adv_q = TS / p.Wp;
+  const int adv_y = adv_q % H1, adv_n = adv_q / H1;
+  const int act = p.act;
+  uint32_t xpar = 0;  // byte offset of the exchange parity in use
 
-        // the pixel this lane holds (decoded once per CTA, then advanced by TS rows per tile)
-        const int64_t prow = int64_t(TS) * t - H_ + row;
-        const bool valid_px = lane_valid && prow < p.rows_valid && (px < p.W) && (pyy > 0);
-        bool valid = valid_px;
-        const int n = pn, y = pyy - 1, x = px;
-        {
-          px += adv_x;
-          const int cx = px >= p.Wp;
-          px -= cx ? p.Wp : 0;
-          pyy += adv_y + cx;
-          const int cy = pyy >= H1;
-          pyy -= cy ? H1 : 0;
-          pn += adv_n + cy;
-        }
+  for (int t = t_begin; t < t_end; ++t) {
+    const int it = t - t_begin, acc = it % ACC, accgen = it / ACC;
+    mbar_wait(e.bar_tfull0 + 8u * acc, accgen & 1);
+    tc_fence_after();
+    const uint32_t taddr = tmem + acc * KN + col0 + (uint32_t(quad * 32) << 16);
+    float blk[KS][CP];
+#pragma unroll
+    for (int b = 0; b < KS; ++b) tmem_load_cols<CP>(taddr + b * NP, blk[b]);
+    tmem_ld_wait();
+    tc_fence_before();
+    mbar_arrive(e.bar_tempty0 + 8u * acc);
 
-        if constexpr (EPI == EPI_FPA) {
-          static_assert(CP >= 8, "FPA epilogue stores 16-byte chunks");
-          uint32_t packed[CP / 2];
-          if (valid) {
+    float v[CP];
 #pragma unroll
-            for (int c = 0; c < CP; ++c) v[c] = act_apply(v[c] + bias_r[c], p.act);
-            if (p.mask_src) {
-              const uint4* m = reinterpret_cast<const uint4*>(p.mask_src + size_t(prow) * NP + col0);
+    for (int c = 0; c < CP; ++c) v[c] = blk[H_][c];
+    if constexpr (KS > 1) {
+      // ---- lane-shift add of the KS column blocks: y[j] = sum_dx D[j + dx][block dx]
 #pragma unroll
-              for (int j = 0; j < CP / 8; ++j) {
-                const uint4 mv = __ldg(m + j);
-                const uint32_t w4[4] = {mv.x, mv.y, mv.z, mv.w};
+      for (int b = 0; b < KS; ++b) {
+        if (b == H_) continue;
+        if (do_pub[b]) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e]));
-                  if (p.mask_kind == SRK_ACT_RELU) {
-                    v[j * 8 + e * 2] = f.x > 0.f ? v[j * 8 + e * 2] : 0.f;
-                    v[j * 8 + e * 2 + 1] = f.y > 0.f ? v[j * 8 + e * 2 + 1] : 0.f;
-                  } else {
-                    v[j * 8 + e * 2] *= (1.f - f.x * f.x);
-                    v[j * 8 + e * 2 + 1] *= (1.f - f.y * f.y);
-                  }
-                }
-              }
-            }
-            if (p.addend_fpa) {
-              const uint4* a = reinterpret_cast<const uint4*>(p.addend_fpa + size_t(prow) * NP + col0);
+          for (int c = 0; c < CP / 4; ++c) sts128(pub_addr[b] + xpar + c * 16, blk[b][4 * c], blk[b][4 * c + 1], blk[b][4 * c + 2], blk[b][4 * c + 3]);
+        }
+      }
+      named_bar_sync(1 + grp, 128);
+      // the edge lanes take over the neighbouring quadrant's row (their own value of that block is not needed any
+      // more); then ONE rotating shuffle per column serves every lane: no per-element select, and every output
+      // sees the same fp32 addition order (tiled == un-tiled bit for bit)
 #pragma unroll
-              for (int j = 0; j < CP / 8; ++j) {
-                const uint4 av = __ldg(a + j);
-                const uint32_t w4[4] = {av.x, av.y, av.z, av.w};
+      for (int b = 0; b < KS; ++b) {
+        if (b == H_) continue;
+        if (do_sub[b]) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e]));
-                  v[j * 8 + e * 2] += f.x;
-                  v[j * 8 + e * 2 + 1] += f.y;
-                }
-              }
-              if (p.relu_after_add) {
-#pragma unroll
-                for (int c = 0; c < CP; ++c) v[c] = fmaxf(v[c], 0.f);
-              }
-            }
-#pragma unroll
-            for (int c = 0; c < CP / 2; ++c) packed[c] = pack_bf16x2(v[2 * c], v[2 * c + 1]);
-          } else {
-#pragma unroll
-            for (int c = 0; c < CP / 2; ++c) packed[c] = 0u;  // pad rows/columns stay exactly zero
+          for (int c = 0; c < CP / 4; ++c) {
+            const float4 o = lds128(sub_addr[b] + xpar + c * 16);
+            blk[b][4 * c] = o.x;
+            blk[b][4 * c + 1] = o.y;
+            blk[b][4 * c + 2] = o.z;
+            blk[b][4 * c + 3] = o.w;
           }
-          // staging buffer free? (the store of tile it-2, which used the same buffer, has finished reading it)
-          const int sb = it & 1, sgen = it >> 1;
-          uint8_t* stage_ptr = e.stage_ptr + sb * e.stage_stride;
-          mbar_wait(e.bar_sfree + 8u * sb, (sgen & 1) ^ 1);
-          if (lane_valid) {
-            constexpr int kOutRowBytes = NP * 2;
-            const int srow = row - H_;  // staging row = output row within the tile
-            const int sw = (NP == 64) ? (srow & 7) : ((srow >> 1) & 3);
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < KS; ++b) {
+        if (b == H_) continue;
+        const int src_lane = (lane + (b - H_)) & 31;
+        float sh[CP];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) sh[c] = __shfl_sync(0xffffffffu, blk[b][c], src_lane);
+#pragma unroll
+        for (int c = 0; c < CP; c += 2) {
+          const float2 r = __fadd2_rn(make_float2(v[c], v[c + 1]), make_float2(sh[c], sh[c + 1]));
+          v[c] = r.x;
+          v[c + 1] = r.y;
+        }
+      }
+      xpar ^= kXpar;
+    }
+
+    // the pixel this lane holds
+    const int64_t prow = int64_t(TS) * t - H_ + row;
+    bool valid = lane_valid && prow < p.rows_valid && (px < p.W) && (pyy > 0);
+    const int n = pn, y = pyy - 1, x = px;
+    {
+      px += adv_x;
+      const int cx = px >= p.Wp;
+      px -= cx ? p.Wp : 0;
+      pyy += adv_y + cx;
+      const int cy = pyy >= H1;
+      pyy -= cy ? H1 : 0;
+      pn += adv_n + cy;
+    }
+
+    // bias (packed fp32x2 adds) and tanh
+#pragma unroll
+    for (int c = 0; c < CP; c += 2) {
+      const float2 r = __fadd2_rn(make_float2(v[c], v[c + 1]), make_float2(bias_r[c], bias_r[c + 1]));
+      v[c] = r.x;
+      v[c + 1] = r.y;
+    }
+    if (act == SRK_ACT_TANH) {
+#pragma unroll
+      for (int c = 0; c < CP; ++c) v[c] = act_apply(v[c], SRK_ACT_TANH);
+    }
+
+    if constexpr (EPI == EPI_FPA) {
+      static_assert(CP >= 8, "FPA epilogue stores 16-byte chunks");
+      uint32_t packed[CP / 2];
+      const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+      if (valid) {
+        if (p.addend_fpa || (p.mask_src && p.mask_kind != SRK_ACT_RELU)) {
+          // rare forms (EnhanceNet block residual, tanh' mask): fp32 path
+          if (act == SRK_ACT_RELU) {
+#pragma unroll
+            for (int c = 0; c < CP; ++c) v[c] = fmaxf(v[c], 0.f);
+          }
+          if (p.mask_src) {
+            const uint4* m = reinterpret_cast<const uint4*>(p.mask_src + size_t(prow) * NP + col0);
 #pragma unroll
             for (int j = 0; j < CP / 8; ++j) {
-              const int chunk = grp * (CP / 8) + j;  // 16-byte chunk index within the output row
-              uint4 q4 = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-              *reinterpret_cast<uint4*>(stage_ptr + srow * kOutRowBytes + ((chunk ^ sw) << 4)) = q4;
+              const uint4 mv = __ldg(m + j);
+              const uint32_t w4[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[q]));
+                v[j * 8 + q * 2] *= (1.f - f.x * f.x);
+                v[j * 8 + q * 2 + 1] *= (1.f - f.y * f.y);
+              }
             }
           }
-          fence_proxy_async_smem();
-          mbar_arrive(e.bar_sfull + 8u * sb);
-        } else {
-          // fp32 NHWC scatter: residual add, panel crop, depth_to_space
-          if (valid) {
-            int fn = n, fy = y, fx = x;
-            if (p.panels) {
-              const srk_panel e = p.panels[n];
-              valid = (y >= e.own_y0) && (y < e.own_y1) && (x >= e.own_x0) && (x < e.own_x1);
-              fn = e.frame;
-              fy = e.y0 + y;
-              fx = e.x0 + x;
-            }
-            if (valid) {
-              const int r = p.shuffle_r, C = p.cout / (r * r);
-              const int64_t OW = int64_t(p.FW) * r;
-              const int64_t base = ((int64_t(fn) * p.FH * r + int64_t(fy) * r) * OW + int64_t(fx) * r) * C;
+          if (p.addend_fpa) {
+            const uint4* a = reinterpret_cast<const uint4*>(p.addend_fpa + size_t(prow) * NP + col0);
 #pragma unroll
-              for (int c = 0; c < CP; ++c) {
-                const int off = tab_r[c];
-                if (off >= 0) {
-                  const int64_t idx = base + off;
-                  float o = act_apply(v[c] + bias_r[c], p.act);
-                  if (p.addend) o += __ldg(p.addend + idx);
-                  p.out[idx] = o;
-                }
+            for (int j = 0; j < CP / 8; ++j) {
+              const uint4 av = __ldg(a + j);
+              const uint32_t w4[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[q]));
+                v[j * 8 + q * 2] += f.x;
+                v[j * 8 + q * 2 + 1] += f.y;
+              }
+            }
+            if (p.relu_after_add) {
+#pragma unroll
+              for (int c = 0; c < CP; ++c) v[c] = fmaxf(v[c], 0.f);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < CP / 2; ++c) packed[c] = pack_bf16x2(v[2 * c], v[2 * c + 1]);
+        } else {
+          // common forms: ReLU and the ReLU' mask act on the packed bf16 pairs (both commute with the rounding)
+#pragma unroll
+          for (int c = 0; c < CP / 2; ++c) packed[c] = pack_bf16x2(v[2 * c], v[2 * c + 1]);
+          if (act == SRK_ACT_RELU) {
+#pragma unroll
+            for (int c = 0; c < CP / 2; ++c) {
+              const __nv_bfloat162 h = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&packed[c]), zero2);
+              packed[c] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+          }
+          if (p.mask_src) {
+            const uint4* m = reinterpret_cast<const uint4*>(p.mask_src + size_t(prow) * NP + col0);
+#pragma unroll
+            for (int j = 0; j < CP / 8; ++j) {
+              const uint4 mv = __ldg(m + j);
+              const uint32_t w4[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const __nv_bfloat162 gt = __hgt2(*reinterpret_cast<const __nv_bfloat162*>(&w4[q]), zero2);  // 1.0 / 0.0 per half
+                const __nv_bfloat162 h = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&packed[j * 4 + q]), gt);
+                packed[j * 4 + q] = *reinterpret_cast<const uint32_t*>(&h);
               }
             }
           }
         }
+      } else {
+#pragma unroll
+        for (int c = 0; c < CP / 2; ++c) packed[c] = 0u;  // pad rows/columns stay exactly zero
       }
+      // staging buffer free? (the store that last used this buffer has finished reading it)
+      const int sb = (e.stage_bufs == 2) ? (it & 1) : 0, sgen = (e.stage_bufs == 2) ? (it >> 1) : it;
+      mbar_wait(e.bar_sfree + 8u * sb, (sgen & 1) ^ 1);
+      if (lane_valid) {
+#pragma unroll
+        for (int j = 0; j < CP / 8; ++j)
+          sts128u(st_addr[j] + sb * e.stage_stride, packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(e.bar_sfull + 8u * sb);
+    } else {
+      // fp32 NHWC scatter: residual add, panel crop, depth_to_space
+      if (act == SRK_ACT_RELU) {
+#pragma unroll
+        for (int c = 0; c < CP; ++c) v[c] = fmaxf(v[c], 0.f);
+      }
+      if (valid) {
+        int fn = n, fy = y, fx = x;
+        if (p.panels) {
+          const srk_panel pe = p.panels[n];
+          valid = (y >= pe.own_y0) && (y < pe.own_y1) && (x >= pe.own_x0) && (x < pe.own_x1);
+          fn = pe.frame;
+          fy = pe.y0 + y;
+          fx = pe.x0 + x;
+        }
+        if (valid) {
+          const int r = p.shuffle_r, C = p.cout / (r * r);
+          const int64_t OW = int64_t(p.FW) * r;
+          const int64_t base = ((int64_t(fn) * p.FH * r + int64_t(fy) * r) * OW + int64_t(fx) * r) * C;
+#pragma unroll
+          for (int c = 0; c < CP; ++c) {
+            const int off = tab_r[c];
+            if (off >= 0) {
+              const int64_t idx = base + off;
+              float o = v[c];
+              if (p.addend) o += __ldg(p.addend + idx);
+              p.out[idx] = o;
+            }
+          }
+        }
+      }
+    }
   }
 }
 
 template <int CIN, int NP, int KS, int EPI>
 __global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS>::kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   using L = ConvTcCfg<CIN, NP, KS>;
+  constexpr int kRingSlots = L::kRingSlots;
   constexpr uint32_t kLayout = (CIN == 64) ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW64;
   constexpr uint32_t kSbo = 8 * L::kRowBytes;
   constexpr int H_ = L::kHalo, TS = L::kTileStride, CP = L::kColPass, ACC = L::kAccStages;
@@ -458,11 +530,12 @@ __global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS>::kThreads, 1) conv_tc_k
   ec.bar_tempty0 = bar_tempty(0);
   ec.bar_sfull = bar_sfull;
   ec.bar_sfree = bar_sfree;
-  ec.stage_ptr = stage_ptr;
-  ec.stage_stride = L::kStageBytes / 2;
+  ec.stage_addr = smem_u32(stage_ptr);
+  ec.stage_stride = 128 * NP * 2;
+  ec.stage_bufs = L::kStageBufs;
   ec.s_bias = s_bias;
   ec.s_tab = s_tab;
-  ec.s_xch = s_xch;
+  ec.xch_addr = smem_u32(s_xch);
 
   if (t_begin < t_end) {
     if (warp == 0) {
@@ -625,11 +698,12 @@ __global__ void __launch_bounds__(ConvGatherCfg<KS, CIN>::kThreads, 1) conv_gath
   ec.bar_tempty0 = bar_tempty(0);
   ec.bar_sfull = bar_sfull;
   ec.bar_sfree = bar_sfree;
-  ec.stage_ptr = smem + L::kOffStage;
+  ec.stage_addr = s_base + L::kOffStage;
   ec.stage_stride = 128 * 64 * 2;
+  ec.stage_bufs = 2;
   ec.s_bias = s_bias;
   ec.s_tab = reinterpret_cast<int*>(smem + L::kOffTab);
-  ec.s_xch = reinterpret_cast<float*>(smem + L::kOffXch);
+  ec.xch_addr = s_base + L::kOffXch;
 
   if (t_begin < t_end) {
     if (warp == 0) {
@@ -759,9 +833,9 @@ static int launch_conv_tc(srk_ctx* h, ConvTcParams& p, const void* x, const void
   }
   p.num_tiles = int((p.rows_valid + L::kTileStride - 1) / L::kTileStride);
   const int span_chunks = (2 * L::kHalo * p.Wp + 128 + kChunkRows - 1) / kChunkRows + 1;
-  SRK_REQUIRE(span_chunks <= kRingSlots - 2,
-              "conv_tc: image width %d too large for the %dx%d flat-stream kernel (a tile needs %d chunks, ring holds %d); "
-              "split the frame into column panels", p.W, KS, KS, span_chunks, kRingSlots);
+  SRK_REQUIRE(span_chunks + 2 <= L::kRingSlots,
+              "conv_tc: image width %d too large for the %dx%d flat-stream kernel (a tile needs %d chunks resident, ring holds %d); "
+              "split the frame into column panels", p.W, KS, KS, span_chunks, L::kRingSlots);
   if (int rc = make_tensor_map_2d(&p.map_in, x, uint64_t(p.rows_valid), CIN, kChunkRows)) return rc;
   if (int rc = make_tensor_map_2d(&p.map_w, w_packed, uint64_t(KS * KS * NP), CIN, NP)) return rc;
   if (EPI == EPI_FPA) {

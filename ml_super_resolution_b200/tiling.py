@@ -1,6 +1,6 @@
 """Tile planner for full-frame inference.
 
-A frame larger than the flat-stream conv kernel's widest panel (223 px), larger than L2, or
+A frame larger than the flat-stream conv kernel's widest panel (254 px), larger than L2, or
 spread over several GPUs is cut into equally sized tiles that all lie INSIDE the frame and
 overlap by at least 2*halo, where halo = the network's receptive-field radius (VDSR 20,
 ESPCN 4 LR px, ENet 13 LR px).  Each tile runs through the network with ordinary per-layer SAME
@@ -13,7 +13,7 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 
-MAX_PANEL_W = 223  # widest image the flat-stream conv kernel's 12-chunk shared-memory ring can serve (2*Wp + 191 < 640)
+MAX_PANEL_W = 254  # widest image the flat-stream kernels serve: a tile's 2*Wp + 128 resident rows must leave look-ahead room in the smem ring
 
 
 @dataclass(frozen=True)

@@ -90,7 +90,7 @@ class VdsrNet:
     # ------------------------------------------------------------------ inference
     def forward(self, sd: torch.Tensor, taps: dict | None = None, out: torch.Tensor | None = None, tile_rows: int | None = None,
                 rank: int = 0, world: int = 1) -> torch.Tensor:
-        """sd fp32 [N,H,W,C] on device -> sr.  Frames wider than 223 px (or taller than `tile_rows`) are
+        """sd fp32 [N,H,W,C] on device -> sr.  Frames wider than 254 px (or taller than `tile_rows`) are
         cut into halo-overlapped tiles; with world > 1 this rank computes only its shard of the tiles
         (tile-sharded multi-GPU inference, no collective; pixels it does not own are left untouched)."""
         n, H, W, C = sd.shape
@@ -181,7 +181,7 @@ class VdsrNet:
         buffer dict (`loss` = [mse, reg], `sr`).  `numel_total` = GLOBAL element count under data
         parallelism so that summing rank gradients reproduces the single-GPU MEAN reduction."""
         n, H, W, C = sd.shape
-        assert W <= MAX_PANEL_W, "training patches wider than 223 px are not supported by the flat-stream kernels"
+        assert W <= MAX_PANEL_W, "training patches wider than 254 px are not supported by the flat-stream kernels"
         a, L = self.arena, self.L
         b = self._get_train_bufs(n, H, W)
         acts, dyb = b["acts"], b["dy"]

@@ -35,8 +35,8 @@ def main():
     dev = "cuda"
     g = torch.Generator(device=dev).manual_seed(0)
     # ---- 64->64 3x3 layer on the VDSR training shape and on one inference panel group
-    for name, (n, h, w) in {"train_64x41x41": (64, 41, 41), "train_64x128x128": (64, 128, 128), "panel_21x2160x223": (21, 2160, 223),
-                            "panel_4x540x223": (4, 540, 223)}.items():
+    for name, (n, h, w) in {"train_64x41x41": (64, 41, 41), "train_64x128x128": (64, 128, 128), "panel_18x2160x252": (18, 2160, 252),
+                            "panel_4x540x252": (4, 540, 252)}.items():
         x = ops.fpa_empty(n, h, w, 64)
         x.data.normal_(generator=g)
         y = ops.fpa_empty(n, h, w, 64)

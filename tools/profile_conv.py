@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ml_super_resolution_b200 import ops  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else "fwd"
-n, h, w = (4, 540, 223) if len(sys.argv) <= 2 else tuple(int(v) for v in sys.argv[2].split("x"))
+n, h, w = (4, 540, 252) if len(sys.argv) <= 2 else tuple(int(v) for v in sys.argv[2].split("x"))
 g = torch.Generator(device="cuda").manual_seed(0)
 x = ops.fpa_empty(n, h, w, 64)
 x.data.normal_(generator=g)
