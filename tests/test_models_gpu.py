@@ -142,3 +142,38 @@ def test_vdsr_graphed_step_equals_eager(srk_ops):
         # sign(g), so a gradient element near zero may move the other way: bounded by 2*lr per step, and rare
         d = np.abs(we[k] - wg[k])
         assert d.max() <= 3 * 2e-3 and d.mean() <= 2e-5, (k, d.max(), d.mean())
+
+
+@pytest.mark.parametrize("channels,S,batch", [(1, 33, 8), (3, 45, 2)])
+def test_srcnn_forward_degrade_and_loss(srk_ops, channels, S, batch):
+    from ml_super_resolution_b200.srcnn.srcnn import SrcnnNet
+    params = _trained_like(OM.srcnn_init(seed=6, channels=channels), scale=60.0)  # sigma 0.001 init -> visible activations
+    net = SrcnnNet(params, channels)
+    hi = OM.synthetic_images(31, batch, S, S, channels)
+    hit = torch.from_numpy(hi).cuda()
+    lo = net.degrade(hit)
+    ref_lo = O.resize_bicubic_tf1(O.resize_bicubic_tf1(hi, S // 3, S // 3), S, S)
+    assert np.array_equal(lo.cpu().numpy(), ref_lo)  # TF1 bicubic: bit exact
+    sr = net.forward(lo)
+    ref_sr = OM.srcnn_forward(params, ref_lo)
+    assert sr.shape == ref_sr.shape == (batch, S - 12, S - 12, channels)
+    assert np.abs(sr.cpu().numpy() - ref_sr).max() <= TOL_BF16
+    loss, dsr = net.loss(sr, hit)
+    bb = S - 12
+    ref_loss, ref_grad = O.l2norm_rows_mean(sr.cpu().numpy(), hi[:, 6:6 + bb, 6:6 + bb, :], bb * bb)
+    assert abs(float(loss) - ref_loss) <= 1e-4 * ref_loss
+    np.testing.assert_allclose(dsr.cpu().numpy(), ref_grad, rtol=1e-4, atol=1e-8)
+
+
+def test_enet_generator_forward(srk_ops):
+    from ml_super_resolution_b200.enet.model_enet import EnetGenerator
+    params = _trained_like(OM.enet_g_init(seed=8), scale=2.5)
+    net = EnetGenerator(params)
+    sd = OM.synthetic_images(41, 2, 32, 32, 3)
+    bq = OM.synthetic_images(42, 2, 128, 128, 3)
+    got = net.forward(torch.from_numpy(sd).cuda(), torch.from_numpy(bq).cuda()).cpu().numpy()
+    ref = OM.enet_generator_forward(params, sd, bq)
+    res_scale = np.abs(ref - bq).max()
+    assert res_scale > 0.05, "test weights too small to exercise the generator"
+    assert np.abs(got - ref).max() <= TOL_BF16 * max(1.0, res_scale)
+    assert abs(_psnr(got, bq + 0.3) - _psnr(ref, bq + 0.3)) <= 0.02
