@@ -559,6 +559,11 @@ __global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS>::kThreads, 1) conv_tc_k
         constexpr uint64_t hi = umma_desc_hi(0, kSbo, kLayout);
         mbar_wait(bar_wfull, 0);
         int loaded = c0 - 1, released = c0;  // chunks <= loaded have landed; chunks < released were handed back
+        // running window rows (relative to the ring origin, already wrapped): advance TS rows per tile, wrap by subtraction
+        constexpr int kRingRows = kRingSlots * kChunkRows;
+        int win[KS];
+#pragma unroll
+        for (int r = 0; r < KS; ++r) win[r] = (TS * t_begin - H_ - c0 * kChunkRows + (r - H_) * p.Wp) % kRingRows;
         for (int t = t_begin; t < t_end; ++t) {
           const int it = t - t_begin, acc = it % ACC, accgen = it / ACC;
           const int need = hi_chunk(t);
@@ -570,15 +575,15 @@ __global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS>::kThreads, 1) conv_tc_k
           mbar_wait(bar_tempty(acc), (accgen & 1) ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem + acc * L::kN;
-          const int row0 = TS * t - H_ - c0 * kChunkRows;  // window start of dy = 0, relative to the ring origin
 #pragma unroll
           for (int r = 0; r < KS; ++r) {
-            const int rr = (row0 + (r - H_) * p.Wp) % (kRingSlots * kChunkRows);
-            const uint32_t a_addr = s_ring + rr * L::kRowBytes;
+            const uint32_t a_addr = s_ring + win[r] * L::kRowBytes;
             const uint32_t b_addr = s_w + r * KS * L::kWTapBytes;
 #pragma unroll
             for (int k = 0; k < CIN / 16; ++k)
               umma_bf16(d_tmem, umma_desc(hi, a_addr + k * 32), umma_desc(hi, b_addr + k * 32), idesc, (r | k) != 0);
+            win[r] += TS;
+            win[r] -= (win[r] >= kRingRows) ? kRingRows : 0;
           }
           umma_commit(bar_tfull(acc));
           // hand back the chunks no later tile needs

@@ -124,6 +124,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         const int dist[5] = {1, 1, 1, Wp, 0 /* ones block */};
         int loaded = c0 - 1;
         const int ring_rows = R * 128;
+        // The single issuing thread is the critical path (every instruction pays its full dependent latency), so the
+        // loop carries running window rows and pre-built descriptor halves instead of recomputing them with
+        // divisions: a_row[pr] advances 16 rows per K-step and wraps by subtraction.
+        int a_row[5];
+        uint64_t a_hi[5];
+#pragma unroll
+        for (int pr = 0; pr < 5; ++pr) {
+          a_row[pr] = (nb * 128 + off_a[pr]) % ring_rows;
+          a_hi[pr] = umma_desc_hi(uint32_t(dist[pr]) * 128u, 1024, UMMA_LAYOUT_SW128);
+        }
+        const uint64_t ones_hi = umma_desc_hi(0, 1024, UMMA_LAYOUT_SW128);
         for (int k = k_begin; k < k_end; ++k) {
           const int j = k - k_begin;
           while (loaded < k + nb) {
@@ -133,18 +144,20 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
           }
           mbar_wait(bar_yfull(j % kYRing), (j / kYRing) & 1);
           tc_fence_after();
-          const int row0 = (j + nb) * 128;
           const uint32_t y_addr = s_y + (j % kYRing) * kChunk;
-#pragma unroll 1
+#pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
             const uint64_t bdesc = umma_desc(b_hi, y_addr + kk * 2048);
+            const uint32_t acc_flag = (j | kk) != 0;
 #pragma unroll
             for (int pr = 0; pr < 5; ++pr) {
-              const int a0 = (row0 + off_a[pr] + 16 * kk) % ring_rows;
-              const uint32_t a_addr = s_x + uint32_t(a0) * 128u;
-              const uint32_t lbo = (pr == 4) ? (s_ones - a_addr) : uint32_t(dist[pr]) * 128u;
-              umma_bf16(tmem + pr * 64, umma_desc(umma_desc_hi(lbo, 1024, UMMA_LAYOUT_SW128), a_addr), bdesc, idesc,
-                        (j | kk) != 0);
+              const uint32_t a_addr = s_x + uint32_t(a_row[pr]) * 128u;
+              uint64_t adesc;
+              if (pr == 4) adesc = ones_hi | (uint64_t(((s_ones - a_addr) >> 4) & 0x3FFF) << 16) | uint64_t((a_addr >> 4) & 0x3FFF);
+              else adesc = umma_desc(a_hi[pr], a_addr);
+              umma_bf16(tmem + pr * 64, adesc, bdesc, idesc, acc_flag);
+              a_row[pr] += 16;
+              a_row[pr] -= (a_row[pr] >= ring_rows) ? ring_rows : 0;
             }
           }
           umma_commit(bar_xempty(j % R));  // X chunk k-nb (= c0+j) is done
