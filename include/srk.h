@@ -141,10 +141,18 @@ int srk_conv_wgrad_tc(srk_handle_t h, const void* x_fpa, const void* dy_fpa, int
                       srk_stream_t stream);
 /* Deferred form: call srk_conv_wgrad_tc with dw_hwio = NULL for each of n_layers layers, each with its own
  * workspace slice `workspace_base + l * layer_stride_bytes`, then fold all of them with ONE launch.
- * dw_ptrs_device / db_ptrs_device: device arrays of n_layers destination pointers. */
+ * dsts_device: device array of n_layers destinations.  ci_n / co_n < 64 keep only the leading input / output
+ * channels and write the dense [9][ci_n][co_n] kernel gradient: this is how the first layer (x = the input frame
+ * zero-padded to 64 channels by srk_nhwc_to_fpa_pad, ci_n = C) and the last layer (dy zero-padded, co_n = C)
+ * share the tensor-core kernel. */
+typedef struct {
+  float* dw;
+  float* db;
+  int32_t ci_n, co_n;
+} srk_wgrad_dst;
 int srk_wgrad_reduce_many(srk_handle_t h, const void* workspace_base, size_t layer_stride_bytes, int n_layers,
-                          int n_img, int H, int W, float* const* dw_ptrs_device, float* const* db_ptrs_device,
-                          int accumulate, srk_stream_t stream);
+                          int n_img, int H, int W, const srk_wgrad_dst* dsts_device, int accumulate,
+                          srk_stream_t stream);
 
 /* Weight gradient of the first layer (x fp32 NHWC cin<=4, dy FPA 64ch) -> dw [k,k,cin,64], db[64]. */
 int srk_conv_first_wgrad(srk_handle_t h, const float* x, int n_img, int H, int W, int cin, int k,
@@ -205,6 +213,10 @@ int srk_fpa_to_nhwc(srk_handle_t h, const void* x_fpa, int C, int n_img, int H, 
                     srk_stream_t stream);
 int srk_nhwc_to_fpa(srk_handle_t h, const float* x, int C, int n_img, int H, int W, void* y_fpa,
                     srk_stream_t stream);
+/* Same with the channel count padded with zeros to Cp (e.g. 3 -> 64), so a 3-channel frame or gradient can feed
+ * the 64-channel tensor-core kernels. */
+int srk_nhwc_to_fpa_pad(srk_handle_t h, const float* x, int C, int Cp, int n_img, int H, int W, void* y_fpa,
+                        srk_stream_t stream);
 
 #ifdef __cplusplus
 }

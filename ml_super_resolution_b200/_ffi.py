@@ -20,6 +20,10 @@ class SrkPackJob(C.Structure):
                 ("cin", C.c_int32), ("cout", C.c_int32), ("mode", C.c_int32), ("np", C.c_int32), ("cinp", C.c_int32)]
 
 
+class SrkWgradDst(C.Structure):
+    _fields_ = [("dw", C.c_void_p), ("db", C.c_void_p), ("ci_n", C.c_int32), ("co_n", C.c_int32)]
+
+
 class SrkPanel(C.Structure):
     _fields_ = [("frame", C.c_int32), ("y0", C.c_int32), ("x0", C.c_int32), ("own_y0", C.c_int32),
                 ("own_y1", C.c_int32), ("own_x0", C.c_int32), ("own_x1", C.c_int32), ("reserved", C.c_int32)]
@@ -45,7 +49,8 @@ SIGNATURES = {
     "srk_conv_tc_last": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P]),
     "srk_conv_wgrad_tc_workspace_bytes": (_SZ, [_P, _I, _I, _I]),
     "srk_conv_wgrad_tc": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _SZ, _P]),
-    "srk_wgrad_reduce_many": (_I, [_P, _P, _SZ, _I, _I, _I, _I, _P, _P, _I, _P]),
+    "srk_wgrad_reduce_many": (_I, [_P, _P, _SZ, _I, _I, _I, _I, _P, _I, _P]),
+    "srk_nhwc_to_fpa_pad": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "srk_conv_first_wgrad": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "srk_conv_last_wgrad": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "srk_pixel_shuffle": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),

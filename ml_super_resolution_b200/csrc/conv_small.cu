@@ -244,19 +244,19 @@ __global__ void fpa_to_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int C, i
     y[i] = __bfloat162float(x[(n * S + int64_t(yy + 1) * Wp + xx) * C + c]);
   }
 }
-__global__ void nhwc_to_fpa_kernel(const float* __restrict__ x, int C, int n_img, int H, int W, int64_t rows_valid,
+__global__ void nhwc_to_fpa_kernel(const float* __restrict__ x, int C, int Cp, int n_img, int H, int W, int64_t rows_valid,
                                    __nv_bfloat16* __restrict__ y) {
-  const int64_t total = rows_valid * C;
+  const int64_t total = rows_valid * Cp;
   const int Wp = W + 1;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-    const int c = int(i % C);
-    const int64_t prow = i / C;
+    const int c = int(i % Cp);
+    const int64_t prow = i / Cp;
     const int64_t q = prow / Wp;
     const int xx = int(prow - q * Wp);
     const int64_t n = q / (H + 1);
     const int yy = int(q - n * (H + 1));
     float v = 0.f;
-    if (xx < W && yy > 0) v = x[((n * H + (yy - 1)) * int64_t(W) + xx) * C + c];
+    if (xx < W && yy > 0 && c < C) v = x[((n * H + (yy - 1)) * int64_t(W) + xx) * C + c];
     y[i] = __float2bfloat16_rn(v);
   }
 }
@@ -283,13 +283,14 @@ __global__ void __launch_bounds__(1024) conv_first_wgrad_kernel(const float* __r
   float acc[kAcc];
 #pragma unroll
   for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
-  for (int64_t pix = p0 + pl; pix < p1; pix += 16) {
-    const int xx = int(pix % W);
-    const int yy = int((pix / W) % H);
-    const int64_t n = pix / (int64_t(W) * H);
-    const float g = __bfloat162float(dy[(n * S + int64_t(yy + 1) * Wp + xx) * 64 + co]);
+  const uint32_t HW = uint32_t(H) * uint32_t(W);
+  for (uint32_t pix = uint32_t(p0) + pl; pix < uint32_t(p1); pix += 16) {  // npix < 2^31: 32-bit divisions only
+    const uint32_t n = pix / HW, rem = pix - n * HW;
+    const int yy = int(rem / uint32_t(W));
+    const int xx = int(rem - uint32_t(yy) * uint32_t(W));
+    const float g = __bfloat162float(dy[(int64_t(n) * S + int64_t(yy + 1) * Wp + xx) * 64 + co]);
     acc[kAcc - 1] += g;
-    const float* img = x + n * int64_t(H) * W * CIN;
+    const float* img = x + int64_t(n) * H * W * CIN;
 #pragma unroll
     for (int u = 0; u < KS; ++u) {
       const int sy = yy + u - po;
@@ -337,17 +338,18 @@ __global__ void __launch_bounds__(1024) conv_last_wgrad_kernel(const __nv_bfloat
   for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
 #pragma unroll
   for (int i = 0; i < COUT; ++i) bacc[i] = 0.f;
-  for (int64_t pix = p0 + pl; pix < p1; pix += 16) {
-    const int xx = int(pix % W);
-    const int yy = int((pix / W) % H);
-    const int64_t n = pix / (int64_t(W) * H);
+  const uint32_t HW = uint32_t(H) * uint32_t(W);
+  for (uint32_t pix = uint32_t(p0) + pl; pix < uint32_t(p1); pix += 16) {  // npix < 2^31: 32-bit divisions only
+    const uint32_t n = pix / HW, rem = pix - n * HW;
+    const int yy = int(rem / uint32_t(W));
+    const int xx = int(rem - uint32_t(yy) * uint32_t(W));
     float g[COUT];
 #pragma unroll
     for (int co = 0; co < COUT; ++co) {
-      g[co] = __ldg(dy + pix * COUT + co);
+      g[co] = __ldg(dy + size_t(pix) * COUT + co);
       bacc[co] += g[co];
     }
-    const int64_t row = n * S + int64_t(yy + 1) * Wp + xx;
+    const int64_t row = int64_t(n) * S + int64_t(yy + 1) * Wp + xx;
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
       const int64_t r = row + int64_t(tap / 3 - 1) * Wp + (tap % 3 - 1);
@@ -447,20 +449,25 @@ extern "C" int srk_fpa_to_nhwc(srk_handle_t h, const void* x_fpa, int C, int n_i
   return 0;
 }
 
-extern "C" int srk_nhwc_to_fpa(srk_handle_t h, const float* x, int C, int n_img, int H, int W, void* y_fpa, srk_stream_t stream) {
-  SRK_REQUIRE(h && x && y_fpa, "srk_nhwc_to_fpa: null argument");
+extern "C" int srk_nhwc_to_fpa_pad(srk_handle_t h, const float* x, int C, int Cp, int n_img, int H, int W, void* y_fpa, srk_stream_t stream) {
+  SRK_REQUIRE(h && x && y_fpa && Cp >= C && C > 0, "srk_nhwc_to_fpa_pad: bad argument");
   const FpaGeom g = fpa_geom(n_img, H, W);
-  const int64_t total = g.rows_valid * C;
+  const int64_t total = g.rows_valid * Cp;
   const int grid = int(std::min<int64_t>((total + 255) / 256, int64_t(h->num_sms) * 16));
-  nhwc_to_fpa_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, C, n_img, H, W, g.rows_valid, static_cast<__nv_bfloat16*>(y_fpa));
+  nhwc_to_fpa_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, C, Cp, n_img, H, W, g.rows_valid, static_cast<__nv_bfloat16*>(y_fpa));
   SRK_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int srk_nhwc_to_fpa(srk_handle_t h, const float* x, int C, int n_img, int H, int W, void* y_fpa, srk_stream_t stream) {
+  return srk_nhwc_to_fpa_pad(h, x, C, C, n_img, H, W, y_fpa, stream);
 }
 
 extern "C" int srk_conv_first_wgrad(srk_handle_t h, const float* x, int n_img, int H, int W, int cin, int k, const void* dy_fpa,
                                     float* dw_hwio, float* dbias, srk_stream_t stream) {
   SRK_REQUIRE(h && x && dy_fpa && dw_hwio && dbias, "srk_conv_first_wgrad: null argument");
   const int64_t npix = int64_t(n_img) * H * W;
+  SRK_REQUIRE(npix < (int64_t(1) << 31), "srk_conv_first_wgrad: too many pixels");
   const int grid = int(std::min<int64_t>((npix + 63) / 64, int64_t(h->num_sms)));
   const __nv_bfloat16* dy = static_cast<const __nv_bfloat16*>(dy_fpa);
   cudaStream_t s = as_stream(stream);
@@ -480,6 +487,7 @@ extern "C" int srk_conv_last_wgrad(srk_handle_t h, const void* x_fpa, const floa
                                    float* dw_hwio, float* dbias, srk_stream_t stream) {
   SRK_REQUIRE(h && x_fpa && dy && dw_hwio && dbias, "srk_conv_last_wgrad: null argument");
   const int64_t npix = int64_t(n_img) * H * W;
+  SRK_REQUIRE(npix < (int64_t(1) << 31), "srk_conv_last_wgrad: too many pixels");
   const int grid = int(std::min<int64_t>((npix + 63) / 64, int64_t(h->num_sms)));
   const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(x_fpa);
   cudaStream_t s = as_stream(stream);

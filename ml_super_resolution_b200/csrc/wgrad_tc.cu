@@ -201,16 +201,26 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
 }
 
 // Deterministic second pass: dw/dbias = (accumulate ? dw : 0) + sum over CTA partials (fixed order).
-// blockIdx.y selects the layer: one launch can fold the partial blocks of every layer of a model.
+// blockIdx.y selects the layer: one launch folds the partial blocks of every layer of a model.  A layer may keep
+// only the leading ci_n input / co_n output channels of the 64x64 block (first layer: ci_n = C, last layer:
+// co_n = C, computed over zero-padded 64-channel operands); its destination is then the dense [9][ci_n][co_n].
+struct WgradDst {
+  float* dw;
+  float* db;
+  int ci_n, co_n;
+};
 __global__ void __launch_bounds__(128) wgrad_reduce_kernel(const float4* __restrict__ partial_base, size_t layer_stride_f4, int n_part,
-                                                           float* const* __restrict__ dw_ptrs, float* const* __restrict__ db_ptrs,
-                                                           float4* dw_single, float4* db_single, int accumulate) {
+                                                           const WgradDst* __restrict__ dsts, WgradDst single, int accumulate) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // float4 index
   constexpr int kN4 = kPartialFloats / 4;
   if (i >= kN4) return;
+  const WgradDst d = dsts ? dsts[blockIdx.y] : single;
+  // which output elements does this float4 cover?
+  const bool is_bias = i >= 9 * 64 * 64 / 4;
+  const int e0 = (is_bias ? i - 9 * 64 * 64 / 4 : i) * 4;
+  const int co0 = e0 & 63, ci = (e0 >> 6) & 63, tap = e0 >> 12;
+  if (co0 >= d.co_n || (!is_bias && ci >= d.ci_n)) return;
   const float4* partial = partial_base + size_t(blockIdx.y) * layer_stride_f4;
-  float4* dw = dw_ptrs ? reinterpret_cast<float4*>(dw_ptrs[blockIdx.y]) : dw_single;
-  float4* dbias = db_ptrs ? reinterpret_cast<float4*>(db_ptrs[blockIdx.y]) : db_single;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   int pidx = 0;
   for (; pidx + 8 <= n_part; pidx += 8) {
@@ -229,12 +239,11 @@ __global__ void __launch_bounds__(128) wgrad_reduce_kernel(const float4* __restr
     const float4 a = __ldg(partial + size_t(pidx) * kN4 + i);
     acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
   }
-  float4* dst = (i < 9 * 64 * 64 / 4) ? dw + i : dbias + (i - 9 * 64 * 64 / 4);
-  if (accumulate) {
-    const float4 o = *dst;
-    acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
-  }
-  *dst = acc;
+  float* dst = is_bias ? d.db + co0 : d.dw + (size_t(tap) * d.ci_n + ci) * d.co_n + co0;
+  const float r[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (co0 + q < d.co_n) dst[q] = accumulate ? dst[q] + r[q] : r[q];
 }
 
 static int wgrad_grid(srk_ctx* h, int num_chunks) {
@@ -281,24 +290,24 @@ extern "C" int srk_conv_wgrad_tc(srk_handle_t h, const void* x_fpa, const void* 
   wgrad_tc_kernel<<<grid, kWgThreads, WgSmem::kTotal, as_stream(stream)>>>(p);
   SRK_LAUNCH_CHECK();
   if (dw_hwio) {
-    wgrad_reduce_kernel<<<dim3((kPartialFloats / 4 + 127) / 128, 1), 128, 0, as_stream(stream)>>>(
-        static_cast<const float4*>(workspace), 0, grid, nullptr, nullptr, reinterpret_cast<float4*>(dw_hwio),
-        reinterpret_cast<float4*>(dbias), accumulate);
+    WgradDst single{dw_hwio, dbias, 64, 64};
+    wgrad_reduce_kernel<<<dim3((kPartialFloats / 4 + 127) / 128, 1), 128, 0, as_stream(stream)>>>(static_cast<const float4*>(workspace), 0, grid,
+                                                                                            nullptr, single, accumulate);
     SRK_LAUNCH_CHECK();
   }
   return 0;
 }
 
 extern "C" int srk_wgrad_reduce_many(srk_handle_t h, const void* workspace_base, size_t layer_stride_bytes, int n_layers, int n_img, int H,
-                                     int W, float* const* dw_ptrs_device, float* const* db_ptrs_device, int accumulate,
-                                     srk_stream_t stream) {
-  SRK_REQUIRE(h && workspace_base && dw_ptrs_device && db_ptrs_device && n_layers > 0, "srk_wgrad_reduce_many: bad argument");
+                                     int W, const srk_wgrad_dst* dsts_device, int accumulate, srk_stream_t stream) {
+  SRK_REQUIRE(h && workspace_base && dsts_device && n_layers > 0, "srk_wgrad_reduce_many: bad argument");
   SRK_REQUIRE(layer_stride_bytes % 16 == 0, "srk_wgrad_reduce_many: layer stride must be a multiple of 16 bytes");
+  static_assert(sizeof(srk_wgrad_dst) == sizeof(WgradDst), "ABI struct mismatch");
   const FpaGeom g = fpa_geom(n_img, H, W);
   const int n_part = wgrad_grid(h, int((g.rows_valid + 127) / 128));
   SRK_REQUIRE(layer_stride_bytes >= size_t(n_part) * kPartialFloats * sizeof(float), "srk_wgrad_reduce_many: layer stride smaller than one layer's partials");
   wgrad_reduce_kernel<<<dim3((kPartialFloats / 4 + 127) / 128, n_layers), 128, 0, as_stream(stream)>>>(
-      static_cast<const float4*>(workspace_base), layer_stride_bytes / 16, n_part, dw_ptrs_device, db_ptrs_device, nullptr, nullptr, accumulate);
+      static_cast<const float4*>(workspace_base), layer_stride_bytes / 16, n_part, reinterpret_cast<const WgradDst*>(dsts_device), WgradDst{}, accumulate);
   SRK_LAUNCH_CHECK();
   return 0;
 }

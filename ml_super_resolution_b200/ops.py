@@ -246,11 +246,28 @@ def conv_wgrad_tc(x: Fpa, dy: Fpa, dw: torch.Tensor | None, dbias: torch.Tensor 
         _ffi.launch_count += 1  # the reduce kernel
 
 
+def make_wgrad_dsts(entries, device="cuda") -> torch.Tensor:
+    """entries: iterable of (dw tensor, db tensor, ci_n, co_n) -> device array of srk_wgrad_dst."""
+    arr = (_ffi.SrkWgradDst * len(entries))()
+    for i, (dw, db, ci_n, co_n) in enumerate(entries):
+        arr[i] = _ffi.SrkWgradDst(dw.data_ptr(), db.data_ptr(), ci_n, co_n)
+    return torch.from_numpy(np.frombuffer(bytes(arr), dtype=np.uint8).copy()).to(device)
+
+
 def wgrad_reduce_many(workspace: torch.Tensor, layer_stride_bytes: int, n_layers: int, n_img: int, H: int, W: int,
-                      dw_ptrs: torch.Tensor, db_ptrs: torch.Tensor, accumulate=False) -> None:
+                      dsts: torch.Tensor, accumulate=False) -> None:
     """Fold the deferred per-CTA partial blocks of n_layers layers into their dw/dbias with one launch."""
-    check(_ffi.lib().srk_wgrad_reduce_many(handle(), _ptr(workspace), layer_stride_bytes, n_layers, n_img, H, W, _ptr(dw_ptrs),
-                                           _ptr(db_ptrs), int(accumulate), _stream()), "srk_wgrad_reduce_many")
+    check(_ffi.lib().srk_wgrad_reduce_many(handle(), _ptr(workspace), layer_stride_bytes, n_layers, n_img, H, W, _ptr(dsts),
+                                           int(accumulate), _stream()), "srk_wgrad_reduce_many")
+
+
+def nhwc_to_fpa_pad(x: torch.Tensor, Cp: int, out: Fpa | None = None) -> Fpa:
+    """fp32 NHWC [n,h,w,c] -> FPA with the channels zero-padded to Cp (feeds 3-channel tensors to the 64-channel kernels)."""
+    n, h, w, c = x.shape
+    if out is None:
+        out = fpa_empty(n, h, w, Cp, x.device)
+    check(_ffi.lib().srk_nhwc_to_fpa_pad(handle(), _ptr(_f32(x)), c, Cp, n, h, w, _ptr(out.data), _stream()), "srk_nhwc_to_fpa_pad")
+    return out
 
 
 def wgrad_workspace_bytes(n_img: int, H: int, W: int) -> int:

@@ -167,13 +167,18 @@ class VdsrNet:
                 "lr_t": torch.zeros(1, dtype=torch.float32, device=self.device),
             }
             b = self._train_bufs
-            # one workspace slice per 64->64 layer so a single launch can fold all of their partial sums
-            b["wg_ws"] = torch.empty(b["wg_stride"] * (self.L - 2), dtype=torch.uint8, device=self.device)
+            # every layer's weight gradient runs on the tensor-core wgrad kernel (first / last layer over operands
+            # zero-padded to 64 channels); one workspace slice per layer so a single launch folds all partial sums
+            b["wg_ws"] = torch.empty(b["wg_stride"] * self.L, dtype=torch.uint8, device=self.device)
+            b["sd_fpa"] = ops.fpa_empty(n, H, W, 64, self.device)
+            b["dsr_fpa"] = ops.fpa_empty(n, H, W, 64, self.device)
             a = self.arena
-            dw = [a.view(self._kname(i), "g").data_ptr() for i in range(1, self.L - 1)]
-            db = [a.view(self._bname(i), "g").data_ptr() for i in range(1, self.L - 1)]
-            b["wg_dw_ptrs"] = torch.tensor(dw, dtype=torch.int64, device=self.device)
-            b["wg_db_ptrs"] = torch.tensor(db, dtype=torch.int64, device=self.device)
+            ents = []
+            for i in range(self.L):
+                ci_n = self.C if i == 0 else 64
+                co_n = self.C if i == self.L - 1 else 64
+                ents.append((a.view(self._kname(i), "g"), a.view(self._bname(i), "g"), ci_n, co_n))
+            b["wg_dsts"] = ops.make_wgrad_dsts(ents, self.device)
         return self._train_bufs
 
     def forward_backward(self, sd: torch.Tensor, hd: torch.Tensor, numel_total: float | None = None):
@@ -192,19 +197,20 @@ class VdsrNet:
         ops.conv_tc_last(acts[L - 2], self.wf(L - 1), self.bias_last, 3, C, None, addend=sd, out=b["sr"])
         # ---- loss + d(loss)/d(sr)
         b["loss"].zero_()
-        a.g.zero_()
         ops.mse_fwd_bwd(b["sr"], hd, b["loss"][0:1], b["dsr"], numel_total)
         ops.sumsq_masked(a.w, a.decay_mask, 0.5 * WEIGHT_DECAY, b["loss"][1:2])
-        # ---- backward
-        ops.conv_last_wgrad(acts[L - 2], b["dsr"], a.view(self._kname(L - 1), "g"), a.view(self._bname(L - 1), "g"))
-        d = ops.conv_first_tc(b["dsr"], self.wd(L - 1), None, 3, "SAME", None, out=dyb[0], mask_src=acts[L - 2], mask_kind="relu")
+        # ---- backward: dgrad chain + one tensor-core wgrad per layer (partials), folded by a single reduce launch
         stride = b["wg_stride"]
+        ws = lambda i: b["wg_ws"][i * stride:(i + 1) * stride]
+        ops.nhwc_to_fpa_pad(b["dsr"], 64, out=b["dsr_fpa"])
+        ops.conv_wgrad_tc(acts[L - 2], b["dsr_fpa"], None, None, workspace=ws(L - 1))
+        d = ops.conv_first_tc(b["dsr"], self.wd(L - 1), None, 3, "SAME", None, out=dyb[0], mask_src=acts[L - 2], mask_kind="relu")
         for i in range(L - 2, 0, -1):
-            ws = b["wg_ws"][(i - 1) * stride:i * stride]
-            ops.conv_wgrad_tc(acts[i - 1], d, None, None, workspace=ws)  # partial sums only; folded below in one launch
+            ops.conv_wgrad_tc(acts[i - 1], d, None, None, workspace=ws(i))
             d = ops.conv_tc(d, self.wd(i), None, 3, None, out=dyb[(L - 1 - i) % 2], mask_src=acts[i - 1], mask_kind="relu")
-        ops.wgrad_reduce_many(b["wg_ws"], stride, L - 2, n, H, W, b["wg_dw_ptrs"], b["wg_db_ptrs"])
-        ops.conv_first_wgrad(sd, d, 3, a.view(self._kname(0), "g"), a.view(self._bname(0), "g"))
+        ops.nhwc_to_fpa_pad(sd, 64, out=b["sd_fpa"])
+        ops.conv_wgrad_tc(b["sd_fpa"], d, None, None, workspace=ws(0))
+        ops.wgrad_reduce_many(b["wg_ws"], stride, L, n, H, W, b["wg_dsts"])
         return b
 
     def apply_gradients(self, lr: float, use_adam=True, lr_t_dev: torch.Tensor | None = None):
