@@ -59,6 +59,8 @@ __global__ void pack_first_kernel(const float* __restrict__ w, int k, int cin, i
 __global__ void pack_weights_batched_kernel(const float* __restrict__ arena, const srk_pack_job* __restrict__ jobs, int n_jobs,
                                             int64_t total, uint8_t* __restrict__ out_base) {
   extern __shared__ srk_pack_job s_jobs[];
+  pdl_wait();
+  pdl_launch_dependents();
   for (int i = threadIdx.x; i < n_jobs; i += blockDim.x) s_jobs[i] = jobs[i];
   __syncthreads();
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
@@ -246,6 +248,8 @@ __global__ void fpa_to_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int C, i
 }
 __global__ void nhwc_to_fpa_kernel(const float* __restrict__ x, int C, int Cp, int n_img, int H, int W, int64_t rows_valid,
                                    __nv_bfloat16* __restrict__ y) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t total = rows_valid * Cp;
   const int Wp = W + 1;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
@@ -454,8 +458,8 @@ extern "C" int srk_nhwc_to_fpa_pad(srk_handle_t h, const float* x, int C, int Cp
   const FpaGeom g = fpa_geom(n_img, H, W);
   const int64_t total = g.rows_valid * Cp;
   const int grid = int(std::min<int64_t>((total + 255) / 256, int64_t(h->num_sms) * 16));
-  nhwc_to_fpa_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, C, Cp, n_img, H, W, g.rows_valid, static_cast<__nv_bfloat16*>(y_fpa));
-  SRK_LAUNCH_CHECK();
+  SRK_CHECK_CUDA(launch_pdl(nhwc_to_fpa_kernel, dim3(grid), dim3(256), 0, as_stream(stream), x, C, Cp, n_img, H, W, g.rows_valid,
+                            static_cast<__nv_bfloat16*>(y_fpa)));
   return 0;
 }
 
@@ -507,9 +511,8 @@ extern "C" int srk_pack_conv_weights_batched(srk_handle_t h, const float* arena,
                                              int64_t total_elems, void* out_base, srk_stream_t stream) {
   SRK_REQUIRE(h && arena && jobs_device && out_base && n_jobs > 0 && n_jobs <= 256, "srk_pack_conv_weights_batched: bad argument");
   const int grid = int(std::min<int64_t>((total_elems + 255) / 256, int64_t(h->num_sms) * 8));
-  pack_weights_batched_kernel<<<grid, 256, n_jobs * sizeof(srk_pack_job), as_stream(stream)>>>(
-      arena, jobs_device, n_jobs, total_elems, static_cast<uint8_t*>(out_base));
-  SRK_LAUNCH_CHECK();
+  SRK_CHECK_CUDA(launch_pdl(pack_weights_batched_kernel, dim3(grid), dim3(256), n_jobs * sizeof(srk_pack_job), as_stream(stream), arena,
+                            jobs_device, n_jobs, total_elems, static_cast<uint8_t*>(out_base)));
   return 0;
 }
 

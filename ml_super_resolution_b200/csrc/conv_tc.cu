@@ -503,6 +503,14 @@ __global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS>::kThreads, 1) conv_tc_k
     }
     fence_mbar_init();
   }
+  if (warp == 1) tmem_alloc<L::kTmemCols>(smem_u32(tmem_slot));
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.map_in);
+    tma_prefetch_desc(&p.map_w);
+    if (EPI == EPI_FPA) tma_prefetch_desc(&p.map_out);
+  }
+  pdl_wait();               // predecessor kernels are complete and their writes visible from here on
+  pdl_launch_dependents();  // the next kernel may start filling SMs as our CTAs retire
   if (threadIdx.x < NP) s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
   if (EPI == EPI_NHWC && threadIdx.x < NP) {
     // output offset of packed channel c relative to pixel (Y*r, X*r, 0): depth_to_space index, -1 = padding channel
@@ -513,12 +521,6 @@ __global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS>::kThreads, 1) conv_tc_k
       off = (ddy * p.FW * r + ddx) * C + ch;
     }
     s_tab[c] = off;
-  }
-  if (warp == 1) tmem_alloc<L::kTmemCols>(smem_u32(tmem_slot));
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.map_in);
-    tma_prefetch_desc(&p.map_w);
-    if (EPI == EPI_FPA) tma_prefetch_desc(&p.map_out);
   }
   tc_fence_before();
   __syncthreads();
@@ -687,12 +689,14 @@ __global__ void __launch_bounds__(ConvGatherCfg<KS, CIN>::kThreads, 1) conv_gath
     }
     fence_mbar_init();
   }
-  if (threadIdx.x < 64) s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
   if (warp == 1) tmem_alloc<256>(smem_u32(tmem_slot));
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.map_w);
     tma_prefetch_desc(&p.map_out);
   }
+  pdl_wait();
+  pdl_launch_dependents();
+  if (threadIdx.x < 64) s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -821,8 +825,7 @@ static int launch_conv_gather(srk_ctx* h, ConvGatherParams& gp, const void* w_pa
   if (int rc = make_tensor_map_2d(&p.map_w, w_packed, uint64_t(L::kBlocks * 64), 64, 64)) return rc;
   if (int rc = make_tensor_map_2d(&p.map_out, y_fpa, uint64_t(p.rows_valid), 64, 128)) return rc;
   const int grid = p.num_tiles < h->num_sms ? p.num_tiles : h->num_sms;
-  conv_gather_tc_kernel<KS, CIN><<<grid, L::kThreads, L::kTotal, stream>>>(gp);
-  SRK_LAUNCH_CHECK();
+  SRK_CHECK_CUDA(launch_pdl(conv_gather_tc_kernel<KS, CIN>, dim3(grid), dim3(L::kThreads), L::kTotal, stream, gp));
   return 0;
 }
 
@@ -847,8 +850,7 @@ static int launch_conv_tc(srk_ctx* h, ConvTcParams& p, const void* x, const void
     if (int rc = make_tensor_map_2d(&p.map_out, y_fpa, uint64_t(p.rows_valid), NP, L::kTileStride)) return rc;
   }
   const int grid = p.num_tiles < h->num_sms ? p.num_tiles : h->num_sms;
-  conv_tc_kernel<CIN, NP, KS, EPI><<<grid, L::kThreads, L::kTotal, stream>>>(p);
-  SRK_LAUNCH_CHECK();
+  SRK_CHECK_CUDA(launch_pdl(conv_tc_kernel<CIN, NP, KS, EPI>, dim3(grid), dim3(L::kThreads), L::kTotal, stream, p));
   return 0;
 }
 

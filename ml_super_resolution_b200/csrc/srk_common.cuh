@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <utility>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -68,5 +69,29 @@ inline FpaGeom fpa_geom(int n_img, int H, int W) {
 int make_tensor_map_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint32_t cols, uint32_t box_rows);
 
 inline cudaStream_t as_stream(srk_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Programmatic dependent launch: the kernel may become resident while its predecessor in the stream is still
+// draining (its CTAs start on an SM the moment the predecessor's CTA there exits, instead of after the whole grid
+// has finished plus a launch latency).  Every kernel launched this way calls pdl_wait() before its first access to
+// global memory and pdl_launch_dependents() right after, so data dependencies stay exactly those of the stream.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 }  // namespace srk

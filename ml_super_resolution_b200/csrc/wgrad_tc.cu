@@ -80,6 +80,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     mbar_init(bar_done, 1);
     fence_mbar_init();
   }
+  pdl_wait();
+  pdl_launch_dependents();
   // 16 rows x 64 channels of bf16 1.0 (0x3F80): the swizzle of a constant block is the block itself
   for (int i = threadIdx.x; i < 2048 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem + WgSmem::kOffOnes)[i] = 0x3F803F80u;
   fence_proxy_async_smem();
@@ -211,6 +213,8 @@ struct WgradDst {
 };
 __global__ void __launch_bounds__(128) wgrad_reduce_kernel(const float4* __restrict__ partial_base, size_t layer_stride_f4, int n_part,
                                                            const WgradDst* __restrict__ dsts, WgradDst single, int accumulate) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // float4 index
   constexpr int kN4 = kPartialFloats / 4;
   if (i >= kN4) return;
@@ -287,13 +291,11 @@ extern "C" int srk_conv_wgrad_tc(srk_handle_t h, const void* x_fpa, const void* 
     SRK_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem::kTotal));
     attr_set = true;
   }
-  wgrad_tc_kernel<<<grid, kWgThreads, WgSmem::kTotal, as_stream(stream)>>>(p);
-  SRK_LAUNCH_CHECK();
+  SRK_CHECK_CUDA(launch_pdl(wgrad_tc_kernel, dim3(grid), dim3(kWgThreads), size_t(WgSmem::kTotal), as_stream(stream), p));
   if (dw_hwio) {
     WgradDst single{dw_hwio, dbias, 64, 64};
-    wgrad_reduce_kernel<<<dim3((kPartialFloats / 4 + 127) / 128, 1), 128, 0, as_stream(stream)>>>(static_cast<const float4*>(workspace), 0, grid,
-                                                                                            nullptr, single, accumulate);
-    SRK_LAUNCH_CHECK();
+    SRK_CHECK_CUDA(launch_pdl(wgrad_reduce_kernel, dim3((kPartialFloats / 4 + 127) / 128, 1), dim3(128), 0, as_stream(stream),
+                              static_cast<const float4*>(workspace), size_t(0), grid, static_cast<const WgradDst*>(nullptr), single, accumulate));
   }
   return 0;
 }
@@ -306,8 +308,8 @@ extern "C" int srk_wgrad_reduce_many(srk_handle_t h, const void* workspace_base,
   const FpaGeom g = fpa_geom(n_img, H, W);
   const int n_part = wgrad_grid(h, int((g.rows_valid + 127) / 128));
   SRK_REQUIRE(layer_stride_bytes >= size_t(n_part) * kPartialFloats * sizeof(float), "srk_wgrad_reduce_many: layer stride smaller than one layer's partials");
-  wgrad_reduce_kernel<<<dim3((kPartialFloats / 4 + 127) / 128, n_layers), 128, 0, as_stream(stream)>>>(
-      static_cast<const float4*>(workspace_base), layer_stride_bytes / 16, n_part, reinterpret_cast<const WgradDst*>(dsts_device), WgradDst{}, accumulate);
-  SRK_LAUNCH_CHECK();
+  SRK_CHECK_CUDA(launch_pdl(wgrad_reduce_kernel, dim3((kPartialFloats / 4 + 127) / 128, n_layers), dim3(128), 0, as_stream(stream),
+                            static_cast<const float4*>(workspace_base), size_t(layer_stride_bytes / 16), n_part,
+                            reinterpret_cast<const WgradDst*>(dsts_device), WgradDst{}, accumulate));
   return 0;
 }
