@@ -29,6 +29,8 @@
 //                 profiles/r1_ncu_conv_tc_v2.txt): tcgen05.ld -> lane-shift add -> bias/activation/mask ->
 //                 bf16 -> swizzled smem -> TMA store, or fp32 NHWC scatter with residual add / panel crop /
 //                 pixel shuffle
+#include <cstdlib>
+
 #include "sm100_ptx.cuh"
 #include "srk_common.cuh"
 
@@ -60,6 +62,7 @@ struct alignas(64) ConvTcParams {
   const float* addend;
   const srk_panel* panels;
   int cout, shuffle_r, FH, FW;
+  int dbg;  // development switches (env SRK_DBG): bit0 skip lane exchange+shuffles, bit1 skip staging store, bit2 skip tmem loads
 };
 
 template <int CIN, int NP, int KS>
@@ -162,6 +165,7 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 template <int TS>
 __device__ __forceinline__ void conv_store_loop(const ConvTcParams& p, const EpiCtx& e, int t_begin, int t_end) {
   const bool dbl = e.stage_bufs == 2;
+  if (p.dbg & (8 | 16)) return;
   for (int t = t_begin; t < t_end; ++t) {
     const int it = t - t_begin, sb = dbl ? (it & 1) : 0, sgen = dbl ? (it >> 1) : it;
     mbar_wait(e.bar_sfull + 8u * sb, sgen & 1);
@@ -246,6 +250,11 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
     const int it = t - t_begin, acc = it % ACC, accgen = it / ACC;
     mbar_wait(e.bar_tfull0 + 8u * acc, accgen & 1);
     tc_fence_after();
+    if (p.dbg & 16) {
+      tc_fence_before();
+      mbar_arrive(e.bar_tempty0 + 8u * acc);
+      continue;
+    }
     const uint32_t taddr = tmem + acc * KN + col0 + (uint32_t(quad * 32) << 16);
     float blk[KS][CP];
 #pragma unroll
@@ -257,7 +266,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
     float v[CP];
 #pragma unroll
     for (int c = 0; c < CP; ++c) v[c] = blk[H_][c];
-    if constexpr (KS > 1) {
+    if (KS > 1 && !(p.dbg & 1)) {
       // ---- lane-shift add of the KS column blocks: y[j] = sum_dx D[j + dx][block dx]
 #pragma unroll
       for (int b = 0; b < KS; ++b) {
@@ -404,9 +413,10 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
         for (int c = 0; c < CP / 2; ++c) packed[c] = 0u;  // pad rows/columns stay exactly zero
       }
       // staging buffer free? (the store that last used this buffer has finished reading it)
+      if (p.dbg & 8) continue;
       const int sb = (e.stage_bufs == 2) ? (it & 1) : 0, sgen = (e.stage_bufs == 2) ? (it >> 1) : it;
       mbar_wait(e.bar_sfree + 8u * sb, (sgen & 1) ^ 1);
-      if (lane_valid) {
+      if (lane_valid && !(p.dbg & 2)) {
 #pragma unroll
         for (int j = 0; j < CP / 8; ++j)
           sts128u(st_addr[j] + sb * e.stage_stride, packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
@@ -557,43 +567,73 @@ __global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS>::kThreads, 1) conv_tc_k
     } else if (warp == 1) {
       // ------------------------------------------------------------------ MMA issuer (one thread)
       if (lane == 0) {
+        // This single thread is the kernel's critical path: every instruction it executes pays its full dependent
+        // latency (~10 cycles), and 12 MMAs of 96 cycles leave only ~1150 cycles per tile.  So the loop carries running
+        // counters (no divisions, no modulo), the weight descriptors are built once, and a window's descriptor is one
+        // 32-bit add away from the previous one.
         constexpr uint32_t idesc = umma_idesc_bf16(128, L::kN, 0, 0);
         constexpr uint64_t hi = umma_desc_hi(0, kSbo, kLayout);
-        mbar_wait(bar_wfull, 0);
-        int loaded = c0 - 1, released = c0;  // chunks <= loaded have landed; chunks < released were handed back
-        // running window rows (relative to the ring origin, already wrapped): advance TS rows per tile, wrap by subtraction
+        constexpr uint32_t hi32 = uint32_t(hi >> 32);
         constexpr int kRingRows = kRingSlots * kChunkRows;
-        int win[KS];
+        constexpr int KK = CIN / 16;
+        mbar_wait(bar_wfull, 0);
+        uint32_t b_lo[KS * KK];  // low words of the weight descriptors: constant for the whole kernel
+#pragma unroll
+        for (int r = 0; r < KS; ++r)
+#pragma unroll
+          for (int k = 0; k < KK; ++k) b_lo[r * KK + k] = ((s_w + r * KS * L::kWTapBytes + k * 32) >> 4) & 0x3FFF;
+        int win[KS];  // window start rows relative to the ring origin, already wrapped
 #pragma unroll
         for (int r = 0; r < KS; ++r) win[r] = (TS * t_begin - H_ - c0 * kChunkRows + (r - H_) * p.Wp) % kRingRows;
+        // chunk bookkeeping as running values: rows (relative to chunk c0) of the last row a tile touches / first row the
+        // next tile touches; ring slot + parity of the next chunk to wait for / to hand back
+        int hi_row = TS * t_begin - H_ + reach + 127 - c0 * kChunkRows;      // >= 0
+        int lo_row_next = TS * (t_begin + 1) - H_ - reach - c0 * kChunkRows;  // may be negative for the first tiles
+        int loaded_n = 0, released_n = 0;                                    // chunks waited for / handed back so far
+        uint32_t wait_slot = 0, wait_par = 0, rel_slot = 0;
+        uint32_t acc = 0, acc_par = 1;  // accumulator stage and the parity its "empty" barrier is waited with
         for (int t = t_begin; t < t_end; ++t) {
-          const int it = t - t_begin, acc = it % ACC, accgen = it / ACC;
-          const int need = hi_chunk(t);
-          while (loaded < need) {
-            ++loaded;
-            const int i = loaded - c0;
-            mbar_wait(bar_full(i % kRingSlots), (i / kRingSlots) & 1);
+          const int need_n = (hi_row >> 6) + 1;  // kChunkRows == 64
+          while (loaded_n < need_n) {
+            mbar_wait(bar_full(wait_slot), wait_par);
+            ++loaded_n;
+            if (++wait_slot == kRingSlots) {
+              wait_slot = 0;
+              wait_par ^= 1;
+            }
           }
-          mbar_wait(bar_tempty(acc), (accgen & 1) ^ 1);
+          mbar_wait(bar_tempty(acc), acc_par);
           tc_fence_after();
           const uint32_t d_tmem = tmem + acc * L::kN;
 #pragma unroll
           for (int r = 0; r < KS; ++r) {
-            const uint32_t a_addr = s_ring + win[r] * L::kRowBytes;
-            const uint32_t b_addr = s_w + r * KS * L::kWTapBytes;
+            const uint32_t a_lo = ((s_ring + win[r] * L::kRowBytes) >> 4) & 0x3FFF;
 #pragma unroll
-            for (int k = 0; k < CIN / 16; ++k)
-              umma_bf16(d_tmem, umma_desc(hi, a_addr + k * 32), umma_desc(hi, b_addr + k * 32), idesc, (r | k) != 0);
+            for (int k = 0; k < KK; ++k) {
+              const uint64_t adesc = (uint64_t(hi32) << 32) | uint64_t(a_lo + 2 * k);
+              const uint64_t bdesc = (uint64_t(hi32) << 32) | uint64_t(b_lo[r * KK + k]);
+              if (r == 0 && k == 0) umma_bf16(d_tmem, adesc, bdesc, idesc, 0u);
+              else umma_bf16(d_tmem, adesc, bdesc, idesc, 1u);
+            }
             win[r] += TS;
             win[r] -= (win[r] >= kRingRows) ? kRingRows : 0;
           }
           umma_commit(bar_tfull(acc));
-          // hand back the chunks no later tile needs
-          const int keep_from = (t + 1 < t_end) ? lo_chunk(t + 1) : released;
-          while (released < keep_from) {
-            umma_commit(bar_empty((released - c0) % kRingSlots));
-            ++released;
+          if (++acc == ACC) {
+            acc = 0;
+            acc_par ^= 1;
           }
+          // hand back the chunks no later tile needs
+          if (t + 1 < t_end) {
+            const int keep_n = lo_row_next >> 6;  // arithmetic shift == floor; negative: nothing to release yet
+            while (released_n < keep_n) {
+              umma_commit(bar_empty(rel_slot));
+              ++released_n;
+              if (++rel_slot == kRingSlots) rel_slot = 0;
+            }
+          }
+          hi_row += TS;
+          lo_row_next += TS;
         }
       }
     } else if (warp == 2) {
@@ -855,6 +895,10 @@ static int launch_conv_tc(srk_ctx* h, ConvTcParams& p, const void* x, const void
 }
 
 static int fill_geom(ConvTcParams& p, int n_img, int H, int W) {
+  {
+    const char* e = getenv("SRK_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
   SRK_REQUIRE(n_img > 0 && H > 0 && W > 0, "conv_tc: bad geometry n_img=%d H=%d W=%d", n_img, H, W);
   const FpaGeom g = fpa_geom(n_img, H, W);
   SRK_REQUIRE(g.rows_valid < (int64_t(1) << 30), "conv_tc: %lld rows exceed the 2^30 row limit", (long long)g.rows_valid);

@@ -63,12 +63,14 @@ void run(int grid, int iters, int stride) {
 }
 
 int main() {
-  for (int grid : {1, 148}) {
+  for (int grid : {148}) {
     run<64>(grid, 4096, 1);
     run<64>(grid, 4096, 43);
     run<32>(grid, 4096, 43);
     run<16>(grid, 4096, 43);
+    run<96>(grid, 4096, 43);
     run<128>(grid, 4096, 43);
+    run<192>(grid, 4096, 43);
     run<256>(grid, 4096, 43);
   }
   return 0;
