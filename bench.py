@@ -284,8 +284,20 @@ def vdsr_infer_workload(args, rank, world):
     sd = torch.rand((1, H, W, 3), device="cuda", generator=g) * 2 - 1
     out = torch.empty_like(sd)
 
+    # tile grid: 252-px column panels; with several GPUs the panels are also cut into row bands (20-px halo) until the tile
+    # count divides evenly over the ranks (18 panels -> 72 tiles on 8 GPUs)
+    from ml_super_resolution_b200.tiling import plan_tiles
+    tile_rows = None
+    if world > 1:
+        n_panels = len(plan_tiles(1, H, W, VDSR_LAYERS)[2])
+        for k in (1, 2, 3, 4):
+            if (n_panels * k) % world == 0:
+                break
+        if k > 1:
+            tile_rows = -(-(H - 2 * VDSR_LAYERS) // k) + 2 * VDSR_LAYERS
+
     def step():
-        net.forward(sd, out=out, rank=rank, world=world)
+        net.forward(sd, out=out, rank=rank, world=world, tile_rows=tile_rows)
 
     ms, clocks = timed_steps(step, args.steps, args.warmup, world, ClockSampler(torch.cuda.current_device()) if rank == 0 else None)
     value = H * W * args.steps / ms / 1e3  # one frame per step for the whole job (strong scaling over tiles)
@@ -299,7 +311,7 @@ def vdsr_infer_workload(args, rank, world):
 
     def e2e_step():
         s = sd_h.to("cuda", non_blocking=True)
-        net.forward(s, out=out, rank=rank, world=world)
+        net.forward(s, out=out, rank=rank, world=world, tile_rows=tile_rows)
         out_h.copy_(out, non_blocking=True)
 
     ms_e, _ = timed_steps(e2e_step, max(2, args.steps // 2), 1, world, None)

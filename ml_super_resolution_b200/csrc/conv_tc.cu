@@ -565,9 +565,11 @@ __global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS>::kThreads, 1) conv_tc_k
         }
       }
     } else if (warp == 1) {
-      // ------------------------------------------------------------------ MMA issuer (one thread)
-      if (lane == 0) {
-        // This single thread is the kernel's critical path: every instruction it executes pays its full dependent
+      // ------------------------------------------------------------------ MMA issuer (whole warp runs the loop, one elected lane issues)
+      {
+        // The warp executes the loop convergently so that addresses and descriptors live in UNIFORM registers (no R2UR
+        // hops before every UTCHMMA); only the tcgen05 instructions themselves are predicated on one elected lane.
+        // This single issue stream is the kernel's critical path: every instruction it executes pays its full dependent
         // latency (~10 cycles), and 12 MMAs of 96 cycles leave only ~1150 cycles per tile.  So the loop carries running
         // counters (no divisions, no modulo), the weight descriptors are built once, and a window's descriptor is one
         // 32-bit add away from the previous one.
@@ -608,17 +610,21 @@ __global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS>::kThreads, 1) conv_tc_k
 #pragma unroll
           for (int r = 0; r < KS; ++r) {
             const uint32_t a_lo = ((s_ring + win[r] * L::kRowBytes) >> 4) & 0x3FFF;
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < KK; ++k) {
-              const uint64_t adesc = (uint64_t(hi32) << 32) | uint64_t(a_lo + 2 * k);
-              const uint64_t bdesc = (uint64_t(hi32) << 32) | uint64_t(b_lo[r * KK + k]);
-              if (r == 0 && k == 0) umma_bf16(d_tmem, adesc, bdesc, idesc, 0u);
-              else umma_bf16(d_tmem, adesc, bdesc, idesc, 1u);
+              for (int k = 0; k < KK; ++k) {
+                const uint64_t adesc = (uint64_t(hi32) << 32) | uint64_t(a_lo + 2 * k);
+                const uint64_t bdesc = (uint64_t(hi32) << 32) | uint64_t(b_lo[r * KK + k]);
+                if (r == 0 && k == 0) umma_bf16(d_tmem, adesc, bdesc, idesc, 0u);
+                else umma_bf16(d_tmem, adesc, bdesc, idesc, 1u);
+              }
             }
+            __syncwarp();
             win[r] += TS;
             win[r] -= (win[r] >= kRingRows) ? kRingRows : 0;
           }
-          umma_commit(bar_tfull(acc));
+          if (elect_one()) umma_commit(bar_tfull(acc));
+          __syncwarp();
           if (++acc == ACC) {
             acc = 0;
             acc_par ^= 1;
@@ -627,7 +633,8 @@ __global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS>::kThreads, 1) conv_tc_k
           if (t + 1 < t_end) {
             const int keep_n = lo_row_next >> 6;  // arithmetic shift == floor; negative: nothing to release yet
             while (released_n < keep_n) {
-              umma_commit(bar_empty(rel_slot));
+              if (elect_one()) umma_commit(bar_empty(rel_slot));
+              __syncwarp();
               ++released_n;
               if (++rel_slot == kRingSlots) rel_slot = 0;
             }
