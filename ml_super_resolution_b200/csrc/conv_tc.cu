@@ -182,31 +182,29 @@ __device__ __forceinline__ void conv_store_loop(const ConvTcParams& p, const Epi
   tma_store_wait_all<0>();
 }
 
-// Epilogue warp `ewarp` (0..15): TMEM lane quadrant ewarp & 3, column group ewarp >> 2 (CP = NP/4 channels).
-// Per tile and thread: KS tcgen05.ld of CP columns -> lane-shift add (rotating shuffles; the two edge lanes of a
-// warp first swap in the neighbouring quadrant's row through shared memory) -> packed fp32x2 bias add -> bf16x2
-// pack -> ReLU / ReLU' mask on the packed pairs -> two swizzled 16-byte stores into the staging tile.
+// Epilogue.  The 16 epilogue warps form TWO SETS of 8 that take alternate tiles, so two tiles' epilogue chains
+// (tcgen05.ld -> lane exchange -> shuffles -> pack -> staging) are in flight at once: with a single set the chain
+// latency of ~1.4 us per tile, not the tensor pipe, bounded the kernel.  Within a set: TMEM lane quadrant
+// ewarp & 3, column half (ewarp >> 2) & 1; a thread covers its half of the NP output channels in two passes of
+// CP = NP/4 columns (keeps the live accumulator registers at 3*CP).
+//   per pass: KS tcgen05.ld of CP columns -> lane-shift add (rotating shuffles; the edge lanes of a warp first swap in
+//   the neighbouring quadrant's row through shared memory) -> packed fp32x2 bias add -> bf16x2 pack -> ReLU / ReLU'
+//   mask on the packed pairs;  per tile: swizzled 16-byte stores into the staging tile (TMA-stored by warp 2).
 template <int NP, int KS, int EPI, int ACC, int KN>
 __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCtx& e, int ewarp, int lane, int t_begin, int t_end) {
   constexpr int H_ = KS / 2, TS = 128 - (KS - 1), CP = NP / 4;
   constexpr int kNB = (KS > 1) ? KS - 1 : 1;           // shifted blocks
   constexpr int kXq = kNB * (H_ > 0 ? H_ : 1) * CP * 4;  // bytes per (parity, quadrant)
   constexpr int kXpar = 4 * kXq;                       // bytes per parity
-  constexpr int kXgrp = 2 * kXpar;                     // bytes per column group
+  constexpr int kXgrp = 2 * kXpar;                     // bytes per exchange group
   const uint32_t tmem = e.tmem;
-  const int quad = ewarp & 3;   // TMEM lane quadrant this warp may access (hardware: warp index % 4)
-  const int grp = ewarp >> 2;   // column group: channels [CP*grp, CP*grp + CP)
-  const int row = quad * 32 + lane;  // lane j of the accumulator <-> flat row TS*t - h + j
-  const int col0 = grp * CP;
+  const int quad = ewarp & 3;          // TMEM lane quadrant this warp may access (hardware: warp index % 4)
+  const int half = (ewarp >> 2) & 1;   // which half of the output channels
+  const int set = ewarp >> 3;          // which tiles: local tile index it with (it & 1) == set
+  const int grp = set * 2 + half;      // exchange group / named barrier: the 4 quadrant warps that share columns and tile
+  const int row = quad * 32 + lane;    // lane j of the accumulator <-> flat row TS*t - h + j
   const bool lane_valid = (row >= H_) && (row < H_ + TS);
   const uint32_t xg = e.xch_addr + grp * kXgrp;
-  float bias_r[CP];
-  int tab_r[CP];
-#pragma unroll
-  for (int c = 0; c < CP; ++c) {
-    bias_r[c] = e.s_bias[col0 + c];
-    tab_r[c] = (EPI == EPI_NHWC) ? e.s_tab[col0 + c] : 0;
-  }
   // per-thread constant addresses of the lane exchange (parity 0) ...
   uint32_t pub_addr[KS], sub_addr[KS];
   bool do_pub[KS], do_sub[KS];
@@ -222,95 +220,29 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
     pub_addr[b] = xg + quad * kXq + (bi * H_ + li) * CP * 4;
     sub_addr[b] = xg + nq * kXq + (bi * H_ + li) * CP * 4;
   }
-  // ... and of this thread's 16-byte chunks in staging buffer 0
-  uint32_t st_addr[CP >= 8 ? CP / 8 : 1];
-  if constexpr (EPI == EPI_FPA) {
-    const int srow = row - H_;
-    const int sw = (NP == 64) ? (srow & 7) : ((srow >> 1) & 3);
-#pragma unroll
-    for (int j = 0; j < CP / 8; ++j) st_addr[j] = e.stage_addr + srow * (NP * 2) + (((grp * (CP / 8) + j) ^ sw) << 4);
-  }
-  // pixel coordinates of this lane's row in the first tile, then advanced by TS rows per tile
+  // ... and of this thread's first 16-byte chunk in staging buffer 0 (chunk index XOR swizzle applied per chunk)
+  const int srow = row - H_;
+  const int sw = (NP == 64) ? (srow & 7) : ((srow >> 1) & 3);
+  const uint32_t st_row = e.stage_addr + srow * (NP * 2);
+  // pixel coordinates of this lane's row in this set's first tile, then advanced by 2*TS rows per processed tile
   const int H1 = p.H + 1;
   int px, pyy, pn;
   {
-    const int64_t prow0 = int64_t(TS) * t_begin - H_ + row;
+    const int64_t prow0 = int64_t(TS) * (t_begin + set) - H_ + row;
     const uint32_t pr = uint32_t(prow0 < 0 ? 0 : prow0);
     const uint32_t q = pr / uint32_t(p.Wp);
     px = int(pr - q * uint32_t(p.Wp));
     pn = int(q / uint32_t(H1));
     pyy = int(q - uint32_t(pn) * uint32_t(H1));
   }
-  const int adv_x = TS % p.Wp, adv_q = TS / p.Wp;
+  const int adv_x = (2 * TS) % p.Wp, adv_q = (2 * TS) / p.Wp;
   const int adv_y = adv_q % H1, adv_n = adv_q / H1;
   const int act = p.act;
+  const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
   uint32_t xpar = 0;  // byte offset of the exchange parity in use
 
-  for (int t = t_begin; t < t_end; ++t) {
+  for (int t = t_begin + set; t < t_end; t += 2) {
     const int it = t - t_begin, acc = it % ACC, accgen = it / ACC;
-    mbar_wait(e.bar_tfull0 + 8u * acc, accgen & 1);
-    tc_fence_after();
-    if (p.dbg & 16) {
-      tc_fence_before();
-      mbar_arrive(e.bar_tempty0 + 8u * acc);
-      continue;
-    }
-    const uint32_t taddr = tmem + acc * KN + col0 + (uint32_t(quad * 32) << 16);
-    float blk[KS][CP];
-#pragma unroll
-    for (int b = 0; b < KS; ++b) tmem_load_cols<CP>(taddr + b * NP, blk[b]);
-    tmem_ld_wait();
-    tc_fence_before();
-    mbar_arrive(e.bar_tempty0 + 8u * acc);
-
-    float v[CP];
-#pragma unroll
-    for (int c = 0; c < CP; ++c) v[c] = blk[H_][c];
-    if (KS > 1 && !(p.dbg & 1)) {
-      // ---- lane-shift add of the KS column blocks: y[j] = sum_dx D[j + dx][block dx]
-#pragma unroll
-      for (int b = 0; b < KS; ++b) {
-        if (b == H_) continue;
-        if (do_pub[b]) {
-#pragma unroll
-          for (int c = 0; c < CP / 4; ++c) sts128(pub_addr[b] + xpar + c * 16, blk[b][4 * c], blk[b][4 * c + 1], blk[b][4 * c + 2], blk[b][4 * c + 3]);
-        }
-      }
-      named_bar_sync(1 + grp, 128);
-      // the edge lanes take over the neighbouring quadrant's row (their own value of that block is not needed any
-      // more); then ONE rotating shuffle per column serves every lane: no per-element select, and every output
-      // sees the same fp32 addition order (tiled == un-tiled bit for bit)
-#pragma unroll
-      for (int b = 0; b < KS; ++b) {
-        if (b == H_) continue;
-        if (do_sub[b]) {
-#pragma unroll
-          for (int c = 0; c < CP / 4; ++c) {
-            const float4 o = lds128(sub_addr[b] + xpar + c * 16);
-            blk[b][4 * c] = o.x;
-            blk[b][4 * c + 1] = o.y;
-            blk[b][4 * c + 2] = o.z;
-            blk[b][4 * c + 3] = o.w;
-          }
-        }
-      }
-#pragma unroll
-      for (int b = 0; b < KS; ++b) {
-        if (b == H_) continue;
-        const int src_lane = (lane + (b - H_)) & 31;
-        float sh[CP];
-#pragma unroll
-        for (int c = 0; c < CP; ++c) sh[c] = __shfl_sync(0xffffffffu, blk[b][c], src_lane);
-#pragma unroll
-        for (int c = 0; c < CP; c += 2) {
-          const float2 r = __fadd2_rn(make_float2(v[c], v[c + 1]), make_float2(sh[c], sh[c + 1]));
-          v[c] = r.x;
-          v[c + 1] = r.y;
-        }
-      }
-      xpar ^= kXpar;
-    }
-
     // the pixel this lane holds
     const int64_t prow = int64_t(TS) * t - H_ + row;
     bool valid = lane_valid && prow < p.rows_valid && (px < p.W) && (pyy > 0);
@@ -324,127 +256,178 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
       pyy -= cy ? H1 : 0;
       pn += adv_n + cy;
     }
+    mbar_wait(e.bar_tfull0 + 8u * acc, accgen & 1);
+    tc_fence_after();
+    uint32_t packed[2][CP >= 2 ? CP / 2 : 1];
 
-    // bias (packed fp32x2 adds) and tanh
 #pragma unroll
-    for (int c = 0; c < CP; c += 2) {
-      const float2 r = __fadd2_rn(make_float2(v[c], v[c + 1]), make_float2(bias_r[c], bias_r[c + 1]));
-      v[c] = r.x;
-      v[c + 1] = r.y;
-    }
-    if (act == SRK_ACT_TANH) {
+    for (int pass = 0; pass < 2; ++pass) {
+      const int col0 = (half * 2 + pass) * CP;
+      const uint32_t taddr = tmem + acc * KN + col0 + (uint32_t(quad * 32) << 16);
+      float blk[KS][CP];
 #pragma unroll
-      for (int c = 0; c < CP; ++c) v[c] = act_apply(v[c], SRK_ACT_TANH);
-    }
-
-    if constexpr (EPI == EPI_FPA) {
-      static_assert(CP >= 8, "FPA epilogue stores 16-byte chunks");
-      uint32_t packed[CP / 2];
-      const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
-      if (valid) {
-        if (p.addend_fpa || (p.mask_src && p.mask_kind != SRK_ACT_RELU)) {
-          // rare forms (EnhanceNet block residual, tanh' mask): fp32 path
-          if (act == SRK_ACT_RELU) {
+      for (int b = 0; b < KS; ++b) tmem_load_cols<CP>(taddr + b * NP, blk[b]);
+      tmem_ld_wait();
+      if (pass == 1) {  // this thread has read everything it needs from the accumulator stage
+        tc_fence_before();
+        mbar_arrive(e.bar_tempty0 + 8u * acc);
+      }
+      float v[CP];
 #pragma unroll
-            for (int c = 0; c < CP; ++c) v[c] = fmaxf(v[c], 0.f);
+      for (int c = 0; c < CP; ++c) v[c] = blk[H_][c];
+      if constexpr (KS > 1) {
+        // ---- lane-shift add of the KS column blocks: y[j] = sum_dx D[j + dx][block dx]
+#pragma unroll
+        for (int b = 0; b < KS; ++b) {
+          if (b == H_) continue;
+          if (do_pub[b]) {
+#pragma unroll
+            for (int c = 0; c < CP / 4; ++c) sts128(pub_addr[b] + xpar + c * 16, blk[b][4 * c], blk[b][4 * c + 1], blk[b][4 * c + 2], blk[b][4 * c + 3]);
           }
-          if (p.mask_src) {
-            const uint4* m = reinterpret_cast<const uint4*>(p.mask_src + size_t(prow) * NP + col0);
+        }
+        named_bar_sync(1 + grp, 128);
+        // the edge lanes take over the neighbouring quadrant's row (their own value of that block is not needed any
+        // more); then ONE rotating shuffle per column serves every lane: no per-element select, and every output
+        // sees the same fp32 addition order (tiled == un-tiled bit for bit)
 #pragma unroll
-            for (int j = 0; j < CP / 8; ++j) {
-              const uint4 mv = __ldg(m + j);
-              const uint32_t w4[4] = {mv.x, mv.y, mv.z, mv.w};
+        for (int b = 0; b < KS; ++b) {
+          if (b == H_) continue;
+          if (do_sub[b]) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[q]));
-                v[j * 8 + q * 2] *= (1.f - f.x * f.x);
-                v[j * 8 + q * 2 + 1] *= (1.f - f.y * f.y);
-              }
-            }
-          }
-          if (p.addend_fpa) {
-            const uint4* a = reinterpret_cast<const uint4*>(p.addend_fpa + size_t(prow) * NP + col0);
-#pragma unroll
-            for (int j = 0; j < CP / 8; ++j) {
-              const uint4 av = __ldg(a + j);
-              const uint32_t w4[4] = {av.x, av.y, av.z, av.w};
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[q]));
-                v[j * 8 + q * 2] += f.x;
-                v[j * 8 + q * 2 + 1] += f.y;
-              }
-            }
-            if (p.relu_after_add) {
-#pragma unroll
-              for (int c = 0; c < CP; ++c) v[c] = fmaxf(v[c], 0.f);
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < CP / 2; ++c) packed[c] = pack_bf16x2(v[2 * c], v[2 * c + 1]);
-        } else {
-          // common forms: ReLU and the ReLU' mask act on the packed bf16 pairs (both commute with the rounding)
-#pragma unroll
-          for (int c = 0; c < CP / 2; ++c) packed[c] = pack_bf16x2(v[2 * c], v[2 * c + 1]);
-          if (act == SRK_ACT_RELU) {
-#pragma unroll
-            for (int c = 0; c < CP / 2; ++c) {
-              const __nv_bfloat162 h = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&packed[c]), zero2);
-              packed[c] = *reinterpret_cast<const uint32_t*>(&h);
-            }
-          }
-          if (p.mask_src) {
-            const uint4* m = reinterpret_cast<const uint4*>(p.mask_src + size_t(prow) * NP + col0);
-#pragma unroll
-            for (int j = 0; j < CP / 8; ++j) {
-              const uint4 mv = __ldg(m + j);
-              const uint32_t w4[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const __nv_bfloat162 gt = __hgt2(*reinterpret_cast<const __nv_bfloat162*>(&w4[q]), zero2);  // 1.0 / 0.0 per half
-                const __nv_bfloat162 h = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&packed[j * 4 + q]), gt);
-                packed[j * 4 + q] = *reinterpret_cast<const uint32_t*>(&h);
-              }
+            for (int c = 0; c < CP / 4; ++c) {
+              const float4 o = lds128(sub_addr[b] + xpar + c * 16);
+              blk[b][4 * c] = o.x;
+              blk[b][4 * c + 1] = o.y;
+              blk[b][4 * c + 2] = o.z;
+              blk[b][4 * c + 3] = o.w;
             }
           }
         }
+#pragma unroll
+        for (int b = 0; b < KS; ++b) {
+          if (b == H_) continue;
+          const int src_lane = (lane + (b - H_)) & 31;
+          float sh[CP];
+#pragma unroll
+          for (int c = 0; c < CP; ++c) sh[c] = __shfl_sync(0xffffffffu, blk[b][c], src_lane);
+#pragma unroll
+          for (int c = 0; c < CP; c += 2) {
+            const float2 r = __fadd2_rn(make_float2(v[c], v[c + 1]), make_float2(sh[c], sh[c + 1]));
+            v[c] = r.x;
+            v[c + 1] = r.y;
+          }
+        }
+        xpar ^= kXpar;
+      }
+      // bias (packed fp32x2 adds; read from shared memory to keep registers for the accumulator blocks) and tanh
+#pragma unroll
+      for (int c = 0; c < CP; c += 2) {
+        const float2 bb = *reinterpret_cast<const float2*>(e.s_bias + col0 + c);
+        const float2 r = __fadd2_rn(make_float2(v[c], v[c + 1]), bb);
+        v[c] = r.x;
+        v[c + 1] = r.y;
+      }
+      if (act == SRK_ACT_TANH) {
+#pragma unroll
+        for (int c = 0; c < CP; ++c) v[c] = act_apply(v[c], SRK_ACT_TANH);
+      }
+
+      if constexpr (EPI == EPI_FPA) {
+        static_assert(CP >= 8, "FPA epilogue stores 16-byte chunks");
+        uint32_t* pk = packed[pass];
+        if (valid) {
+          if (p.addend_fpa || (p.mask_src && p.mask_kind != SRK_ACT_RELU)) {
+            // rare forms (EnhanceNet block residual, tanh' mask): fp32 path
+            if (act == SRK_ACT_RELU) {
+#pragma unroll
+              for (int c = 0; c < CP; ++c) v[c] = fmaxf(v[c], 0.f);
+            }
+            if (p.mask_src) {
+              const uint4* m = reinterpret_cast<const uint4*>(p.mask_src + size_t(prow) * NP + col0);
+#pragma unroll
+              for (int j = 0; j < CP / 8; ++j) {
+                const uint4 mv = __ldg(m + j);
+                const uint32_t w4[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[q]));
+                  v[j * 8 + q * 2] *= (1.f - f.x * f.x);
+                  v[j * 8 + q * 2 + 1] *= (1.f - f.y * f.y);
+                }
+              }
+            }
+            if (p.addend_fpa) {
+              const uint4* a = reinterpret_cast<const uint4*>(p.addend_fpa + size_t(prow) * NP + col0);
+#pragma unroll
+              for (int j = 0; j < CP / 8; ++j) {
+                const uint4 av = __ldg(a + j);
+                const uint32_t w4[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[q]));
+                  v[j * 8 + q * 2] += f.x;
+                  v[j * 8 + q * 2 + 1] += f.y;
+                }
+              }
+              if (p.relu_after_add) {
+#pragma unroll
+                for (int c = 0; c < CP; ++c) v[c] = fmaxf(v[c], 0.f);
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < CP / 2; ++c) pk[c] = pack_bf16x2(v[2 * c], v[2 * c + 1]);
+          } else {
+            // common forms: ReLU and the ReLU' mask act on the packed bf16 pairs (both commute with the rounding)
+#pragma unroll
+            for (int c = 0; c < CP / 2; ++c) pk[c] = pack_bf16x2(v[2 * c], v[2 * c + 1]);
+            if (act == SRK_ACT_RELU) {
+#pragma unroll
+              for (int c = 0; c < CP / 2; ++c) {
+                const __nv_bfloat162 h = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&pk[c]), zero2);
+                pk[c] = *reinterpret_cast<const uint32_t*>(&h);
+              }
+            }
+            if (p.mask_src) {
+              const uint4* m = reinterpret_cast<const uint4*>(p.mask_src + size_t(prow) * NP + col0);
+#pragma unroll
+              for (int j = 0; j < CP / 8; ++j) {
+                const uint4 mv = __ldg(m + j);
+                const uint32_t w4[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const __nv_bfloat162 gt = __hgt2(*reinterpret_cast<const __nv_bfloat162*>(&w4[q]), zero2);  // 1.0 / 0.0 per half
+                  const __nv_bfloat162 h = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&pk[j * 4 + q]), gt);
+                  pk[j * 4 + q] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < CP / 2; ++c) pk[c] = 0u;  // pad rows/columns stay exactly zero
+        }
       } else {
+        // fp32 NHWC scatter: residual add, panel crop, depth_to_space
+        if (act == SRK_ACT_RELU) {
 #pragma unroll
-        for (int c = 0; c < CP / 2; ++c) packed[c] = 0u;  // pad rows/columns stay exactly zero
-      }
-      // staging buffer free? (the store that last used this buffer has finished reading it)
-      if (p.dbg & 8) continue;
-      const int sb = (e.stage_bufs == 2) ? (it & 1) : 0, sgen = (e.stage_bufs == 2) ? (it >> 1) : it;
-      mbar_wait(e.bar_sfree + 8u * sb, (sgen & 1) ^ 1);
-      if (lane_valid && !(p.dbg & 2)) {
-#pragma unroll
-        for (int j = 0; j < CP / 8; ++j)
-          sts128u(st_addr[j] + sb * e.stage_stride, packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(e.bar_sfull + 8u * sb);
-    } else {
-      // fp32 NHWC scatter: residual add, panel crop, depth_to_space
-      if (act == SRK_ACT_RELU) {
-#pragma unroll
-        for (int c = 0; c < CP; ++c) v[c] = fmaxf(v[c], 0.f);
-      }
-      if (valid) {
+          for (int c = 0; c < CP; ++c) v[c] = fmaxf(v[c], 0.f);
+        }
+        bool st = valid;
         int fn = n, fy = y, fx = x;
-        if (p.panels) {
+        if (st && p.panels) {
           const srk_panel pe = p.panels[n];
-          valid = (y >= pe.own_y0) && (y < pe.own_y1) && (x >= pe.own_x0) && (x < pe.own_x1);
+          st = (y >= pe.own_y0) && (y < pe.own_y1) && (x >= pe.own_x0) && (x < pe.own_x1);
           fn = pe.frame;
           fy = pe.y0 + y;
           fx = pe.x0 + x;
         }
-        if (valid) {
+        if (st) {
           const int r = p.shuffle_r, C = p.cout / (r * r);
           const int64_t OW = int64_t(p.FW) * r;
           const int64_t base = ((int64_t(fn) * p.FH * r + int64_t(fy) * r) * OW + int64_t(fx) * r) * C;
 #pragma unroll
           for (int c = 0; c < CP; ++c) {
-            const int off = tab_r[c];
+            const int off = e.s_tab[col0 + c];
             if (off >= 0) {
               const int64_t idx = base + off;
               float o = v[c];
@@ -454,6 +437,24 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
           }
         }
       }
+    }  // pass
+
+    if constexpr (EPI == EPI_FPA) {
+      // staging buffer free? (the store that last used this buffer has finished reading it)
+      const int sb = (e.stage_bufs == 2) ? (it & 1) : 0, sgen = (e.stage_bufs == 2) ? (it >> 1) : it;
+      mbar_wait(e.bar_sfree + 8u * sb, (sgen & 1) ^ 1);
+      if (lane_valid) {
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass)
+#pragma unroll
+          for (int j = 0; j < CP / 8; ++j) {
+            const int chunk = (half * 2 + pass) * (CP / 8) + j;
+            sts128u(st_row + sb * e.stage_stride + ((chunk ^ sw) << 4), packed[pass][4 * j], packed[pass][4 * j + 1], packed[pass][4 * j + 2],
+                    packed[pass][4 * j + 3]);
+          }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(e.bar_sfull + 8u * sb);
     }
   }
 }
@@ -505,10 +506,10 @@ __global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS>::kThreads, 1) conv_tc_k
     mbar_init(bar_wfull, 1);
     for (int i = 0; i < ACC; ++i) {
       mbar_init(bar_tfull(i), 1);
-      mbar_init(bar_tempty(i), L::kEpiThreads);
+      mbar_init(bar_tempty(i), L::kEpiThreads / 2);  // one epilogue set (8 warps) per tile
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_sfull + 8u * i, L::kEpiThreads);
+      mbar_init(bar_sfull + 8u * i, L::kEpiThreads / 2);
       mbar_init(bar_sfree + 8u * i, 1);
     }
     fence_mbar_init();
@@ -728,10 +729,10 @@ __global__ void __launch_bounds__(ConvGatherCfg<KS, CIN>::kThreads, 1) conv_gath
     mbar_init(bar_wfull, 1);
     for (int i = 0; i < ACC; ++i) {
       mbar_init(bar_tfull(i), 1);
-      mbar_init(bar_tempty(i), L::kEpiThreads);
+      mbar_init(bar_tempty(i), L::kEpiThreads / 2);  // one epilogue set (8 warps) per tile
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_sfull + 8u * i, L::kEpiThreads);
+      mbar_init(bar_sfull + 8u * i, L::kEpiThreads / 2);
       mbar_init(bar_sfree + 8u * i, 1);
     }
     fence_mbar_init();
