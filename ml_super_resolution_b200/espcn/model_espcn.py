@@ -58,6 +58,86 @@ class EspcnNet:
         self.arena.load_numpy(params)
         self.repack()
 
+    # ------------------------------------------------------------------ training (reference build_model :76-94)
+    def _enable_training(self, n, H, W):
+        """Training runs every layer 64 channels wide (f2's 32 outputs / f3's 32 inputs zero-padded) so that the
+        64x64 tensor-core dgrad / wgrad kernels serve all three layers; loss is MSE in packed space (:76-77)."""
+        key = (n, H, W)
+        if getattr(self, "_tb", None) is not None and self._tb["key"] == key:
+            return self._tb
+        a = self.arena
+        a.enable_training()
+        plan = ops.PackPlan(self.device)
+        i = {}
+        i["f1"] = plan.add(a.offsets["f1/kernel:0"], 5, self.C, 64, ops.PACK_FIRST)
+        i["f2"] = plan.add(a.offsets["f2/kernel:0"], 3, 64, 32, ops.PACK_FWD, 64, 64)
+        i["f3"] = plan.add(a.offsets["f3/kernel:0"], 3, 32, self.cout3, ops.PACK_FWD, 32 if self.cout3 <= 32 else 64, 64)
+        i["d3"] = plan.add(a.offsets["f3/kernel:0"], 3, 32, self.cout3, ops.PACK_DGRAD, 64, 64)
+        i["d2"] = plan.add(a.offsets["f2/kernel:0"], 3, 64, 32, ops.PACK_DGRAD, 64, 64)
+        plan.finalize()
+        stride = (ops.wgrad_workspace_bytes(n, H, W) + 1023) // 1024 * 1024
+        np3 = plan.views[i["f3"]].shape[1]
+        self._tb = {
+            "key": key, "plan": plan, "idx": i, "stride": stride,
+            "a1": ops.fpa_empty(n, H, W, 64, self.device), "a2": ops.fpa_empty(n, H, W, 64, self.device),
+            "d": [ops.fpa_empty(n, H, W, 64, self.device) for _ in range(2)], "dP": ops.fpa_empty(n, H, W, 64, self.device),
+            "sr": torch.empty((n, H, W, self.cout3), dtype=torch.float32, device=self.device),
+            "dsr": torch.empty((n, H, W, self.cout3), dtype=torch.float32, device=self.device),
+            "loss": torch.zeros(1, dtype=torch.float32, device=self.device),
+            "bias2": torch.zeros(64, dtype=torch.float32, device=self.device),
+            "bias3": torch.zeros(np3, dtype=torch.float32, device=self.device),
+            "ws": torch.empty(stride * 2, dtype=torch.uint8, device=self.device),
+            "dsts": ops.make_wgrad_dsts([(a.view("f2/kernel:0", "g"), a.view("f2/bias:0", "g"), 64, 32),
+                                         (a.view("f3/kernel:0", "g"), a.view("f3/bias:0", "g"), 32, self.cout3)], self.device),
+        }
+        self.step = getattr(self, "step", 0)
+        self._repack_train()
+        return self._tb
+
+    def _repack_train(self):
+        b, a = self._tb, self.arena
+        b["plan"].run(a.w)
+        b["bias2"][:32].copy_(a.view("f2/bias:0"))
+        b["bias3"][: self.cout3].copy_(a.view("f3/bias:0"))
+
+    def forward_backward(self, lr: torch.Tensor, hr_packed: torch.Tensor, numel_total: float | None = None):
+        n, H, W, _ = lr.shape
+        assert W <= MAX_PANEL_W
+        b, a = self._enable_training(n, H, W), self.arena
+        V, ix = b["plan"].views, b["idx"]
+        ops.conv_first_tc(lr, V[ix["f1"]], a.view("f1/bias:0"), 5, "SAME", "tanh", out=b["a1"])
+        ops.conv_tc(b["a1"], V[ix["f2"]], b["bias2"], 3, "tanh", out=b["a2"])
+        ops.conv_tc_last(b["a2"], V[ix["f3"]], b["bias3"], 3, self.cout3, None, out=b["sr"])
+        b["loss"].zero_()
+        ops.mse_fwd_bwd(b["sr"], hr_packed, b["loss"], b["dsr"], numel_total)
+        # backward: f3 (linear) -> f2 (tanh) -> f1 (tanh)
+        st = b["stride"]
+        ops.nhwc_to_fpa_pad(b["dsr"], 64, out=b["dP"])
+        ops.conv_wgrad_tc(b["a2"], b["dP"], None, None, workspace=b["ws"][st:2 * st])
+        d2 = ops.conv_tc(b["dP"], V[ix["d3"]], None, 3, None, out=b["d"][0], mask_src=b["a2"], mask_kind="tanh")
+        ops.conv_wgrad_tc(b["a1"], d2, None, None, workspace=b["ws"][0:st])
+        d1 = ops.conv_tc(d2, V[ix["d2"]], None, 3, None, out=b["d"][1], mask_src=b["a1"], mask_kind="tanh")
+        ops.wgrad_reduce_many(b["ws"], st, 2, n, H, W, b["dsts"])
+        a.view("f1/kernel:0", "g").zero_()
+        a.view("f1/bias:0", "g").zero_()
+        ops.conv_first_wgrad(lr, d1, 5, a.view("f1/kernel:0", "g"), a.view("f1/bias:0", "g"))
+        return b
+
+    def train_step(self, lr: torch.Tensor, hr_packed: torch.Tensor, learning_rate: float, group=None):
+        """One Adam step (reference `session.run(model['optimizer'], feed_dict={learning_rate: ...})`); returns the pre-update loss."""
+        world = 1
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            world = torch.distributed.get_world_size(group)
+        b = self.forward_backward(lr, hr_packed, float(hr_packed.numel()) * world)
+        a = self.arena
+        if world > 1:
+            torch.distributed.all_reduce(a.g, group=group)
+        self.step += 1
+        ops.adam_step(a.w, a.g, a.m, a.v, learning_rate, self.step)
+        self._repack_train()
+        self.repack()
+        return b["loss"]
+
     def _get_bufs(self, n, H, W):
         key = (n, H, W)
         if key not in self._bufs:
@@ -108,11 +188,18 @@ class _EspcnGraph:
     def execute(self, keys, feeds):
         net = self.net
         out = {}
-        if "optimizer" in keys:
-            raise NotImplementedError("ESPCN training is not part of this round's hot path (SURVEY 8a: inference config)")
         x = feeds[self.lr_ph]
         lr = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
         lr = lr.to(net.device, torch.float32).contiguous()
+        if "optimizer" in keys:
+            hr = torch.from_numpy(np.ascontiguousarray(feeds[self.hr_ph], dtype=np.float32)).to(net.device)
+            rate = [v for k, v in feeds.items() if isinstance(k, Placeholder) and k.name == "learning_rate"]
+            step_before = getattr(net, "step", 0)
+            loss = net.train_step(lr, hr, float(rate[0]) if rate else 0.01)
+            out.update(optimizer=None, loss=float(loss), step=step_before)
+            if keys & {"sr_result", "sr_results"}:
+                out["sr_result"] = out["sr_results"] = net._tb["sr"].cpu().numpy()
+            return out
         if keys & {"sr_result", "sr_results", "loss"}:
             packed = net.forward(lr, shuffle=False)
             out["sr_result"] = out["sr_results"] = packed.cpu().numpy()
@@ -123,7 +210,7 @@ class _EspcnGraph:
                 out["loss"] = float(acc)
         if "hr_images" in keys:
             out["hr_images"] = net.forward(lr, shuffle=True).cpu().numpy()
-        out["step"] = 0
+        out["step"] = getattr(net, "step", 0)
         out["scaling_factor"] = net.r
         return out
 

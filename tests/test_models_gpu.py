@@ -177,3 +177,36 @@ def test_enet_generator_forward(srk_ops):
     assert res_scale > 0.05, "test weights too small to exercise the generator"
     assert np.abs(got - ref).max() <= TOL_BF16 * max(1.0, res_scale)
     assert abs(_psnr(got, bq + 0.3) - _psnr(ref, bq + 0.3)) <= 0.02
+
+
+def test_espcn_train_step_matches_oracle(srk_ops):
+    """ESPCN training (MSE in packed space, tanh layers, Adam): loss, every gradient and a 5-step trajectory vs the oracle."""
+    from ml_super_resolution_b200.espcn.model_espcn import EspcnNet
+    from oracle.ops import adam_tf
+    params = _trained_like(OM.espcn_init(seed=12, scaling_factor=3, channels=3), scale=4.0)
+    net = EspcnNet(params, 3, 3)
+    lr = OM.synthetic_images(51, 16, 17, 17, 3)
+    hr = O.pixel_unshuffle(OM.synthetic_images(52, 16, 51, 51, 3), 3)
+    lrt, hrt = torch.from_numpy(lr).cuda(), torch.from_numpy(np.ascontiguousarray(hr)).cuda()
+    b = net.forward_backward(lrt, hrt)
+    ref_loss, ref_g, _ = OM.espcn_loss_and_grads(params, lr, hr)
+    assert abs(float(b["loss"]) - ref_loss) <= 2e-3 * ref_loss
+    got = net.arena.to_numpy("g")
+    for k, g in ref_g.items():
+        rel = np.linalg.norm(got[k] - g) / (np.linalg.norm(g) + 1e-30)
+        assert rel <= 3e-2, f"{k}: relative gradient error {rel:.4f}"
+    p64 = {k: v.astype(np.float64) for k, v in params.items()}
+    m = {k: np.zeros_like(v) for k, v in p64.items()}
+    v_ = {k: np.zeros_like(v) for k, v in p64.items()}
+    ours, theirs = [], []
+    for t in range(1, 6):
+        ours.append(float(net.train_step(lrt, hrt, 1e-3)))
+        l, g, _ = OM.espcn_loss_and_grads(p64, lr, hr)
+        theirs.append(l)
+        for k in p64:
+            p64[k], m[k], v_[k] = adam_tf(p64[k], g[k], m[k], v_[k], t, 1e-3, dtype=np.float64)
+    assert np.allclose(ours, theirs, rtol=2e-2), (ours, theirs)
+    assert ours[-1] < ours[0]
+    # inference weights were re-packed too: the forward path sees the trained parameters
+    packed = net.forward(lrt, shuffle=False).cpu().numpy()
+    assert np.abs(packed - OM.espcn_forward(p64, lr)).max() <= TOL_BF16
