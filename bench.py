@@ -181,11 +181,17 @@ def espcn_workload(args, rank, world):
         "espcn_f2_conv_tc(3x3,64->32,tanh)": (k_f2, lr_px * (128 + 64)),
         "espcn_f3_conv_tc_last(3x3,32->9,shuffle)": (k_f3, lr_px * (64 + 4 * C * SCALE * SCALE)),
     }
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of these three
+    # kernels at this exact shape (profiles/r1_ncu_espcn_kernels.txt): no wasted re-reads (traffic ~ algorithmic bytes)
+    ncu_traffic = {"espcn_f1_conv_first_tc(5x5,C->64,tanh)": 1.081e9, "espcn_f2_conv_tc(3x3,64->32,tanh)": 1.630e9,
+                   "espcn_f3_conv_tc_last(3x3,32->9,shuffle)": 0.834e9}
     dom = max(kernels, key=lambda k: kernels[k][0])
     pk = peaks()
     ach = kernels[dom][1] / kernels[dom][0] / 1e6  # GB/s
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s", "frac": round(ach / pk["hbm"], 4),
-                "traffic": None, "peak_source": pk["src"], "kernel_ms": {k: round(v[0], 4) for k, v in kernels.items()},
+                "traffic": ncu_traffic[dom] if FRAMES_PER_STEP == 4 else None, "algorithmic_bytes": kernels[dom][1], "peak_source": pk["src"],
+                "kernel_ms": {k: round(v[0], 4) for k, v in kernels.items()},
+                "kernel_GBps": {k: round(v[1] / v[0] / 1e6, 1) for k, v in kernels.items()},
                 "step_algorithmic_GB": round(sum(v[1] for v in kernels.values()) / 1e9, 3)}
 
     # ---- end to end through the public call with HOST buffers: every step copies its pinned input host->device and its
