@@ -65,7 +65,7 @@ struct alignas(64) ConvTcParams {
   int dbg;  // development switches (env SRK_DBG): bit0 skip lane exchange+shuffles, bit1 skip staging store, bit2 skip tmem loads
 };
 
-template <int CIN, int NP, int KS>
+template <int CIN, int NP, int KS, int EPI = EPI_FPA>
 struct ConvTcCfg {
   static constexpr int kRowBytes = CIN * 2;
   static constexpr int kChunkBytes = kChunkRows * kRowBytes;
@@ -79,7 +79,12 @@ struct ConvTcCfg {
   static constexpr int kWTapBytes = NP * kRowBytes;
   static constexpr int kWBytes = ((kTaps * kWTapBytes + 1023) / 1024) * 1024;
   static constexpr int kStageBufs = (NP == 64 && CIN == 64 && KS == 3) ? 1 : 2;  // the widest config spends its smem on the ring
-  static constexpr int kStageBytes = kStageBufs * 128 * NP * 2;                  // output staging (EPI_FPA)
+  // EPI_NHWC with NP <= 32: per (tile set, lane quadrant) a double-buffered 32-pixel x NP fp32 transpose tile (row pitch
+  // NP+1 words: conflict-free) plus 32 output base indices, so that the fp32 NHWC stores go out coalesced
+  static constexpr bool kCoopStore = (EPI == EPI_NHWC) && (NP <= 32);
+  static constexpr int kCoopBufBytes = 32 * (NP + 1) * 4 + 32 * 8;
+  static constexpr int kStageBytes = (EPI == EPI_NHWC) ? (kCoopStore ? 8 * 2 * kCoopBufBytes : 0)
+                                                       : kStageBufs * 128 * NP * 2;  // output staging (EPI_FPA)
   static constexpr int kGroups = 4;                 // epilogue column groups (4 warps each): 16 epilogue warps
   static constexpr int kColPass = NP / kGroups;     // accumulator columns per epilogue thread (16 / 8 / 4)
   static constexpr int kEpiThreads = 128 * kGroups;
@@ -240,6 +245,17 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
   const int act = p.act;
   const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
   uint32_t xpar = 0;  // byte offset of the exchange parity in use
+  // cooperative NHWC store (EPI_NHWC, NP <= 32): the two column-half warps of a (set, quadrant) pair transpose
+  // their 32 pixels x NP channels through shared memory and then write each output row segment with
+  // consecutive threads on consecutive floats (a lane-per-pixel scatter touches 3x the sectors)
+  constexpr bool kCoop = (EPI == EPI_NHWC) && (NP <= 32);
+  constexpr int kTP = NP + 1;
+  constexpr int kCoopBuf = 32 * kTP * 4 + 32 * 8;
+  const uint32_t coop0 = e.stage_addr + (set * 4 + quad) * 2 * kCoopBuf;
+  const int sr = (EPI == EPI_NHWC) ? p.shuffle_r : 1;
+  const int rC = (EPI == EPI_NHWC) ? p.cout / sr : 1;             // floats per pixel per output row
+  const uint32_t div_m = 65536u / uint32_t(rC) + 1u;              // el / rC == (el * div_m) >> 16 for el < 1024
+  const int64_t orow = (EPI == EPI_NHWC) ? int64_t(p.FW) * rC : 0;  // floats per output row
 
   for (int t = t_begin + set; t < t_end; t += 2) {
     const int it = t - t_begin, acc = it % ACC, accgen = it / ACC;
@@ -407,7 +423,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
           for (int c = 0; c < CP / 2; ++c) pk[c] = 0u;  // pad rows/columns stay exactly zero
         }
       } else {
-        // fp32 NHWC scatter: residual add, panel crop, depth_to_space
+        // fp32 NHWC: residual add, panel crop, depth_to_space
         if (act == SRK_ACT_RELU) {
 #pragma unroll
           for (int c = 0; c < CP; ++c) v[c] = fmaxf(v[c], 0.f);
@@ -421,10 +437,15 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
           fy = pe.y0 + y;
           fx = pe.x0 + x;
         }
-        if (st) {
-          const int r = p.shuffle_r, C = p.cout / (r * r);
-          const int64_t OW = int64_t(p.FW) * r;
-          const int64_t base = ((int64_t(fn) * p.FH * r + int64_t(fy) * r) * OW + int64_t(fx) * r) * C;
+        const int64_t base = (int64_t(fn) * p.FH + fy) * sr * orow + int64_t(fx) * rC;
+        if constexpr (kCoop) {
+          const uint32_t tb = coop0 + ((it >> 1) & 1) * kCoopBuf;
+#pragma unroll
+          for (int c = 0; c < CP; ++c)
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(tb + (lane * kTP + col0 + c) * 4), "f"(v[c]) : "memory");
+          if (half == 0 && pass == 0)
+            asm volatile("st.shared.b64 [%0], %1;" ::"r"(tb + 32 * kTP * 4 + lane * 8), "l"(st ? base : int64_t(-1)) : "memory");
+        } else if (st) {
 #pragma unroll
           for (int c = 0; c < CP; ++c) {
             const int off = e.s_tab[col0 + c];
@@ -439,6 +460,28 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
       }
     }  // pass
 
+    if constexpr (kCoop) {
+      const uint32_t tb = coop0 + ((it >> 1) & 1) * kCoopBuf;
+      named_bar_sync(5 + set * 4 + quad, 64);  // both column halves of these 32 pixels are in the tile
+      const int n_el = 32 * rC;
+      for (int dy = 0; dy < sr; ++dy) {
+        for (int el = half * 32 + lane; el < n_el; el += 64) {
+          const uint32_t pi = (uint32_t(el) * div_m) >> 16;
+          const int rem = el - int(pi) * rC;
+          int64_t pbase;
+          asm volatile("ld.shared.b64 %0, [%1];" : "=l"(pbase) : "r"(tb + 32 * kTP * 4 + pi * 8) : "memory");
+          if (pbase >= 0) {
+            float o;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o) : "r"(tb + (pi * kTP + dy * rC + rem) * 4) : "memory");
+            const int64_t idx = pbase + dy * orow + rem;
+            if (p.addend) o += __ldg(p.addend + idx);
+            p.out[idx] = o;
+          }
+        }
+      }
+      // no second barrier: the next tile of this set writes the other buffer, and the barrier of that tile orders
+      // these reads before the writes of the tile after it
+    }
     if constexpr (EPI == EPI_FPA) {
       // staging buffer free? (the store that last used this buffer has finished reading it)
       const int sb = (e.stage_bufs == 2) ? (it & 1) : 0, sgen = (e.stage_bufs == 2) ? (it >> 1) : it;
@@ -460,8 +503,8 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
 }
 
 template <int CIN, int NP, int KS, int EPI>
-__global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS>::kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
-  using L = ConvTcCfg<CIN, NP, KS>;
+__global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS, EPI>::kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
+  using L = ConvTcCfg<CIN, NP, KS, EPI>;
   constexpr int kRingSlots = L::kRingSlots;
   constexpr uint32_t kLayout = (CIN == 64) ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW64;
   constexpr uint32_t kSbo = 8 * L::kRowBytes;
@@ -880,7 +923,7 @@ static int launch_conv_gather(srk_ctx* h, ConvGatherParams& gp, const void* w_pa
 // --------------------------------------------------------------------------------------- host side
 template <int CIN, int NP, int KS, int EPI>
 static int launch_conv_tc(srk_ctx* h, ConvTcParams& p, const void* x, const void* w_packed, void* y_fpa, cudaStream_t stream) {
-  using L = ConvTcCfg<CIN, NP, KS>;
+  using L = ConvTcCfg<CIN, NP, KS, EPI>;
   static bool attr_set = false;
   SRK_REQUIRE(L::kTotal <= h->smem_optin, "conv_tc: needs %d B smem, device allows %d", L::kTotal, h->smem_optin);
   if (!attr_set) {
