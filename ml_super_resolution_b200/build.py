@@ -31,5 +31,13 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+def build_trace_library() -> str:
+    """Development build with the in-kernel timeline enabled (tools/trace_conv.py); never loaded by the product."""
+    out = os.path.join(PKG_DIR, "libsrk_trace.so")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    subprocess.run([nvcc, *NVCC_FLAGS, "-DSRK_TRACE", "-o", out, *[os.path.join(CSRC, s) for s in SOURCES]], check=True)
+    return out
+
+
 if __name__ == "__main__":
     print(build_library(force=True, verbose=True))

@@ -46,11 +46,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, P;\n\t}\n"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
+      : "r"(bar), "r"(parity), "r"(0x989680u)  // suspend-time hint: a waiting warp sleeps in hardware instead of
+      : "memory");                              // re-polling (spinning epilogue warps starved the MMA issuers of issue slots)
   return ok != 0;
 }
 // Bounded wait: traps (kernel error, not a hang) if the barrier never flips.

@@ -8,7 +8,7 @@ net = EspcnNet(None, 3, 1)
 F = 4
 lr = torch.rand((F, 1080, 1920, 1), device="cuda", generator=g) * 2 - 1
 out = torch.empty((F, 3240, 5760, 1), device="cuda")
-Ht, Wt, tiles = plan_tiles(F, 1080, 1920, 4)
+Ht, Wt, tiles = plan_tiles(F, 1080, 1920, 4, max_w=int(os.environ.get('PANEL_W', '254')))
 panels = ops.make_panels([t.as_tuple() for t in tiles])
 t1, t2 = net._get_bufs(len(tiles), Ht, Wt)
 a = net.arena
