@@ -45,11 +45,11 @@ else:
 for _ in range(3):
     run()
 torch.cuda.synchronize()
-buf = np.zeros(16 * 256, dtype=np.uint64)
+buf = np.zeros(24 * 256, dtype=np.uint64)
 raw = C.CDLL(os.environ["SRK_LIB_OVERRIDE"])
 rc = raw.srk_debug_trace_read(buf.ctypes.data_as(C.c_void_p))
 assert rc == 0, rc
-T = buf.reshape(16, 256).astype(np.int64)
+T = buf.reshape(24, 256).astype(np.int64)
 t0 = T[3, 0]
 names = ["load-issued(chunk)", "mma:data-ready", "mma:acc-free", "mma:committed", "epi:acc-full", "epi:tmem-read", "epi:passes-done",
          "epi:tile-done", "store:staged", "store:freed"]
@@ -62,8 +62,7 @@ d = lambda a: float(np.mean(a))  # noqa: E731
 r = np.arange(lo, hi)
 print("\naverages over these tiles (cycles):")
 print(f"  tile period (commit -> commit)           {d(T[3, r] - T[3, r - 1]):8.0f}")
-print(f"  mma: commit -> ring slots handed back    {d(T[15, r] - T[3, r]):8.0f}")
-print(f"  mma: handed back -> next data ready      {d(T[1, r + 2] - T[15, r]):8.0f}   (same issuer, its next tile)")
+print(f"  mma: commit -> next tile seen ready      {d(T[1, r + 2] - T[3, r]):8.0f}   (same issuer, its next tile)")
 print(f"  mma: wait for a free accumulator         {d(T[2, r] - T[1, r]):8.0f}")
 print(f"  mma: issue (acc-free -> commit)          {d(T[3, r] - T[2, r]):8.0f}")
 print(f"  commit -> epilogue sees acc full         {d(T[4, r] - T[3, r]):8.0f}")
@@ -80,6 +79,11 @@ if T[10, lo]:
 if T[8, lo]:
     print(f"  store: tile done -> staged seen          {d(T[8, r] - T[7, r]):8.0f}")
     print(f"  store: staged -> freed                   {d(T[9, r] - T[8, r]):8.0f}")
+for a_, b_ in ((8, 32), (32, 64), (64, 128), (128, 192), (192, 250)):
+    print(f"  tile period over tiles {a_:3d}..{b_:3d}: {(T[3, b_] - T[3, a_]) / (b_ - a_):7.0f} cycles")
+cr = np.arange(60, 200)
+print(f"  producer per chunk: slot-free wait {d(T[17, cr] - T[16, cr]):6.0f} | ready arrives {d(T[0, cr] - T[17, cr]):6.0f} | expect_tx {d(T[18, cr] - T[0, cr]):6.0f} | "
+      f"TMA issue {d(T[19, cr] - T[18, cr]):6.0f} | loop {d(T[16, cr + 1] - T[19, cr]):6.0f}")
 ch = T[0]
 n_ch = int((ch > 0).sum())
 print(f"  chunks loaded by CTA 0: {n_ch}; mean issue period over chunks 40..120: {d(np.diff(ch[40:120])):.0f} cycles")
