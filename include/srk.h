@@ -185,9 +185,11 @@ int srk_fpa_upsample2_bwd(srk_handle_t h, const void* dy_fpa, int n_img, int H, 
  * and dsr = 2(sr-hd)/numel_total.  numel_total lets a data-parallel rank scale by the GLOBAL element count. */
 int srk_mse_fwd_bwd(srk_handle_t h, const float* sr, const float* hd, size_t numel, double numel_total,
                     float* loss_accum, float* dsr, srk_stream_t stream);
-/* SRCNN loss (srcnn/srcnn.py:142-144): mean over rows of ||reshape(sr-hd,[rows,cols])||_2, and its gradient. */
+/* SRCNN loss (srcnn/srcnn.py:142-144): mean over rows of ||reshape(sr-hd,[rows,cols])||_2, and its gradient.
+ * sr_act = SRK_ACT_TANH: sr is the tanh output of the reconstruction layer (srcnn/srcnn.py:128) and dsr receives the
+ * gradient w.r.t. its pre-activation, dloss/dsr * (1 - sr^2); SRK_ACT_NONE: plain dloss/dsr. */
 int srk_l2norm_rows_mean_fwd_bwd(srk_handle_t h, const float* sr, const float* hd, int rows, int cols,
-                                 float* loss_accum, float* dsr, srk_stream_t stream);
+                                 float* loss_accum, float* dsr, int sr_act, srk_stream_t stream);
 /* tf.train.AdamOptimizer step over a flat fp32 arena (vdsr/vdsr/model_vdsr.py:145-148; A.8 epsilon-hat
  * form); t = 1-based step.  decay_mask (optional, n floats): g += weight_decay * decay_mask[i] * w[i]
  * (the l2_regularizer term of model_vdsr.py:34,125: kernels 1, biases 0). */

@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(256) mse_fwd_bwd_kernel(const float* __restric
 
 // one CTA per row of `cols` consecutive elements
 __global__ void __launch_bounds__(256) l2norm_rows_kernel(const float* __restrict__ sr, const float* __restrict__ hd, int rows, int cols,
-                                                          float* __restrict__ loss, float* __restrict__ dsr) {
+                                                          float* __restrict__ loss, float* __restrict__ dsr, int sr_act) {
   const int r = blockIdx.x;
   const float* a = sr + int64_t(r) * cols;
   const float* b = hd + int64_t(r) * cols;
@@ -305,7 +305,11 @@ __global__ void __launch_bounds__(256) l2norm_rows_kernel(const float* __restric
   __syncthreads();
   if (dsr) {
     const float inv = s_nrm > 0.f ? 1.f / (s_nrm * float(rows)) : 0.f;
-    for (int i = threadIdx.x; i < cols; i += blockDim.x) dsr[int64_t(r) * cols + i] = (a[i] - b[i]) * inv;
+    for (int i = threadIdx.x; i < cols; i += blockDim.x) {
+      float g = (a[i] - b[i]) * inv;
+      if (sr_act == SRK_ACT_TANH) g *= 1.f - a[i] * a[i];  // sr = tanh(pre): hand back dloss/dpre
+      dsr[int64_t(r) * cols + i] = g;
+    }
   }
 }
 
@@ -424,9 +428,10 @@ extern "C" int srk_mse_fwd_bwd(srk_handle_t h, const float* sr, const float* hd,
 }
 
 extern "C" int srk_l2norm_rows_mean_fwd_bwd(srk_handle_t h, const float* sr, const float* hd, int rows, int cols, float* loss_accum,
-                                            float* dsr, srk_stream_t stream) {
+                                            float* dsr, int sr_act, srk_stream_t stream) {
   SRK_REQUIRE(h && sr && hd && loss_accum && rows > 0 && cols > 0, "srk_l2norm_rows_mean_fwd_bwd: bad argument");
-  l2norm_rows_kernel<<<rows, 256, 0, as_stream(stream)>>>(sr, hd, rows, cols, loss_accum, dsr);
+  SRK_REQUIRE(sr_act == SRK_ACT_NONE || sr_act == SRK_ACT_TANH, "srk_l2norm_rows_mean_fwd_bwd: sr_act must be NONE or TANH");
+  l2norm_rows_kernel<<<rows, 256, 0, as_stream(stream)>>>(sr, hd, rows, cols, loss_accum, dsr, sr_act);
   SRK_LAUNCH_CHECK();
   return 0;
 }

@@ -30,16 +30,16 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int k, int cin,
 }
 
 // First-layer forms (srk_conv_first_tc): out[blk][n < 64][kk < 64] with GEMM-K index kg = blk*64 + kk.
-//   SRK_PACK_FIRST          : kg = (u*k + v)*cin + ci, n = co        -> w[u][v][ci][co]            (cout == 64)
-//   SRK_PACK_FIRST_ROT180T  : kg = (u*k + v)*cout + co, n = ci       -> w[k-1-u][k-1-v][ci][co]    (cin == 64): the last layer's
+//   SRK_PACK_FIRST          : kg = (u*k + v)*cin + ci, n = co        -> w[u][v][ci][co]            (cout <= 64, zero beyond)
+//   SRK_PACK_FIRST_ROT180T  : kg = (u*k + v)*cout + co, n = ci       -> w[k-1-u][k-1-v][ci][co]    (cin <= 64): the last layer's
 //                             data gradient as a first-layer style conv over dY[..., cout]
 __device__ __forceinline__ float first_form_value(const float* __restrict__ w, int k, int cin, int cout, int mode, int n, int kg) {
   if (mode == SRK_PACK_FIRST) {
-    if (kg >= k * k * cin) return 0.f;
+    if (kg >= k * k * cin || n >= cout) return 0.f;
     const int ci = kg % cin, tap = kg / cin;
     return w[(tap * cin + ci) * cout + n];
   }
-  if (kg >= k * k * cout) return 0.f;
+  if (kg >= k * k * cout || n >= cin) return 0.f;
   const int co = kg % cout, tap = kg / cout;
   const int u = k - 1 - tap / k, v = k - 1 - tap % k;
   return w[((u * k + v) * cin + n) * cout + co];

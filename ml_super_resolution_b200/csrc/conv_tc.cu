@@ -1109,6 +1109,7 @@ extern "C" int srk_conv_tc_last(srk_handle_t h, const void* x_fpa, int cin_p, co
   SRK_CASE(32, 16, 3)
   SRK_CASE(32, 32, 3)
   SRK_CASE(32, 16, 5)
+  SRK_CASE(64, 16, 5)
   SRK_CASE(32, 64, 3)
   SRK_CASE(64, 32, 3)
 #undef SRK_CASE

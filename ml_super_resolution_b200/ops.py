@@ -348,10 +348,11 @@ def mse_fwd_bwd(sr: torch.Tensor, hd: torch.Tensor, loss_accum: torch.Tensor, ds
 
 
 def l2norm_rows_mean_fwd_bwd(sr: torch.Tensor, hd: torch.Tensor, cols: int, loss_accum: torch.Tensor,
-                             dsr: torch.Tensor | None = None) -> None:
+                             dsr: torch.Tensor | None = None, sr_act=None) -> None:
+    """sr_act='tanh': sr is a tanh output and dsr receives the gradient w.r.t. its pre-activation."""
     rows = sr.numel() // cols
     check(_ffi.lib().srk_l2norm_rows_mean_fwd_bwd(handle(), _ptr(_f32(sr)), _ptr(_f32(hd)), rows, cols, _ptr(loss_accum), _ptr(dsr),
-                                                  _stream()), "srk_l2norm_rows_mean_fwd_bwd")
+                                                  ACT[sr_act], _stream()), "srk_l2norm_rows_mean_fwd_bwd")
 
 
 def adam_step(w, g, m, v, lr: float, t: int, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, decay_mask=None) -> None:

@@ -12,6 +12,16 @@ out of scope: `hi_images` is fed like any other placehol
   non_linear_mapping   1x1 VALID 64->32 ReLU        srk_conv_tc (k=1, N=32)         reference :111-119
   reconstruction       5x5 VALID 32->C tanh         srk_conv_tc_last (k=5, crop)    reference :122-130
   loss                 mean_rows ||sr - hi||_2      srk_l2norm_rows_mean_fwd_bwd    reference :142-144
+  trainer              Adam(1e-3, .5, .9)           backward below + srk_adam_step  reference :155-157
+
+Backward (what `minimize` adds, reference :155-157).  A VALID k x k layer is the SAME layer over the larger of its two
+geometries with the smaller tensor embedded behind a zero border of k/2 pixels, so every gradient runs on the 3x3 /
+64-channel tensor-core kernels the other models use:
+  wgrad of a k x k kernel = ceil(k/3)^2 calls of srk_conv_wgrad_tc, one per 3x3 block of taps, with the activation
+      pointer shifted by (a*Wp + b) rows (tap block centre (a, b)); the zero border of the embedded gradient
+      guarantees that no shifted read that matters wraps around an image row;
+  dgrad of the 5x5 reconstruction layer = srk_conv_first_tc over the embedded gradient frame with
+      SRK_PACK_FIRST_ROT180T weights (+ ReLU' mask); dgrad of the 1x1 layer = srk_conv_tc with SRK_PACK_DGRAD weights.
 """
 from __future__ import annotations
 
@@ -92,6 +102,130 @@ class SrcnnNet:
         return ops.conv_tc_last(t2, self.plan.views[self._i3], self.bias3, 5, C, "tanh", panels=self._panels[key],
                                 frame_shape=(n, h2 - 4, w2 - 4))
 
+    # ------------------------------------------------------------------------------------------ training
+    def _enable_training(self, n, S):
+        key = (n, S)
+        if getattr(self, "_tb", None) is not None and self._tb["key"] == key:
+            return self._tb
+        a, dev, C = self.arena, self.device, self.C
+        a.enable_training()
+        H1, bb = S - 8, S - 12
+        plan = ops.PackPlan(dev)
+        ix = {
+            "f1": plan.add(a.offsets["patch_extraction/weights:0"], 9, C, 64, ops.PACK_FIRST),
+            "f2": plan.add(a.offsets["non_linear_mapping/weights:0"], 1, 64, 32, ops.PACK_FWD, 64, 64),
+            "f3": plan.add(a.offsets["reconstruction/weights:0"], 5, 32, C, ops.PACK_FWD, 16, 64),
+            "d3": plan.add(a.offsets["reconstruction/weights:0"], 5, 32, C, ops.PACK_FIRST_ROT180T),
+            "d2": plan.add(a.offsets["non_linear_mapping/weights:0"], 1, 64, 32, ops.PACK_DGRAD, 64, 64),
+        }
+        plan.finalize()
+        # geometry G0 = S x S (input), G1 = H1 x H1 (both hidden layers)
+        Wp0 = S + 1
+        margin = ((4 * Wp0 + 8 + 7) // 8) * 8  # rows the shifted activation views may reach before / behind the buffer
+        rows0 = ops.fpa_rows(n, S, S)
+        lo_store = torch.zeros((margin + rows0 + margin, 64), dtype=torch.bfloat16, device=dev)
+        Wp1 = H1 + 1
+        margin1 = ((3 * Wp1 + 8 + 7) // 8) * 8
+        rows1 = ops.fpa_rows(n, H1, H1)
+        t2_store = torch.zeros((margin1 + rows1 + margin1, 64), dtype=torch.bfloat16, device=dev)
+        st0 = (ops.wgrad_workspace_bytes(n, S, S) + 1023) // 1024 * 1024
+        st1 = (ops.wgrad_workspace_bytes(n, H1, H1) + 1023) // 1024 * 1024
+        tmp1 = torch.zeros((9, 9, C, 64), dtype=torch.float32, device=dev)    # [block][tap][ci][co] of the 9x9 kernel
+        tmp3 = torch.zeros((4, 9, 32, C), dtype=torch.float32, device=dev)    # [block][tap][ci][co] of the 5x5 kernel (6x6 taps)
+        tmp2 = torch.zeros((9, 64, 32), dtype=torch.float32, device=dev)      # 1x1 kernel = centre tap
+        dummy = torch.zeros(64, dtype=torch.float32, device=dev)
+        g = lambda name: a.view(name, "g")  # noqa: E731
+        dsts0 = [(tmp1[blk], g("patch_extraction/biases:0") if blk == 4 else dummy, C, 64) for blk in range(9)]
+        dsts1 = [(tmp3[blk], g("reconstruction/biases:0") if blk == 0 else dummy, 32, C) for blk in range(4)]
+        dsts1.append((tmp2, g("non_linear_mapping/biases:0"), 64, 32))
+        self._tb = {
+            "key": key, "plan": plan, "idx": ix, "st0": st0, "st1": st1, "margin": margin, "margin1": margin1,
+            "lo_store": lo_store, "loF": ops.Fpa(lo_store[margin:margin + rows0], n, S, S),
+            "t1": ops.fpa_empty(n, H1, H1, 64, dev),
+            "t2_store": t2_store, "t2": ops.Fpa(t2_store[margin1:margin1 + rows1], n, H1, H1),
+            "sr": torch.empty((n, bb, bb, C), dtype=torch.float32, device=dev),
+            "dpre": torch.empty((n, bb, bb, C), dtype=torch.float32, device=dev),
+            "dpre_e": torch.zeros((n, H1, H1, C), dtype=torch.float32, device=dev),   # zero border of 2 px stays zero
+            "dP3": ops.fpa_empty(n, H1, H1, 64, dev),
+            "d2": ops.fpa_empty(n, H1, H1, 64, dev), "d1": ops.fpa_empty(n, H1, H1, 64, dev),
+            "d1e": ops.Fpa(torch.zeros((rows0, 64), dtype=torch.bfloat16, device=dev), n, S, S),   # zero border of 4 px stays zero
+            "loss": torch.zeros(1, dtype=torch.float32, device=dev),
+            "bias2": torch.zeros(64, dtype=torch.float32, device=dev),
+            "ws0": torch.empty(st0 * 9, dtype=torch.uint8, device=dev), "ws1": torch.empty(st1 * 5, dtype=torch.uint8, device=dev),
+            "tmp1": tmp1, "tmp2": tmp2, "tmp3": tmp3, "dummy": dummy,   # the dsts tables hold raw pointers: keep the targets alive
+            "dsts0": ops.make_wgrad_dsts(dsts0, dev), "dsts1": ops.make_wgrad_dsts(dsts1, dev),
+        }
+        self.step = getattr(self, "step", 0)
+        self._repack_train()
+        return self._tb
+
+    def _repack_train(self):
+        b, a = self._tb, self.arena
+        b["plan"].run(a.w)
+        b["bias2"][:32].copy_(a.view("non_linear_mapping/biases:0"))
+
+    @staticmethod
+    def _shifted(store: torch.Tensor, margin: int, rows: int, shift: int, like: "ops.Fpa") -> "ops.Fpa":
+        return ops.Fpa(store[margin + shift:margin + shift + rows], like.n_img, like.H, like.W)
+
+    def forward_backward(self, hi: torch.Tensor):
+        """hi fp32 [N,S,S,C] in [-1,1] -> fills the gradient arena; returns the buffer dict (loss, sr, lo)."""
+        n, S, S2, C = hi.shape
+        assert S == S2 and C == self.C and S + 1 <= 255
+        b, a = self._enable_training(n, S), self.arena
+        V, ix = b["plan"].views, b["idx"]
+        H1, bb = S - 8, S - 12
+        lo = self.degrade(hi)
+        # ---- forward (64 channels wide: the padded halves of W2 / bias2 are zero, so t2[..., 32:] == 0)
+        t1 = ops.conv_first_tc(lo, V[ix["f1"]], a.view("patch_extraction/biases:0"), 9, "VALID", "relu", out=b["t1"])
+        t2 = ops.conv_tc(t1, V[ix["f2"]], b["bias2"], 1, "relu", out=b["t2"])
+        pk = (n, H1)
+        if pk not in self._panels:
+            self._panels[pk] = ops.make_panels([(i, -2, -2, 2, H1 - 2, 2, H1 - 2) for i in range(n)], self.device)
+        ops.conv_tc_last(t2, V[ix["f3"]], self.bias3, 5, C, "tanh", panels=self._panels[pk], frame_shape=(n, bb, bb), out=b["sr"])
+        side = (S - bb) // 2
+        hic = hi[:, side:side + bb, side:side + bb, :].contiguous()
+        b["loss"].zero_()
+        ops.l2norm_rows_mean_fwd_bwd(b["sr"], hic, bb * bb, b["loss"], b["dpre"], sr_act="tanh")
+        # ---- backward: reconstruction (5x5) -> non_linear_mapping (1x1) -> patch_extraction (9x9)
+        b["dpre_e"][:, 2:2 + bb, 2:2 + bb, :].copy_(b["dpre"])
+        ops.nhwc_to_fpa_pad(b["dpre_e"], 64, out=b["dP3"])
+        Wp1, rows1 = H1 + 1, b["t2"].data.shape[0]
+        for blk, (ca, cb) in enumerate(((-1, -1), (-1, 2), (2, -1), (2, 2))):   # 3x3 tap blocks centred at (ca, cb)
+            xs = self._shifted(b["t2_store"], b["margin1"], rows1, ca * Wp1 + cb, b["t2"])
+            ops.conv_wgrad_tc(xs, b["dP3"], None, None, workspace=b["ws1"][blk * b["st1"]:(blk + 1) * b["st1"]])
+        d2 = ops.conv_first_tc(b["dpre_e"], V[ix["d3"]], None, 5, "SAME", None, out=b["d2"], mask_src=t2, mask_kind="relu")
+        ops.conv_wgrad_tc(t1, d2, None, None, workspace=b["ws1"][4 * b["st1"]:5 * b["st1"]])
+        d1 = ops.conv_tc(d2, V[ix["d2"]], None, 1, None, out=b["d1"], mask_src=t1, mask_kind="relu")
+        ops.wgrad_reduce_many(b["ws1"], b["st1"], 5, n, H1, H1, b["dsts1"])
+        # d1 lives on G1; embed it 4 px inside G0 next to the input frame
+        src = d1.data[: n * (H1 + 1) * (H1 + 1)].view(n, H1 + 1, H1 + 1, 64)[:, 1:, :H1]
+        b["d1e"].data[: n * (S + 1) * (S + 1)].view(n, S + 1, S + 1, 64)[:, 5:5 + H1, 4:4 + H1].copy_(src)
+        ops.nhwc_to_fpa_pad(lo, 64, out=b["loF"])
+        Wp0, rows0 = S + 1, b["loF"].data.shape[0]
+        for blk in range(9):
+            ca, cb = 3 * (blk // 3) - 3, 3 * (blk % 3) - 3
+            xs = self._shifted(b["lo_store"], b["margin"], rows0, ca * Wp0 + cb, b["loF"])
+            ops.conv_wgrad_tc(xs, b["d1e"], None, None, workspace=b["ws0"][blk * b["st0"]:(blk + 1) * b["st0"]])
+        ops.wgrad_reduce_many(b["ws0"], b["st0"], 9, n, S, S, b["dsts0"])
+        # assemble the kernel gradients from their 3x3 tap blocks
+        g = lambda name: a.view(name, "g")  # noqa: E731
+        g("patch_extraction/weights:0").copy_(b["tmp1"].view(3, 3, 3, 3, C, 64).permute(0, 2, 1, 3, 4, 5).reshape(9, 9, C, 64))
+        g("reconstruction/weights:0").copy_(b["tmp3"].view(2, 2, 3, 3, 32, C).permute(0, 2, 1, 3, 4, 5).reshape(6, 6, 32, C)[:5, :5])
+        g("non_linear_mapping/weights:0").copy_(b["tmp2"][4].view(1, 1, 64, 32))
+        b["lo"] = lo
+        return b
+
+    def train_step(self, hi: torch.Tensor, learning_rate: float = 1e-3):
+        """One Adam(lr, beta1=0.5, beta2=0.9) step (reference :155-157); returns the pre-update loss tensor."""
+        b = self.forward_backward(hi)
+        a = self.arena
+        self.step += 1
+        ops.adam_step(a.w, a.g, a.m, a.v, learning_rate, self.step, beta1=0.5, beta2=0.9)
+        self._repack_train()
+        self.repack()
+        return b["loss"]
+
     def loss(self, sr: torch.Tensor, hi: torch.Tensor):
         """mean over rows of ||reshape(sr - crop(hi), [-1, bb^2])||_2 (reference :132-144); returns (loss, dloss/dsr)."""
         bb = sr.shape[1]
@@ -109,10 +243,19 @@ class _SrcnnGraph:
 
     def execute(self, keys, feeds):
         net = self.net
-        if "trainer" in keys:
-            raise NotImplementedError("SRCNN training is a 'next' row (DESIGN.md section 7); forward, degrade and loss run on the GPU path")
         x = feeds[self.hi_ph]
         hi = (x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))).to(net.device).contiguous()
+        if "trainer" in keys:
+            b = net.forward_backward(hi)
+            a = net.arena
+            net.step += 1
+            ops.adam_step(a.w, a.g, a.m, a.v, 1e-3, net.step, beta1=0.5, beta2=0.9)   # reference :155-156: fixed hyper-parameters
+            net._repack_train()
+            net.repack()
+            side = (hi.shape[1] - b["sr"].shape[1]) // 2
+            crop = lambda t: t[:, side:side + b["sr"].shape[1], side:side + b["sr"].shape[1], :]  # noqa: E731
+            return {"step": net.step, "trainer": None, "loss": float(b["loss"]), "sr_images": b["sr"].cpu().numpy(),
+                    "hd_images": crop(hi).cpu().numpy(), "sd_images": crop(b["lo"]).cpu().numpy()}
         lo = net.degrade(hi)
         sr = net.forward(lo)
         side = (hi.shape[1] - sr.shape[1]) // 2

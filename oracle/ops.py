@@ -47,7 +47,7 @@ def conv2d_nhwc_t(x: torch.Tensor, w_hwio: torch.Tensor, b: torch.Tensor | None,
         p = (0, 0)
     else:
         raise ValueError(padding)
-    y = F.conv2d(x.permute(0, 3, 1, 2), w_hwio.permute(3, 2, 0, 1), b, stride=1, padding=p)
+    y = F.conv2d(x.permute(0, 3, 1, 2).contiguous(), w_hwio.permute(3, 2, 0, 1).contiguous(), b, stride=1, padding=p)
     return _act(y.permute(0, 2, 3, 1), act)
 
 

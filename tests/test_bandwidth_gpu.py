@@ -60,6 +60,10 @@ def test_mse_l2norm_and_optimisers(srk_ops):
     ref_loss, ref_grad = O.l2norm_rows_mean(sr, hi, 21 * 21)
     assert abs(float(loss) - ref_loss) <= 1e-4 * ref_loss
     np.testing.assert_allclose(d2.cpu().numpy(), ref_grad, rtol=1e-4, atol=1e-8)
+    # same with the gradient taken through the reconstruction layer's tanh (sr = tanh(pre))
+    loss.zero_()
+    srk_ops.l2norm_rows_mean_fwd_bwd(_dev(sr), _dev(hi), 21 * 21, loss, d2, sr_act="tanh")
+    np.testing.assert_allclose(d2.cpu().numpy(), ref_grad * (1.0 - sr.astype(np.float64) ** 2), rtol=1e-4, atol=1e-8)
     # TF-Adam, 3 steps, and Momentum+clip
     n = 10007
     w, g = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32) * 0.1

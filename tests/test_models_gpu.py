@@ -210,3 +210,38 @@ def test_espcn_train_step_matches_oracle(srk_ops):
     # inference weights were re-packed too: the forward path sees the trained parameters
     packed = net.forward(lrt, shuffle=False).cpu().numpy()
     assert np.abs(packed - OM.espcn_forward(p64, lr)).max() <= TOL_BF16
+
+
+@pytest.mark.parametrize("channels,S,batch", [(1, 33, 16), (3, 45, 4)])
+def test_srcnn_train_step_matches_oracle(srk_ops, channels, S, batch):
+    """SRCNN training (9-1-5 VALID, row-L2-norm loss through tanh, Adam(1e-3,.5,.9)): loss, every gradient and a 4-step
+    trajectory vs the oracle (srcnn/srcnn.py:100-157)."""
+    from ml_super_resolution_b200.srcnn.srcnn import SrcnnNet
+    from oracle.ops import adam_tf
+    params = _trained_like(OM.srcnn_init(seed=6, channels=channels), scale=60.0)
+    net = SrcnnNet(params, channels)
+    hi = OM.synthetic_images(33, batch, S, S, channels)
+    hit = torch.from_numpy(hi).cuda()
+    lo = O.resize_bicubic_tf1(O.resize_bicubic_tf1(hi, S // 3, S // 3), S, S)
+    b = net.forward_backward(hit)
+    ref_loss, ref_g, ref_sr = OM.srcnn_loss_and_grads(params, lo, hi)
+    assert np.abs(b["sr"].cpu().numpy() - ref_sr).max() <= TOL_BF16
+    assert abs(float(b["loss"]) - ref_loss) <= 5e-3 * ref_loss
+    got = net.arena.to_numpy("g")
+    for k, g in ref_g.items():
+        rel = np.linalg.norm(got[k] - g) / (np.linalg.norm(g) + 1e-30)
+        assert rel <= 3e-2, f"{k}: relative gradient error {rel:.4f}"
+    p64 = {k: v.astype(np.float64) for k, v in params.items()}
+    m = {k: np.zeros_like(v) for k, v in p64.items()}
+    v_ = {k: np.zeros_like(v) for k, v in p64.items()}
+    ours, theirs = [], []
+    for t in range(1, 5):
+        ours.append(float(net.train_step(hit, 1e-3)))
+        l, g, _ = OM.srcnn_loss_and_grads(p64, lo, hi)
+        theirs.append(l)
+        for k in p64:
+            p64[k], m[k], v_[k] = adam_tf(p64[k], g[k], m[k], v_[k], t, 1e-3, beta1=0.5, beta2=0.9, dtype=np.float64)
+    assert np.allclose(ours, theirs, rtol=2e-2), (ours, theirs)
+    # the inference path sees the trained parameters
+    sr = net.forward(net.degrade(hit)).cpu().numpy()
+    assert np.abs(sr - OM.srcnn_forward(p64, lo)).max() <= TOL_BF16
