@@ -369,7 +369,64 @@ def vdsr_infer_cpu(threads: int, rows: int = 270):
     return rows * FRAME_4K[1] / dt / 1e6, dt
 
 
-WORKLOADS = {"espcn": espcn_workload, "vdsr_train": vdsr_train_workload, "vdsr_infer": vdsr_infer_workload}
+# ------------------------------------------------------------------------------------------------ SRCNN training (BASELINE configs[0])
+SRCNN_BATCH, SRCNN_PATCH = 128, 33
+
+
+def srcnn_train_workload(args, rank, world):
+    """SRCNN 9-1-5 forward+backward+Adam on synthetic 33x33 Y patches, batch 128 per GPU (replicas; the reference has no DP for it)."""
+    from ml_super_resolution_b200.srcnn.srcnn import SrcnnNet, FLAGS
+    net = SrcnnNet(None, 1, seed=42, flags=FLAGS)
+    net.arena.w.mul_(60.0)  # trained-like magnitudes (reference init is sigma=0.001: every ReLU would be numerically dead)
+    net.repack()
+    g = torch.Generator(device="cuda").manual_seed(1238 + rank)
+    hi = torch.rand((SRCNN_BATCH, SRCNN_PATCH, SRCNN_PATCH, 1), device="cuda", generator=g) * 2 - 1
+
+    def step():
+        net.train_step(hi, 1e-3)
+
+    ms, clocks = timed_steps(step, args.steps, args.warmup, world, ClockSampler(torch.cuda.current_device()) if rank == 0 else None)
+    value = SRCNN_BATCH * world * args.steps / ms * 1e3
+    # 2*MACs: conv1 81*64 @25x25, conv2 64*32 @25x25, conv3 25*32 @21x21 per patch; backward = wgrad for all + dgrad for conv2/conv3
+    fwd = 2 * (625 * 81 * 64 + 625 * 64 * 32 + 441 * 25 * 32)
+    flops_per_patch = fwd * 3 - 2 * 625 * 81 * 64
+    pk = peaks()
+    tf = value * flops_per_patch / 1e12 / world
+    roofline = {"bound": "tensor", "kernel": "whole SRCNN step (launch-latency bound: 29 MFLOP/patch, ~45 launches)", "achieved": round(tf, 2),
+                "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": round(tf / pk["tf_sust"], 5), "traffic": None, "peak_source": pk["src"]}
+    n_launch = launches_of(step) * args.steps
+    hi_h = hi.cpu().pin_memory()
+    loss_h = torch.zeros(1).pin_memory()
+
+    def e2e_step():
+        hi.copy_(hi_h, non_blocking=True)
+        loss_h.copy_(net.train_step(hi, 1e-3), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    ne = max(2, args.steps // 2)
+    ms_e, _ = timed_steps(e2e_step, ne, 2, world, None)
+    e2e = {"value": round(SRCNN_BATCH * world * ne / ms_e * 1e3, 1), "unit": "patches/s", "h2d_bytes_per_step": hi_h.numel() * 4, "d2h_bytes_per_step": 4}
+    cfg = {"workload": f"SRCNN 9-1-5 3x training (bicubic degrade, VALID convs, row-L2 loss, Adam), {SRCNN_BATCH} synthetic 33x33 Y patches/GPU",
+           "global_batch": SRCNN_BATCH * world, "parallelism": f"replicas x{world}", "l2_policy": "working set ~40 MB < L2: a 3.7 GFLOP step is launch-bound, not memory-bound"}
+    return dict(metric="SRCNN training patches/s", value=round(value, 1), unit="patches/s", ms=ms, clocks=clocks, roofline=roofline, e2e=e2e,
+                gpu_launches=n_launch, config=cfg, scaling="weak")
+
+
+def srcnn_train_cpu(steps: int, threads: int):
+    from oracle import models as OM
+    from oracle import ops as O
+    torch.set_num_threads(threads)
+    p = OM.srcnn_init(seed=42, channels=1)
+    hi = OM.synthetic_images(4, SRCNN_BATCH, SRCNN_PATCH, SRCNN_PATCH, 1)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        lo = O.resize_bicubic_tf1(O.resize_bicubic_tf1(hi, SRCNN_PATCH // 3, SRCNN_PATCH // 3), SRCNN_PATCH, SRCNN_PATCH)
+        OM.srcnn_loss_and_grads(p, lo, hi, dtype=np.float32)
+    dt = time.perf_counter() - t0
+    return steps * SRCNN_BATCH / dt, dt
+
+
+WORKLOADS = {"espcn": espcn_workload, "vdsr_train": vdsr_train_workload, "vdsr_infer": vdsr_infer_workload, "srcnn_train": srcnn_train_workload}
 
 
 def run_reference(args, rank, world):
@@ -386,6 +443,11 @@ def run_reference(args, rank, world):
             v, dt = espcn_cpu(frames, threads)
         unit, metric, steps, sample = "output Mpix/s", "ESPCN 3x output Mpix/s (fwd)", frames, f"{frames} step(s) of ONE 1920x1080 Y frame each (GPU arm: {FRAMES_PER_STEP}/step)"
         cfg = {"workload": "ESPCN 3x inference on synthetic 1920x1080 Y frames (CPU restatement, torch-CPU fp32)"}
+    elif args.workload == "srcnn_train":
+        steps = max(1, min(args.steps, 10))
+        v, dt = srcnn_train_cpu(steps, threads)
+        unit, metric, sample = "patches/s", "SRCNN training patches/s", f"{steps} degrade+fwd+bwd step(s) of 128 33x33 Y patches (no optimiser step)"
+        cfg = {"workload": "SRCNN 9-1-5 training, 128 synthetic 33x33 Y patches (CPU restatement, torch-CPU fp32 autograd)"}
     elif args.workload == "vdsr_train":
         steps = max(1, min(args.steps, 5))
         v, dt = vdsr_train_cpu(steps, threads)
@@ -431,7 +493,7 @@ def main():
     if args.workload == "espcn" and not args.no_also:
         sub = argparse.Namespace(**vars(args))
         sub.steps, sub.warmup = max(5, args.steps // 2), 3
-        for name in ("vdsr_train", "vdsr_infer"):
+        for name in ("vdsr_train", "vdsr_infer", "srcnn_train"):
             r = WORKLOADS[name](sub, rank, world)
             also[name] = {"metric": r["metric"], "value": r["value"], "unit": r["unit"], "ms_per_step": round(r["ms"] / sub.steps, 4),
                           "roofline": r["roofline"], "e2e": r["e2e"], "scaling": r["scaling"], "steps": sub.steps}
@@ -446,6 +508,9 @@ def main():
                 elif args.workload == "vdsr_infer":
                     v, dt = vdsr_infer_cpu(threads)
                     cpu = {"value": round(v, 3), "unit": "output Mpix/s", "cores": threads, "kind": "port", "sample": f"one 270x3840 band, {dt:.1f} s"}
+            if args.workload == "srcnn_train":
+                v, dt = srcnn_train_cpu(5, threads)
+                cpu = {"value": round(v, 2), "unit": "patches/s", "cores": threads, "kind": "port", "sample": f"5 degrade+fwd+bwd steps of 128 patches, {dt:.1f} s"}
             if args.workload == "vdsr_train":
                 v, dt = vdsr_train_cpu(3, threads)
                 cpu = {"value": round(v, 2), "unit": "patches/s", "cores": threads, "kind": "port", "sample": f"3 fwd+bwd steps of 64 patches, {dt:.1f} s"}
