@@ -426,7 +426,86 @@ def srcnn_train_cpu(steps: int, threads: int):
     return steps * SRCNN_BATCH / dt, dt
 
 
-WORKLOADS = {"espcn": espcn_workload, "vdsr_train": vdsr_train_workload, "vdsr_infer": vdsr_infer_workload, "srcnn_train": srcnn_train_workload}
+# ------------------------------------------------------------------------------------------------ EnhanceNet generator fwd+bwd (BASELINE configs[4])
+ENET_BATCH, ENET_LR = 64, 32
+
+
+def enet_train_workload(args, rank, world):
+    """EnhanceNet generator forward + backward (+ Adam) on synthetic 32x32 -> 128x128 patches, batch 64 per GPU; the upstream
+    gradient is the MSE term d(mean((sr-hd)^2))/d(sr) (the VGG / texture / adversarial terms are outside the hot path)."""
+    from ml_super_resolution_b200 import ops
+    from ml_super_resolution_b200.enet.model_enet import EnetGenerator
+    net = EnetGenerator(None, seed=42)
+    net.arena.w.mul_(2.5)
+    net.repack()
+    g = torch.Generator(device="cuda").manual_seed(1239 + rank)
+    sd = torch.rand((ENET_BATCH, ENET_LR, ENET_LR, 3), device="cuda", generator=g) * 2 - 1
+    bq = torch.rand((ENET_BATCH, 4 * ENET_LR, 4 * ENET_LR, 3), device="cuda", generator=g) * 2 - 1
+    hd = torch.rand((ENET_BATCH, 4 * ENET_LR, 4 * ENET_LR, 3), device="cuda", generator=g) * 2 - 1
+    dsr = torch.empty_like(hd)
+    loss = torch.zeros(1, device="cuda")
+    a = net.arena
+    t = [0]
+
+    def step():
+        # forward_backward needs d(sr): one generator forward feeds the loss kernel, then forward+backward (the forward is
+        # recomputed inside: 1/3 of the step's FLOPs; a fused loss hook would remove it)
+        sr = net.forward(sd, bq)
+        loss.zero_()
+        ops.mse_fwd_bwd(sr, hd, loss, dsr)
+        net.forward_backward(sd, bq, dsr)
+        if world > 1:
+            torch.distributed.all_reduce(a.g)
+        t[0] += 1
+        ops.adam_step(a.w, a.g, a.m, a.v, 1e-4, t[0])
+        net._tb["plan"].run(a.w)
+        net.repack()
+
+    net.forward_backward(sd, bq, hd)  # allocate the training buffers outside the timed region
+    ms, clocks = timed_steps(step, args.steps, args.warmup, world, ClockSampler(torch.cuda.current_device()) if rank == 0 else None)
+    value = ENET_BATCH * world * args.steps / ms * 1e3
+    flops_per_patch = 3.617e9 * 4  # fwd (loss) + fwd + dgrad + wgrad, SURVEY 8 row a5: 3.617 GFLOP fwd/patch
+    pk = peaks()
+    tf = value * flops_per_patch / 1e12 / world
+    roofline = {"bound": "tensor", "kernel": "whole generator step (25 fwd + 24 dgrad + 25 wgrad tcgen05 convs, forward run twice)", "achieved": round(tf, 1),
+                "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": round(tf / pk["tf_sust"], 4), "traffic": None, "peak_source": pk["src"]}
+    n_launch = launches_of(step) * args.steps
+    sd_h, bq_h, hd_h = sd.cpu().pin_memory(), bq.cpu().pin_memory(), hd.cpu().pin_memory()
+    loss_h = torch.zeros(1).pin_memory()
+
+    def e2e_step():
+        sd.copy_(sd_h, non_blocking=True)
+        bq.copy_(bq_h, non_blocking=True)
+        hd.copy_(hd_h, non_blocking=True)
+        step()
+        loss_h.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    ne = max(2, args.steps // 2)
+    ms_e, _ = timed_steps(e2e_step, ne, 1, world, None)
+    e2e = {"value": round(ENET_BATCH * world * ne / ms_e * 1e3, 1), "unit": "patches/s",
+           "h2d_bytes_per_step": (sd_h.numel() + bq_h.numel() + hd_h.numel()) * 4, "d2h_bytes_per_step": 4}
+    cfg = {"workload": f"EnhanceNet 4x generator forward+backward+Adam (MSE upstream gradient), {ENET_BATCH} synthetic 32x32->128x128 patches/GPU",
+           "global_batch": ENET_BATCH * world, "parallelism": f"dp{world}", "l2_policy": "saved activations ~1.3 GB per step >> 126 MB L2"}
+    return dict(metric="EnhanceNet generator training patches/s", value=round(value, 1), unit="patches/s", ms=ms, clocks=clocks, roofline=roofline,
+                e2e=e2e, gpu_launches=n_launch, config=cfg, scaling="weak")
+
+
+def enet_train_cpu(steps: int, threads: int, batch: int = 4):
+    from oracle import models as OM
+    torch.set_num_threads(threads)
+    p = OM.enet_g_init(seed=42)
+    sd = OM.synthetic_images(5, batch, ENET_LR, ENET_LR, 3)
+    bq = OM.synthetic_images(6, batch, 4 * ENET_LR, 4 * ENET_LR, 3)
+    dsr = OM.synthetic_images(7, batch, 4 * ENET_LR, 4 * ENET_LR, 3) * 1e-4
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        OM.enet_generator_grads(p, sd, bq, dsr, dtype=np.float32)
+    dt = time.perf_counter() - t0
+    return steps * batch / dt, dt
+
+
+WORKLOADS = {"enet_train": enet_train_workload, "espcn": espcn_workload, "vdsr_train": vdsr_train_workload, "vdsr_infer": vdsr_infer_workload, "srcnn_train": srcnn_train_workload}
 
 
 def run_reference(args, rank, world):
@@ -443,6 +522,11 @@ def run_reference(args, rank, world):
             v, dt = espcn_cpu(frames, threads)
         unit, metric, steps, sample = "output Mpix/s", "ESPCN 3x output Mpix/s (fwd)", frames, f"{frames} step(s) of ONE 1920x1080 Y frame each (GPU arm: {FRAMES_PER_STEP}/step)"
         cfg = {"workload": "ESPCN 3x inference on synthetic 1920x1080 Y frames (CPU restatement, torch-CPU fp32)"}
+    elif args.workload == "enet_train":
+        steps = max(1, min(args.steps, 3))
+        v, dt = enet_train_cpu(steps, threads)
+        unit, metric, sample = "patches/s", "EnhanceNet generator training patches/s", f"{steps} fwd+bwd step(s) of 4 32x32->128x128 patches (GPU arm: 64/step, + loss forward + Adam)"
+        cfg = {"workload": "EnhanceNet generator forward+backward, synthetic 32x32->128x128 patches (CPU restatement, torch-CPU fp32 autograd)"}
     elif args.workload == "srcnn_train":
         steps = max(1, min(args.steps, 10))
         v, dt = srcnn_train_cpu(steps, threads)
@@ -493,7 +577,7 @@ def main():
     if args.workload == "espcn" and not args.no_also:
         sub = argparse.Namespace(**vars(args))
         sub.steps, sub.warmup = max(5, args.steps // 2), 3
-        for name in ("vdsr_train", "vdsr_infer", "srcnn_train"):
+        for name in ("vdsr_train", "vdsr_infer", "srcnn_train", "enet_train"):
             r = WORKLOADS[name](sub, rank, world)
             also[name] = {"metric": r["metric"], "value": r["value"], "unit": r["unit"], "ms_per_step": round(r["ms"] / sub.steps, 4),
                           "roofline": r["roofline"], "e2e": r["e2e"], "scaling": r["scaling"], "steps": sub.steps}
@@ -508,6 +592,9 @@ def main():
                 elif args.workload == "vdsr_infer":
                     v, dt = vdsr_infer_cpu(threads)
                     cpu = {"value": round(v, 3), "unit": "output Mpix/s", "cores": threads, "kind": "port", "sample": f"one 270x3840 band, {dt:.1f} s"}
+            if args.workload == "enet_train":
+                v, dt = enet_train_cpu(2, threads)
+                cpu = {"value": round(v, 2), "unit": "patches/s", "cores": threads, "kind": "port", "sample": f"2 fwd+bwd steps of 4 patches, {dt:.1f} s"}
             if args.workload == "srcnn_train":
                 v, dt = srcnn_train_cpu(5, threads)
                 cpu = {"value": round(v, 2), "unit": "patches/s", "cores": threads, "kind": "port", "sample": f"5 degrade+fwd+bwd steps of 128 patches, {dt:.1f} s"}

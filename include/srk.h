@@ -111,7 +111,9 @@ int srk_conv_first_tc(srk_handle_t h, const float* x, int n_frames, int FH, int 
  *   and, with SRK_PACK_DGRAD weights + mask_src, the data gradient of the same layers.
  * x: FPA bf16 [rows, cin_p] (cin_p 64 or 32); y: FPA bf16 [rows, cout_p] (64 or 32).
  * k is 3 or 1.  mask_kind: SRK_ACT_RELU -> (mask_src>0), SRK_ACT_TANH -> (1-mask_src^2).
- * addend (optional FPA, cout_p channels): y = relu(addend + y) when relu_after_add, else sum. */
+ * addend (optional FPA, cout_p channels): relu_after_add = 0 -> y + addend; 1 -> relu(y + addend) (residual block
+ * output, enet/enet/model_enet.py:29-31); 2 -> (conv + addend) * act'(mask_src): the data gradient through that
+ * junction, where the skip path's gradient joins before the producing layer's activation mask. */
 int srk_conv_tc(srk_handle_t h, const void* x_fpa, int cin_p, const void* w_packed, const float* bias,
                 int k, int cout_p, int act, int n_img, int H, int W, void* y_fpa,
                 const void* mask_src, int mask_kind, const void* addend_fpa, int relu_after_add,

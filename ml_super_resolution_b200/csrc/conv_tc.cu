@@ -404,21 +404,10 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
 #pragma unroll
               for (int c = 0; c < CP; ++c) v[c] = fmaxf(v[c], 0.f);
             }
-            if (p.mask_src) {
-              const uint4* m = reinterpret_cast<const uint4*>(p.mask_src + size_t(prow) * NP + col0);
-#pragma unroll
-              for (int j = 0; j < CP / 8; ++j) {
-                const uint4 mv = __ldg(m + j);
-                const uint32_t w4[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[q]));
-                  v[j * 8 + q * 2] *= (1.f - f.x * f.x);
-                  v[j * 8 + q * 2 + 1] *= (1.f - f.y * f.y);
-                }
-              }
-            }
-            if (p.addend_fpa) {
+            // relu_after_add == 2: data gradient through a residual junction, (conv + addend) * act'(mask_src);
+            // otherwise conv * act'(mask_src) [+ addend [-> ReLU]]
+            const bool add_first = p.addend_fpa && p.relu_after_add == 2;
+            auto add_addend = [&]() {
               const uint4* a = reinterpret_cast<const uint4*>(p.addend_fpa + size_t(prow) * NP + col0);
 #pragma unroll
               for (int j = 0; j < CP / 8; ++j) {
@@ -431,6 +420,25 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
                   v[j * 8 + q * 2 + 1] += f.y;
                 }
               }
+            };
+            if (add_first) add_addend();
+            if (p.mask_src) {
+              const uint4* m = reinterpret_cast<const uint4*>(p.mask_src + size_t(prow) * NP + col0);
+              const bool tanh_kind = p.mask_kind == SRK_ACT_TANH;
+#pragma unroll
+              for (int j = 0; j < CP / 8; ++j) {
+                const uint4 mv = __ldg(m + j);
+                const uint32_t w4[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[q]));
+                  v[j * 8 + q * 2] *= tanh_kind ? (1.f - f.x * f.x) : (f.x > 0.f ? 1.f : 0.f);
+                  v[j * 8 + q * 2 + 1] *= tanh_kind ? (1.f - f.y * f.y) : (f.y > 0.f ? 1.f : 0.f);
+                }
+              }
+            }
+            if (p.addend_fpa && !add_first) {
+              add_addend();
               if (p.relu_after_add) {
 #pragma unroll
                 for (int c = 0; c < CP; ++c) v[c] = fmaxf(v[c], 0.f);

@@ -8,6 +8,13 @@ SURVEY section 2.1 #10-11).
   2 x upsample      NN x2 ; 3x3 64->64 ReLU             srk_fpa_upsample2 ; srk_conv_tc      reference :77-89
   conv2d_23         3x3 64->64 ReLU                     srk_conv_tc                          reference :92-99
   conv2d_24         3x3 64->3, + bq_images              srk_conv_tc_last (fused addend)      reference :102-113
+
+Backward of the generator for a supplied d(sr) (`forward_backward`; what `minimize(..., var_list=g_variables)` adds,
+reference :336-341 -- the VGG / texture / adversarial loss terms that produce d(sr) are outside the hot path):
+  every stored gradient is taken w.r.t. the PRE-activation of the layer that produced the tensor, so one dgrad launch
+  = conv with SRK_PACK_DGRAD weights * ReLU'(saved input); at a residual junction the skip gradient joins before the
+  mask (srk_conv_tc relu_after_add = 2); NN-upsample backward = srk_fpa_upsample2_bwd of the masked gradient;
+  wgrad = srk_conv_wgrad_tc per layer (1x1 layers keep the centre tap) + one srk_wgrad_reduce_many per resolution.
 """
 from __future__ import annotations
 
@@ -77,6 +84,111 @@ class EnetGenerator:
             i += 1
         t = ops.conv_tc(t, W[self._idx[i]], a.view(self._b(i)), 3, "relu")
         return ops.conv_tc_last(t, W[self._idx[i + 1]], self.bias_last, 3, 3, None, addend=bq)
+
+
+    # ------------------------------------------------------------------------------------------ training
+    def _enable_training(self, n, h, w):
+        key = (n, h, w)
+        if getattr(self, "_tb", None) is not None and self._tb["key"] == key:
+            return self._tb
+        a, dev = self.arena, self.device
+        a.enable_training()
+        L = len(ENET_G_LAYERS)
+        plan = ops.PackPlan(dev)
+        fw, dg = {}, {}
+        for i, (k, cin, cout) in enumerate(ENET_G_LAYERS):
+            off = a.offsets[self._k(i)]
+            if i == 0:
+                fw[i] = plan.add(off, 3, cin, 64, ops.PACK_FIRST)
+            elif i == L - 1:
+                fw[i] = plan.add(off, 3, 64, cout, ops.PACK_FWD, 16, 64)
+                dg[i] = plan.add(off, 3, 64, cout, ops.PACK_FIRST_ROT180T)
+            else:
+                fw[i] = plan.add(off, k, 64, 64, ops.PACK_FWD, 64, 64)
+                dg[i] = plan.add(off, k, 64, 64, ops.PACK_DGRAD, 64, 64)
+        plan.finalize()
+        geo = {"lo": (h, w), "mid": (2 * h, 2 * w), "hi": (4 * h, 4 * w)}
+        F = lambda g: ops.fpa_empty(n, geo[g][0], geo[g][1], 64, dev)  # noqa: E731
+        st = {g: (ops.wgrad_workspace_bytes(n, *geo[g]) + 1023) // 1024 * 1024 for g in geo}
+        gv = lambda i, b=False: a.view(self._b(i) if b else self._k(i), "g")  # noqa: E731
+        tmp1 = torch.zeros((10, 9, 64, 64), dtype=torch.float32, device=dev)  # 1x1 layers: all nine taps, the centre one is kept
+        # wgrad jobs per resolution, in launch order: (layer index, destination kernel buffer, ci_n, co_n)
+        jobs = {"hi": [(24, gv(24), 64, 3), (23, gv(23), 64, 64), (22, gv(22), 64, 64)], "mid": [(21, gv(21), 64, 64)], "lo": []}
+        for b in range(9, -1, -1):
+            jobs["lo"].append((2 + 2 * b, tmp1[b], 64, 64))
+            jobs["lo"].append((1 + 2 * b, gv(1 + 2 * b), 64, 64))
+        jobs["lo"].append((0, gv(0), 3, 64))
+        self._tb = {
+            "key": key, "plan": plan, "fw": fw, "dg": dg, "geo": geo, "st": st, "tmp1": tmp1, "jobs": jobs,
+            "t": [F("lo") for _ in range(11)], "hb": [F("lo") for _ in range(10)],
+            "u1": F("mid"), "m1": F("mid"), "u2": F("hi"), "m2": F("hi"), "m3": F("hi"),
+            "dhi": [F("hi") for _ in range(2)], "dmid": [F("mid") for _ in range(2)], "dlo": [F("lo") for _ in range(3)],
+            "sdF": F("lo"), "dP": F("hi"),
+            "ws": {g: torch.empty(st[g] * max(1, len(jobs[g])), dtype=torch.uint8, device=dev) for g in geo},
+            "dsts": {g: ops.make_wgrad_dsts([(dw, gv(i, True), ci, co) for (i, dw, ci, co) in jobs[g]], dev) for g in geo},
+            "sr": torch.empty((n, 4 * h, 4 * w, 3), dtype=torch.float32, device=dev),
+        }
+        self._tb["plan"].run(a.w)
+        return self._tb
+
+    def forward_backward(self, sd: torch.Tensor, bq: torch.Tensor, dsr: torch.Tensor):
+        """Generator forward, then its backward for the upstream gradient dsr = d(loss)/d(sr): fills the gradient arena
+        (`arena.g`, every kernel and bias of the 25 layers) and returns sr."""
+        n, h, w, _ = sd.shape
+        assert 4 * w <= MAX_PANEL_W
+        b, a = self._enable_training(n, h, w), self.arena
+        V, fw, dg = b["plan"].views, b["fw"], b["dg"]
+        bias = lambda i: a.view(self._b(i))  # noqa: E731
+        # ---- forward, keeping every activation
+        t = b["t"]
+        ops.conv_first_tc(sd, V[fw[0]], bias(0), 3, "SAME", "relu", out=t[0])
+        for k in range(10):
+            i = 1 + 2 * k
+            ops.conv_tc(t[k], V[fw[i]], bias(i), 3, "relu", out=b["hb"][k])
+            ops.conv_tc(b["hb"][k], V[fw[i + 1]], bias(i + 1), 1, None, out=t[k + 1], addend=t[k], relu_after_add=1)
+        ops.fpa_upsample2(t[10], out=b["u1"])
+        ops.conv_tc(b["u1"], V[fw[21]], bias(21), 3, "relu", out=b["m1"])
+        ops.fpa_upsample2(b["m1"], out=b["u2"])
+        ops.conv_tc(b["u2"], V[fw[22]], bias(22), 3, "relu", out=b["m2"])
+        ops.conv_tc(b["m2"], V[fw[23]], bias(23), 3, "relu", out=b["m3"])
+        ops.conv_tc_last(b["m3"], V[fw[24]], self.bias_last, 3, 3, None, addend=bq, out=b["sr"])
+        # ---- backward
+        ws, st = b["ws"], b["st"]
+        slot = {"hi": 0, "mid": 0, "lo": 0}
+
+        def wgrad(g, x, dy):
+            o = slot[g] * st[g]
+            ops.conv_wgrad_tc(x, dy, None, None, workspace=ws[g][o:o + st[g]])
+            slot[g] += 1
+
+        dhi, dmid, dlo = b["dhi"], b["dmid"], b["dlo"]
+        ops.nhwc_to_fpa_pad(dsr, 64, out=b["dP"])
+        wgrad("hi", b["m3"], b["dP"])                                                                            # conv2d_24
+        d = ops.conv_first_tc(dsr, V[dg[24]], None, 3, "SAME", None, out=dhi[0], mask_src=b["m3"], mask_kind="relu")
+        wgrad("hi", b["m2"], d)                                                                                  # conv2d_23
+        d = ops.conv_tc(d, V[dg[23]], None, 3, None, out=dhi[1], mask_src=b["m2"], mask_kind="relu")
+        wgrad("hi", b["u2"], d)                                                                                  # conv2d_22
+        d = ops.conv_tc(d, V[dg[22]], None, 3, None, out=dhi[0], mask_src=b["u2"], mask_kind="relu")
+        d = ops.fpa_upsample2_bwd(d, out=dmid[0])
+        wgrad("mid", b["u1"], d)                                                                                 # conv2d_21
+        d = ops.conv_tc(d, V[dg[21]], None, 3, None, out=dmid[1], mask_src=b["u1"], mask_kind="relu")
+        ds = ops.fpa_upsample2_bwd(d, out=dlo[0])
+        cur = 0
+        for k in range(9, -1, -1):                                                                               # residual blocks, last first
+            i = 1 + 2 * k
+            wgrad("lo", b["hb"][k], ds)                                                                          # 1x1
+            dh = ops.conv_tc(ds, V[dg[i + 1]], None, 1, None, out=dlo[(cur + 1) % 3], mask_src=b["hb"][k], mask_kind="relu")
+            wgrad("lo", t[k], dh)                                                                                # 3x3
+            ds = ops.conv_tc(dh, V[dg[i]], None, 3, None, out=dlo[(cur + 2) % 3], mask_src=t[k], mask_kind="relu", addend=ds, relu_after_add=2)
+            cur = (cur + 2) % 3
+        ops.nhwc_to_fpa_pad(sd, 64, out=b["sdF"])
+        wgrad("lo", b["sdF"], ds)                                                                                # conv2d (first layer)
+        for g in ("hi", "mid", "lo"):
+            gh, gw = b["geo"][g]
+            ops.wgrad_reduce_many(ws[g], st[g], slot[g], n, gh, gw, b["dsts"][g])
+        for k in range(10):
+            a.view(self._k(2 + 2 * k), "g").copy_(b["tmp1"][k, 4].view(1, 1, 64, 64))
+        return b["sr"]
 
 
 class _EnetGraph:

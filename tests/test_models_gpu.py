@@ -245,3 +245,28 @@ def test_srcnn_train_step_matches_oracle(srk_ops, channels, S, batch):
     # the inference path sees the trained parameters
     sr = net.forward(net.degrade(hit)).cpu().numpy()
     assert np.abs(sr - OM.srcnn_forward(p64, lo)).max() <= TOL_BF16
+
+
+def test_enet_generator_backward_matches_oracle(srk_ops):
+    """EnhanceNet generator backward for a supplied d(sr): every kernel / bias gradient of the 25 layers vs autograd of the
+    oracle (enet/enet/model_enet.py:8-31,44-115,336-341; BASELINE cfg5 geometry 32x32 -> 128x128)."""
+    from ml_super_resolution_b200.enet.model_enet import EnetGenerator
+    params = _trained_like(OM.enet_g_init(seed=8), scale=2.5)
+    net = EnetGenerator(params)
+    sd = OM.synthetic_images(41, 2, 32, 32, 3)
+    bq = OM.synthetic_images(42, 2, 128, 128, 3)
+    # upstream gradient of an MSE term against a synthetic HD batch: d(mean((sr-hd)^2))/d(sr).  (An i.i.d.-noise d(sr) makes
+    # every weight gradient an incoherent sum in which the ~1 % of ReLU masks that bf16 activations flip shows up as
+    # ~sqrt(1 %) relative error; a real loss gradient is spatially coherent.)
+    hd = OM.synthetic_images(43, 2, 128, 128, 3)
+    dsr = (2.0 * (OM.enet_generator_forward(params, sd, bq) - hd) / hd.size).astype(np.float32)
+    sr = net.forward_backward(torch.from_numpy(sd).cuda(), torch.from_numpy(bq).cuda(), torch.from_numpy(dsr).cuda()).cpu().numpy()
+    ref_g, ref_sr = OM.enet_generator_grads(params, sd, bq, dsr)
+    assert np.abs(sr - ref_sr).max() <= TOL_BF16 * max(1.0, np.abs(ref_sr - bq).max())
+    got = net.arena.to_numpy("g")
+    worst = 0.0
+    for k, g in ref_g.items():
+        rel = np.linalg.norm(got[k] - g) / (np.linalg.norm(g) + 1e-30)
+        worst = max(worst, rel)
+        assert rel <= 6e-2, f"{k}: relative gradient error {rel:.4f}"
+    assert worst > 0.0
