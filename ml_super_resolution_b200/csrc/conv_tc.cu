@@ -902,16 +902,21 @@ __global__ void __launch_bounds__(ConvGatherCfg<KS, CIN>::kThreads, 1) conv_gath
         mbar_arrive_expect_tx(bar_wfull, L::kWBytes);
         for (int b = 0; b < L::kBlocks; ++b) tma_load_2d(s_w + b * 64 * 128, &p.map_w, 0, b * 64, bar_wfull);
       }
-    } else if (warp == 1) {
+    } else if (warp == 1 || warp == 3) {
+      // two MMA issuers take alternate tiles (AST and ACC are even: an A stage / accumulator stage always belongs to the same
+      // issuer): one warp's barrier waits and commits run under the other's MMAs, as in conv_tc_kernel
       if (lane == 0) {
         constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
         constexpr uint64_t hi = umma_desc_hi(0, 1024, UMMA_LAYOUT_SW128);
+        static_assert(ACC % 2 == 0 && AST % 2 == 0, "stage ownership per issuer");
         mbar_wait(bar_wfull, 0);
-        for (int t = t_begin; t < t_end; ++t) {
+        for (int t = t_begin + (warp >> 1); t < t_end; t += 2) {
           const int it = t - t_begin, acc = it % ACC, st = it % AST;
           mbar_wait(bar_afull(st), (it / AST) & 1);
+          SRK_TRACE_EV(1, it);
           mbar_wait(bar_tempty(acc), ((it / ACC) & 1) ^ 1);
           tc_fence_after();
+          SRK_TRACE_EV(2, it);
 #pragma unroll
           for (int k = 0; k < L::kKP / 16; ++k) {
             const uint32_t a_addr = s_a + st * L::kABytes + (k / 4) * (128 * 128) + (k % 4) * 32;
@@ -920,6 +925,7 @@ __global__ void __launch_bounds__(ConvGatherCfg<KS, CIN>::kThreads, 1) conv_gath
           }
           umma_commit(bar_tfull(acc));
           umma_commit(bar_aempty(st));
+          SRK_TRACE_EV(3, it);
         }
       }
     } else if (warp == 2) {
@@ -944,6 +950,7 @@ __global__ void __launch_bounds__(ConvGatherCfg<KS, CIN>::kThreads, 1) conv_gath
         const int pyy = int(q - uint32_t(pn) * uint32_t(H1));
         const bool valid = prow < p.rows_valid && px < p.W && pyy > 0;
         mbar_wait(bar_aempty(st), ((it / AST) & 1) ^ 1);
+        if (r == 0) SRK_TRACE_EV(16, it);
         if (valid) {
           int fn = pn, y0 = 0, x0 = 0;
           if (p.panels) {
@@ -975,7 +982,7 @@ __global__ void __launch_bounds__(ConvGatherCfg<KS, CIN>::kThreads, 1) conv_gath
               f[j] = 0.f;
               if (k < L::kKT) {
                 const int tap = k / CIN, ci = k % CIN, u = tap / KS, v = tap % KS;
-                const float val = __ldg(frame + rofs[u] + cofs[v] + ci);
+                const float val = SRK_ABLATE(p, 128) ? float(k) : __ldg(frame + rofs[u] + cofs[v] + ci);
                 f[j] = (rok[u] && cok[v]) ? val : 0.f;
               }
             }
@@ -985,6 +992,7 @@ __global__ void __launch_bounds__(ConvGatherCfg<KS, CIN>::kThreads, 1) conv_gath
         }
         fence_proxy_async_smem();
         mbar_arrive(bar_afull(st));
+        if (r == 0) SRK_TRACE_EV(17, it);
       }
     }
   }

@@ -12,7 +12,7 @@ Ht, Wt, tiles = plan_tiles(F, 1080, 1920, 4, max_w=int(os.environ.get('PANEL_W',
 panels = ops.make_panels([t.as_tuple() for t in tiles])
 t1, t2 = net._get_bufs(len(tiles), Ht, Wt)
 a = net.arena
-def tm(fn, n=10):
+def tm(fn, n=int(os.environ.get('N_REP', '10'))):
     for _ in range(3): fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

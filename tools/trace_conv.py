@@ -15,7 +15,7 @@ from ml_super_resolution_b200.espcn.model_espcn import EspcnNet  # noqa: E402
 from ml_super_resolution_b200.tiling import plan_tiles  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else "f2"
-sets = 2 if which == "c64" else 4
+sets = 2 if which in ("c64", "f1") else 4
 g = torch.Generator(device="cuda").manual_seed(0)
 if which == "c64":
     N, H, W = 64, 240, 240
@@ -37,7 +37,9 @@ else:
     a = net.arena
     ops.conv_first_tc(lr, net.plan.views[net._i1], a.view("f1/bias:0"), 5, "SAME", "tanh", panels=panels, panel_hw=(Ht, Wt), out=t1)
     ops.conv_tc(t1, net.plan.views[net._i2], a.view("f2/bias:0"), 3, "tanh", out=t2)
-    if which == "f2":
+    if which == "f1":
+        run = lambda: ops.conv_first_tc(lr, net.plan.views[net._i1], a.view("f1/bias:0"), 5, "SAME", "tanh", panels=panels, panel_hw=(Ht, Wt), out=t1)  # noqa: E731
+    elif which == "f2":
         run = lambda: ops.conv_tc(t1, net.plan.views[net._i2], a.view("f2/bias:0"), 3, "tanh", out=t2)  # noqa: E731
     else:
         run = lambda: ops.conv_tc_last(t2, net.plan.views[net._i3], net.bias3, 3, net.cout3, None, shuffle_r=3, panels=panels,  # noqa: E731
@@ -81,6 +83,11 @@ if T[8, lo]:
     print(f"  store: staged -> freed                   {d(T[9, r] - T[8, r]):8.0f}")
 for a_, b_ in ((8, 32), (32, 64), (64, 128), (128, 192), (192, 250)):
     print(f"  tile period over tiles {a_:3d}..{b_:3d}: {(T[3, b_] - T[3, a_]) / (b_ - a_):7.0f} cycles")
+if which == "f1":
+    print(f"  gather: slot free -> rows written        {d(T[17, r] - T[16, r]):8.0f}")
+    print(f"  gather: rows written -> next slot free   {d(T[16, r + 2] - T[17, r]):8.0f}   (same group, its next tile)")
+    print(f"  gather done -> issuer sees A full        {d(T[1, r] - T[17, r]):8.0f}")
+    sys.exit(0)
 cr = np.arange(60, 200)
 print(f"  producer per chunk: slot-free wait {d(T[17, cr] - T[16, cr]):6.0f} | ready arrives {d(T[0, cr] - T[17, cr]):6.0f} | expect_tx {d(T[18, cr] - T[0, cr]):6.0f} | "
       f"TMA issue {d(T[19, cr] - T[18, cr]):6.0f} | loop {d(T[16, cr + 1] - T[19, cr]):6.0f}")
