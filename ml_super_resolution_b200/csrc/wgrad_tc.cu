@@ -5,13 +5,18 @@
 // is a GEMM whose contraction index is the pixel row p.  Both operands are "MN-major" in smem
 // exactly as TMA lands them ([pixel][channel] rows, SW128), so no transpose is ever materialised:
 // tcgen05.mma reads A = X^T and B = dY through MN-major descriptors (a_major = b_major = 1).
-// One M=128 instruction covers TWO taps: its two 64-row M atoms are two row-shifted windows of the
-// same X ring, LBO = (off_b - off_a) * 128 B apart (probe-verified; LBO must be positive, so the
-// ring keeps a mirror of its first chunks behind its last slot).  The ninth tap is paired with a
-// block of ones, which makes rows 64..127 of that accumulator the bias gradient sum_p dY[p][co].
-// Five fp32 accumulators (5 x 64 TMEM columns) persist over the CTA's whole pixel range (split-K
-// across CTAs); each CTA stores its partial block to a workspace and a second, deterministic
-// kernel sums the partials into dW / dbias (fixed order: bit-reproducible gradients).
+// One M=128 x N=192 instruction covers SIX taps.  With q = p + (v-1) the sum reads
+//   dW[u][v] = sum_q X[q + (u-1)*Wp][ci] * dY[q - (v-1)][co]:
+// the two 64-row M atoms are two row-shifted windows of the X ring (u = 0, 1), LBO = Wp rows apart, and the three
+// 64-column N atoms are three row-shifted windows of the dY tile (v = 2, 1, 0), LBO = ONE row apart (probe-verified:
+// an MN-major atom stride may be any positive multiple of 16 B; it must be positive, so the X ring keeps a mirror of
+// its first chunks behind its last slot, and every dY tile is loaded with one extra row on either side).  A second
+// instruction pairs the u = 2 window with a block of ones, which makes rows 64..127 of that accumulator the bias
+// gradient sum_q dY[q][co].  N = 192 runs at the tensor pipe's full rate (96 cycles), where the earlier five
+// M=128 x N=64 instructions per K-step (60 cycles each, operand-fetch bound) cost 300.
+// Two fp32 accumulators (2 x 192 TMEM columns) persist over the CTA's whole pixel range (split-K across CTAs); each
+// CTA stores its partial block to a workspace and a second, deterministic kernel sums the partials into dW / dbias
+// (fixed order: bit-reproducible gradients).
 //
 //   warp 0: TMA producer for X chunks (+ mirrors)      warp 6: TMA producer for dY chunks
 //   warp 1: TMEM allocator + single-thread MMA issuer  warps 2..5: epilogue
@@ -24,11 +29,13 @@ constexpr int kXSlots = 10;  // ring + mirror slots (16 KB each)
 constexpr int kYRing = 3;
 constexpr int kWgThreads = 224;
 constexpr int kChunk = 128 * 128;  // bytes
+constexpr int kYRows = 130;        // a dY tile: 128 rows + one neighbour row on either side
+constexpr int kYSlot = 17 * 1024;  // bytes per dY slot (130 rows, 1024-byte aligned for the swizzle phase)
 constexpr int kPartialFloats = 9 * 64 * 64 + 64;  // dW[9][64][64] then dbias[64]
 
 struct alignas(64) WgradParams {
   CUtensorMap map_x;   // [rows_valid][64] box {64,128}
-  CUtensorMap map_dy;  // [rows_valid][64] box {64,128}
+  CUtensorMap map_dy;  // [rows_valid][64] box {64,130}
   float* partial;      // workspace: [gridDim.x][kPartialFloats] per-CTA partial sums
   int Wp;
   int num_chunks;
@@ -40,7 +47,7 @@ struct alignas(64) WgradParams {
 struct WgSmem {
   static constexpr int kOffX = 0;
   static constexpr int kOffY = kXSlots * kChunk;
-  static constexpr int kOffOnes = kOffY + kYRing * kChunk;
+  static constexpr int kOffOnes = kOffY + kYRing * kYSlot;
   static constexpr int kOffBars = kOffOnes + 2048;
   static constexpr int kNumBars = 2 * kXSlots + 2 * kYRing + 1;
   static constexpr int kOffTmemSlot = kOffBars + kNumBars * 8;
@@ -112,30 +119,23 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         for (int k = k_begin; k < k_end; ++k) {
           const int j = k - k_begin, slot = j % kYRing, gen = j / kYRing;
           mbar_wait(bar_yempty(slot), (gen & 1) ^ 1);
-          mbar_arrive_expect_tx(bar_yfull(slot), kChunk);
-          tma_load_2d(s_y + slot * kChunk, &p.map_dy, 0, k * 128, bar_yfull(slot));
+          mbar_arrive_expect_tx(bar_yfull(slot), kYRows * 128);
+          tma_load_2d(s_y + slot * kYSlot, &p.map_dy, 0, k * 128 - 1, bar_yfull(slot));  // rows 128k-1 .. 128k+128 (OOB rows: zero)
         }
       }
     } else if (warp == 1) {
       if (lane == 0) {
-        constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
-        constexpr uint64_t b_hi = umma_desc_hi(1024, 1024, UMMA_LAYOUT_SW128);
+        constexpr uint32_t idesc = umma_idesc_bf16(128, 192, 1, 1);
+        constexpr uint64_t b_hi = umma_desc_hi(128 /* N atoms one row apart */, 1024, UMMA_LAYOUT_SW128);
         const int Wp = p.Wp;
-        // tap pairs (a, b): offsets of a, and distance d = off_b - off_a > 0 (rows)
-        const int off_a[5] = {-Wp - 1, -1, Wp - 1, -Wp + 1, Wp + 1};
-        const int dist[5] = {1, 1, 1, Wp, 0 /* ones block */};
         int loaded = c0 - 1;
         const int ring_rows = R * 128;
         // The single issuing thread is the critical path (every instruction pays its full dependent latency), so the
         // loop carries running window rows and pre-built descriptor halves instead of recomputing them with
-        // divisions: a_row[pr] advances 16 rows per K-step and wraps by subtraction.
-        int a_row[5];
-        uint64_t a_hi[5];
-#pragma unroll
-        for (int pr = 0; pr < 5; ++pr) {
-          a_row[pr] = (nb * 128 + off_a[pr]) % ring_rows;
-          a_hi[pr] = umma_desc_hi(uint32_t(dist[pr]) * 128u, 1024, UMMA_LAYOUT_SW128);
-        }
+        // divisions: a_row[] advances 16 rows per K-step and wraps by subtraction.
+        //   a_row[0]: X window of tap row u=0 (its second M atom, u=1, sits Wp rows behind it);  a_row[1]: u=2
+        int a_row[2] = {(nb * 128 - Wp) % ring_rows, (nb * 128 + Wp) % ring_rows};
+        const uint64_t a_hi = umma_desc_hi(uint32_t(Wp) * 128u, 1024, UMMA_LAYOUT_SW128);
         const uint64_t ones_hi = umma_desc_hi(0, 1024, UMMA_LAYOUT_SW128);
         for (int k = k_begin; k < k_end; ++k) {
           const int j = k - k_begin;
@@ -146,20 +146,20 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
           }
           mbar_wait(bar_yfull(j % kYRing), (j / kYRing) & 1);
           tc_fence_after();
-          const uint32_t y_addr = s_y + (j % kYRing) * kChunk;
+          const uint32_t y_addr = s_y + (j % kYRing) * kYSlot;
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
+            // B: dY rows (q0-1 .. q0+16], three windows one row apart = the taps v = 2, 1, 0
             const uint64_t bdesc = umma_desc(b_hi, y_addr + kk * 2048);
             const uint32_t acc_flag = (j | kk) != 0;
+            const uint32_t a0 = s_x + uint32_t(a_row[0]) * 128u, a1 = s_x + uint32_t(a_row[1]) * 128u;
+            umma_bf16(tmem, umma_desc(a_hi, a0), bdesc, idesc, acc_flag);
+            const uint64_t adesc1 = ones_hi | (uint64_t(((s_ones - a1) >> 4) & 0x3FFF) << 16) | uint64_t((a1 >> 4) & 0x3FFF);
+            umma_bf16(tmem + 192, adesc1, bdesc, idesc, acc_flag);
 #pragma unroll
-            for (int pr = 0; pr < 5; ++pr) {
-              const uint32_t a_addr = s_x + uint32_t(a_row[pr]) * 128u;
-              uint64_t adesc;
-              if (pr == 4) adesc = ones_hi | (uint64_t(((s_ones - a_addr) >> 4) & 0x3FFF) << 16) | uint64_t((a_addr >> 4) & 0x3FFF);
-              else adesc = umma_desc(a_hi[pr], a_addr);
-              umma_bf16(tmem + pr * 64, adesc, bdesc, idesc, acc_flag);
-              a_row[pr] += 16;
-              a_row[pr] -= (a_row[pr] >= ring_rows) ? ring_rows : 0;
+            for (int w = 0; w < 2; ++w) {
+              a_row[w] += 16;
+              a_row[w] -= (a_row[w] >= ring_rows) ? ring_rows : 0;
             }
           }
           umma_commit(bar_xempty(j % R));  // X chunk k-nb (= c0+j) is done
@@ -174,24 +174,26 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
       mbar_wait(bar_done, 0);
       tc_fence_after();
       float* part = p.partial + size_t(blockIdx.x) * kPartialFloats;
-      const int tap_of[5][2] = {{0, 1}, {3, 4}, {6, 7}, {2, 5}, {8, -1}};
+      // accumulator 0: rows (u = m>>6, ci), columns (N atom j -> v = 2-j, co); accumulator 1: rows 0..63 = (u = 2, ci),
+      // rows 64..127 = the ones block (row 64, atom 1 = unshifted dY: the bias gradient)
 #pragma unroll 1
-      for (int pr = 0; pr < 5; ++pr) {
-        const int tap = tap_of[pr][m >> 6];
+      for (int acc = 0; acc < 2; ++acc) {
+        const int u = acc == 0 ? (m >> 6) : 2;
         const int ci = m & 63;
-#pragma unroll
-        for (int c = 0; c < 64; c += 32) {
-          uint32_t u[32];
-          tmem_ld_32x32b_x32(tmem + pr * 64 + c + (uint32_t(quad * 32) << 16), u);
+#pragma unroll 1
+        for (int c = 0; c < 192; c += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem + acc * 192 + c + (uint32_t(quad * 32) << 16), r);
           tmem_ld_wait();
+          const int v = 2 - (c >> 6), co0 = c & 63;
           float4* dst = nullptr;
-          if (tap >= 0) dst = reinterpret_cast<float4*>(part + (size_t(tap) * 64 + ci) * 64 + c);
-          else if (m == 64) dst = reinterpret_cast<float4*>(part + 9 * 64 * 64 + c);
+          if (acc == 0 || m < 64) dst = reinterpret_cast<float4*>(part + (size_t(u * 3 + v) * 64 + ci) * 64 + co0);
+          else if (m == 64 && v == 1) dst = reinterpret_cast<float4*>(part + 9 * 64 * 64 + co0);
           if (dst) {
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-              dst[q] = make_float4(__uint_as_float(u[4 * q]), __uint_as_float(u[4 * q + 1]), __uint_as_float(u[4 * q + 2]),
-                                   __uint_as_float(u[4 * q + 3]));
+              dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                                   __uint_as_float(r[4 * q + 3]));
           }
         }
       }
@@ -285,7 +287,7 @@ extern "C" int srk_conv_wgrad_tc(srk_handle_t h, const void* x_fpa, const void* 
   const int grid = wgrad_grid(h, p.num_chunks);
   SRK_REQUIRE(workspace_bytes >= size_t(grid) * kPartialFloats * sizeof(float), "srk_conv_wgrad_tc: workspace too small (%zu B)", workspace_bytes);
   if (int rc = make_tensor_map_2d(&p.map_x, x_fpa, uint64_t(g.rows_valid), 64, 128)) return rc;
-  if (int rc = make_tensor_map_2d(&p.map_dy, dy_fpa, uint64_t(g.rows_valid), 64, 128)) return rc;
+  if (int rc = make_tensor_map_2d(&p.map_dy, dy_fpa, uint64_t(g.rows_valid), 64, kYRows)) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     SRK_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem::kTotal));
