@@ -52,6 +52,21 @@ def sanity_check(flags=FLAGS):
         flags.batch_size = 1
 
 
+def tap_block_centres(k: int):
+    """Centres (a, b) of the 3x3 tap blocks that tile a k x k kernel (taps -k//2 .. k//2), row-major; the last block of an
+    axis may reach past the kernel (k = 5: centres -1 and 2 cover taps -2..3, tap 3 is discarded)."""
+    nb = -(-k // 3)
+    c = [3 * i + 1 - k // 2 for i in range(nb)]
+    return [(a, b) for a in c for b in c]
+
+
+def assemble_tap_blocks(blocks: torch.Tensor, k: int) -> torch.Tensor:
+    """[nb*nb, 9, ci, co] per-block 3x3 tap gradients (block order of `tap_block_centres`) -> the [k, k, ci, co] kernel."""
+    nb = -(-k // 3)
+    ci, co = blocks.shape[-2:]
+    return blocks.reshape(nb, nb, 3, 3, ci, co).permute(0, 2, 1, 3, 4, 5).reshape(3 * nb, 3 * nb, ci, co)[:k, :k]
+
+
 class SrcnnNet:
     NAMES = ("patch_extraction", "non_linear_mapping", "reconstruction")
 
@@ -191,7 +206,7 @@ class SrcnnNet:
         b["dpre_e"][:, 2:2 + bb, 2:2 + bb, :].copy_(b["dpre"])
         ops.nhwc_to_fpa_pad(b["dpre_e"], 64, out=b["dP3"])
         Wp1, rows1 = H1 + 1, b["t2"].data.shape[0]
-        for blk, (ca, cb) in enumerate(((-1, -1), (-1, 2), (2, -1), (2, 2))):   # 3x3 tap blocks centred at (ca, cb)
+        for blk, (ca, cb) in enumerate(tap_block_centres(5)):   # 3x3 tap blocks centred at (-1|2, -1|2)
             xs = self._shifted(b["t2_store"], b["margin1"], rows1, ca * Wp1 + cb, b["t2"])
             ops.conv_wgrad_tc(xs, b["dP3"], None, None, workspace=b["ws1"][blk * b["st1"]:(blk + 1) * b["st1"]])
         d2 = ops.conv_first_tc(b["dpre_e"], V[ix["d3"]], None, 5, "SAME", None, out=b["d2"], mask_src=t2, mask_kind="relu")
@@ -203,15 +218,14 @@ class SrcnnNet:
         b["d1e"].data[: n * (S + 1) * (S + 1)].view(n, S + 1, S + 1, 64)[:, 5:5 + H1, 4:4 + H1].copy_(src)
         ops.nhwc_to_fpa_pad(lo, 64, out=b["loF"])
         Wp0, rows0 = S + 1, b["loF"].data.shape[0]
-        for blk in range(9):
-            ca, cb = 3 * (blk // 3) - 3, 3 * (blk % 3) - 3
+        for blk, (ca, cb) in enumerate(tap_block_centres(9)):   # centres -3, 0, 3
             xs = self._shifted(b["lo_store"], b["margin"], rows0, ca * Wp0 + cb, b["loF"])
             ops.conv_wgrad_tc(xs, b["d1e"], None, None, workspace=b["ws0"][blk * b["st0"]:(blk + 1) * b["st0"]])
         ops.wgrad_reduce_many(b["ws0"], b["st0"], 9, n, S, S, b["dsts0"])
         # assemble the kernel gradients from their 3x3 tap blocks
         g = lambda name: a.view(name, "g")  # noqa: E731
-        g("patch_extraction/weights:0").copy_(b["tmp1"].view(3, 3, 3, 3, C, 64).permute(0, 2, 1, 3, 4, 5).reshape(9, 9, C, 64))
-        g("reconstruction/weights:0").copy_(b["tmp3"].view(2, 2, 3, 3, 32, C).permute(0, 2, 1, 3, 4, 5).reshape(6, 6, 32, C)[:5, :5])
+        g("patch_extraction/weights:0").copy_(assemble_tap_blocks(b["tmp1"], 9))
+        g("reconstruction/weights:0").copy_(assemble_tap_blocks(b["tmp3"], 5))
         g("non_linear_mapping/weights:0").copy_(b["tmp2"][4].view(1, 1, 64, 32))
         b["lo"] = lo
         return b

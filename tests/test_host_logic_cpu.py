@@ -111,3 +111,30 @@ def test_data_parallel_gradients_equal_single_gpu_gloo():
     ref = np.concatenate([grads[k].reshape(-1) for k in params])
     assert abs(ltot - mse) < 1e-12
     assert np.abs(flat - ref).max() < 1e-12
+
+
+@pytest.mark.parametrize("k", [3, 5, 9])
+def test_srcnn_tap_block_decomposition(k):
+    """The k x k weight gradient is computed as 3x3 tap blocks over row-shifted activation views: the block centres must
+    tile the kernel exactly once and the assembly must put every tap back in its place (srcnn/srcnn.py:100-130 backward)."""
+    from ml_super_resolution_b200.srcnn.srcnn import assemble_tap_blocks, tap_block_centres
+    centres = tap_block_centres(k)
+    h = k // 2
+    seen = {}
+    ci, co = 2, 3
+    blocks = torch.zeros((len(centres), 9, ci, co))
+    for blk, (a, b) in enumerate(centres):
+        for u in (-1, 0, 1):
+            for v in (-1, 0, 1):
+                tap = (a + u, b + v)  # offset of this block tap relative to the kernel centre
+                if -h <= tap[0] <= h and -h <= tap[1] <= h:
+                    assert tap not in seen, f"tap {tap} covered twice"
+                    seen[tap] = blk
+                # a block tap's gradient is identified by its (row, column) offset
+                blocks[blk, (u + 1) * 3 + (v + 1)] = float((tap[0] + 16) * 100 + (tap[1] + 16))
+    assert len(seen) == k * k
+    full = assemble_tap_blocks(blocks, k)
+    assert full.shape == (k, k, ci, co)
+    for i in range(k):
+        for j in range(k):
+            assert float(full[i, j, 0, 0]) == float((i - h + 16) * 100 + (j - h + 16))
