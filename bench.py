@@ -318,18 +318,16 @@ def vdsr_infer_workload(args, rank, world):
     sd = torch.rand((1, H, W, 3), device="cuda", generator=g) * 2 - 1
     out = torch.empty_like(sd)
 
-    # tile grid: 252-px column panels; with several GPUs the panels are also cut into row bands (20-px halo) until the tile
-    # count divides evenly over the ranks (18 panels -> 72 tiles on 8 GPUs)
+    # tile grid: 252-px column panels,
     from ml_super_resolution_b200.tiling import plan_tiles
+    # and with several GPUs also into row bands (20-px halo): min(world, 4) bands, so that a rank's shard is (part of) one band
+    # and its host copies are contiguous full-width row ranges (2 / 4 GPUs: one band each; 8 GPUs: half a band each)
     tile_rows = None
     if world > 1:
+        k = min(world, 4)
         n_panels = len(plan_tiles(1, H, W, VDSR_LAYERS)[2])
-        for k in (1, 2, 3, 4):
-            if (n_panels * k) % world == 0:
-                break
-        if k > 1:
-            tile_rows = -(-(H - 2 * VDSR_LAYERS) // k) + 2 * VDSR_LAYERS
-
+        assert (n_panels * k) % world == 0, "tile count must divide over the ranks"
+        tile_rows = -(-(H - 2 * VDSR_LAYERS) // k) + 2 * VDSR_LAYERS
     def step():
         net.forward(sd, out=out, rank=rank, world=world, tile_rows=tile_rows)
 
@@ -354,15 +352,16 @@ def vdsr_infer_workload(args, rank, world):
               max(t.x0 + t.own_x1 for t in mine))
         return rd, ow
 
-    (ry0, ry1, rx0, rx1), (oy0, oy1, ox0, ox1) = boxes(rank)
-    h2d = sum((b[0][1] - b[0][0]) * (b[0][3] - b[0][2]) for b in map(boxes, range(world))) * 3 * 4
-    d2h = sum((b[1][1] - b[1][0]) * (b[1][3] - b[1][2]) for b in map(boxes, range(world))) * 3 * 4
+    # full-width row ranges: contiguous in NHWC, so the pinned copies stay single asynchronous DMA transfers
+    (ry0, ry1, _, _), (oy0, oy1, _, _) = boxes(rank)
+    h2d = sum(b[0][1] - b[0][0] for b in map(boxes, range(world))) * W * 3 * 4
+    d2h = sum(b[1][1] - b[1][0] for b in map(boxes, range(world))) * W * 3 * 4
     sd_dev = torch.empty_like(sd)
 
     def e2e_step():
-        sd_dev[:, ry0:ry1, rx0:rx1].copy_(sd_h[:, ry0:ry1, rx0:rx1], non_blocking=True)
+        sd_dev[:, ry0:ry1].copy_(sd_h[:, ry0:ry1], non_blocking=True)
         net.forward(sd_dev, out=out, rank=rank, world=world, tile_rows=tile_rows)
-        out_h[:, oy0:oy1, ox0:ox1].copy_(out[:, oy0:oy1, ox0:ox1], non_blocking=True)
+        out_h[:, oy0:oy1].copy_(out[:, oy0:oy1], non_blocking=True)
 
     ms_e, _ = timed_steps(e2e_step, max(2, args.steps // 2), 1, world, None)
     e2e = {"value": round(H * W * max(2, args.steps // 2) / ms_e / 1e3, 1), "unit": "output Mpix/s", "h2d_bytes_per_step": h2d,
