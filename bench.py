@@ -320,14 +320,11 @@ def vdsr_infer_workload(args, rank, world):
 
     # tile grid: 252-px column panels,
     from ml_super_resolution_b200.tiling import plan_tiles
-    # and with several GPUs also into row bands (20-px halo): min(world, 4) bands, so that a rank's shard is (part of) one band
-    # and its host copies are contiguous full-width row ranges (2 / 4 GPUs: one band each; 8 GPUs: half a band each)
+    # and with several GPUs also into `world` row bands (20-px halo): a rank's shard is one whole band, so its column panels
+    # can swap seam columns instead of recomputing halos and its host copies are contiguous full-width row ranges
     tile_rows = None
     if world > 1:
-        k = min(world, 4)
-        n_panels = len(plan_tiles(1, H, W, VDSR_LAYERS)[2])
-        assert (n_panels * k) % world == 0, "tile count must divide over the ranks"
-        tile_rows = -(-(H - 2 * VDSR_LAYERS) // k) + 2 * VDSR_LAYERS
+        tile_rows = -(-(H - 2 * VDSR_LAYERS) // world) + 2 * VDSR_LAYERS
     def step():
         net.forward(sd, out=out, rank=rank, world=world, tile_rows=tile_rows)
 
@@ -343,7 +340,7 @@ def vdsr_infer_workload(args, rank, world):
     # every rank moves only what its tile shard needs: the bounding box of the pixels its tiles read (host -> device) and of
     # the pixels they own (device -> host); one rank = the whole frame
     from ml_super_resolution_b200.tiling import MAX_PANEL_W, shard_tiles
-    Ht, Wt, tiles = plan_tiles(1, H, W, VDSR_LAYERS, MAX_PANEL_W, tile_rows)
+    Ht, Wt, tiles = plan_tiles(1, H, W, VDSR_LAYERS, MAX_PANEL_W, tile_rows, halo_x=1)
 
     def boxes(r):
         mine = shard_tiles(tiles, r, world)
@@ -366,7 +363,7 @@ def vdsr_infer_workload(args, rank, world):
     ms_e, _ = timed_steps(e2e_step, max(2, args.steps // 2), 1, world, None)
     e2e = {"value": round(H * W * max(2, args.steps // 2) / ms_e / 1e3, 1), "unit": "output Mpix/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h}
-    cfg = {"workload": "VDSR-20 3x tiled inference, one synthetic 3840x2160x3 frame/step, 252-px column panels with 20-px halo sharded over the GPUs",
+    cfg = {"workload": "VDSR-20 3x tiled inference, one synthetic 3840x2160x3 frame/step, 242-px column panels exchanging seam columns per layer; one 20-px-halo row band per GPU",
            "parallelism": f"tiles x{world}", "l2_policy": "activations 2 x 1.26 GB ping-pong >> 126 MB L2"}
     return dict(metric="VDSR 3x output Mpix/s (fwd)", value=round(value, 1), unit="output Mpix/s", ms=ms, clocks=clocks, roofline=roofline, e2e=e2e,
                 gpu_launches=n_launch, config=cfg, scaling="strong")

@@ -212,6 +212,12 @@ int srk_sumsq_masked(srk_handle_t h, const float* w, const float* mask, size_t n
 int srk_momentum_clip_step(srk_handle_t h, float* w, const float* g, float* accum, size_t n, float lr,
                            float momentum, float gradient_cap, float weight_decay, const float* decay_mask,
                            srk_stream_t stream);
+/* Tiled full-frame inference without recomputing a column halo: the FPA images are panels of one frame
+ * (srk_panel, ordered left to right within a band) that overlap by a few columns; after every layer each column a panel
+ * does not own ([0, own_x0) and [own_x1, W)) is refreshed in place from the neighbouring panel that owns it, so the next
+ * 3x3 layer sees exact neighbours at the panel seam.  max_cols >= the largest number of non-owned columns of any panel. */
+int srk_fpa_halo_exchange(srk_handle_t h, void* x_fpa, int C, const srk_panel* panels, int n_img, int H, int W,
+                          int max_cols, srk_stream_t stream);
 /* FPA (bf16, C ch) <-> fp32 NHWC [n_img,H,W,C] converters (feature-map taps `conv.N:0`, tests). */
 int srk_fpa_to_nhwc(srk_handle_t h, const void* x_fpa, int C, int n_img, int H, int W, float* y,
                     srk_stream_t stream);

@@ -444,6 +444,54 @@ extern "C" int srk_conv_first(srk_handle_t h, const float* x, int n_frames, int 
   return -1;
 }
 
+// Column-halo refresh between neighbouring panels of one frame band (see include/srk.h): every column a panel does not own is
+// copied from the panel that owns it.  Only non-owned columns are written and only owned columns are read, so the in-place
+// update is race free.  One thread moves 16 bytes.
+__global__ void __launch_bounds__(256) fpa_halo_exchange_kernel(__nv_bfloat16* __restrict__ x, int C, const srk_panel* __restrict__ panels,
+                                                                int n_img, int H, int W, int max_cols) {
+  const int cpr = C / 8;  // 16-byte chunks per pixel row
+  const int Wp = W + 1;
+  const int64_t S = int64_t(H + 1) * Wp;
+  const int64_t total = int64_t(n_img) * H * max_cols * cpr;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
+    const int ch = int(idx % cpr);
+    int64_t r = idx / cpr;
+    const int j = int(r % max_cols);
+    r /= max_cols;
+    const int y = int(r % H), i = int(r / H);
+    const srk_panel e = panels[i];
+    const int n_left = e.own_x0, n_right = W - e.own_x1;
+    int xcol, src_img;
+    if (j < n_left) {
+      xcol = j;
+      src_img = i - 1;
+    } else if (j - n_left < n_right) {
+      xcol = e.own_x1 + (j - n_left);
+      src_img = i + 1;
+    } else {
+      continue;
+    }
+    if (src_img < 0 || src_img >= n_img) continue;
+    const srk_panel s = panels[src_img];
+    if (s.frame != e.frame || s.y0 != e.y0) continue;  // frame edge of the band: keep what the layer computed
+    const int sx = e.x0 + xcol - s.x0;
+    if (sx < s.own_x0 || sx >= s.own_x1) continue;     // not owned by the direct neighbour (cannot happen for plan_tiles output)
+    const uint4* src = reinterpret_cast<const uint4*>(x + (int64_t(src_img) * S + int64_t(y + 1) * Wp + sx) * C) + ch;
+    uint4* dst = reinterpret_cast<uint4*>(x + (int64_t(i) * S + int64_t(y + 1) * Wp + xcol) * C) + ch;
+    *dst = *src;
+  }
+}
+
+extern "C" int srk_fpa_halo_exchange(srk_handle_t h, void* x_fpa, int C, const srk_panel* panels, int n_img, int H, int W, int max_cols,
+                                     srk_stream_t stream) {
+  SRK_REQUIRE(h && x_fpa && panels && C % 8 == 0 && max_cols > 0, "srk_fpa_halo_exchange: bad argument");
+  const int64_t total = int64_t(n_img) * H * max_cols * (C / 8);
+  const int grid = int(std::min<int64_t>((total + 255) / 256, int64_t(h->num_sms) * 8));
+  fpa_halo_exchange_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<__nv_bfloat16*>(x_fpa), C, panels, n_img, H, W, max_cols);
+  SRK_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int srk_fpa_to_nhwc(srk_handle_t h, const void* x_fpa, int C, int n_img, int H, int W, float* y, srk_stream_t stream) {
   SRK_REQUIRE(h && x_fpa && y, "srk_fpa_to_nhwc: null argument");
   const int64_t total = int64_t(n_img) * H * W * C;

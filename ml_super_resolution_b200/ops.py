@@ -91,6 +91,13 @@ def fpa_to_nhwc(a: Fpa) -> torch.Tensor:
     return y
 
 
+def fpa_halo_exchange(a: Fpa, panels: torch.Tensor, max_cols: int) -> Fpa:
+    """Refresh in place every column a panel does not own from the neighbouring panel that owns it (srk_fpa_halo_exchange)."""
+    check(_ffi.lib().srk_fpa_halo_exchange(handle(), _ptr(a.data), a.C, _ptr(panels), a.n_img, a.H, a.W, max_cols, _stream()),
+          "srk_fpa_halo_exchange")
+    return a
+
+
 def make_panels(entries, device="cuda") -> torch.Tensor:
     """entries: iterable of (frame, y0, x0, own_y0, own_y1, own_x0, own_x1) -> int32 [n,8] device tensor."""
     arr = np.zeros((len(entries), 8), np.int32)

@@ -58,9 +58,12 @@ def _split_axis(size: int, halo: int, max_len: int | None):
     return length, out
 
 
-def plan_tiles(n_frames: int, FH: int, FW: int, halo: int, max_w: int | None = MAX_PANEL_W, max_h: int | None = None):
-    """Returns (Ht, Wt, [Tile...]): every tile is Ht x Wt, inside the frame, owned rects partition it."""
-    Wt, xs = _split_axis(FW, halo, max_w)
+def plan_tiles(n_frames: int, FH: int, FW: int, halo: int, max_w: int | None = MAX_PANEL_W, max_h: int | None = None,
+               halo_x: int | None = None):
+    """Returns (Ht, Wt, [Tile...]): every tile is Ht x Wt, inside the frame, owned rects partition it.
+    `halo_x` (default: `halo`) is the column overlap radius: 1 when the panels of a band exchange their seam columns after
+    every layer (`srk_fpa_halo_exchange`) instead of recomputing a receptive-field halo."""
+    Wt, xs = _split_axis(FW, halo if halo_x is None else halo_x, max_w)
     Ht, ys = _split_axis(FH, halo, max_h)
     tiles = []
     for f in range(n_frames):

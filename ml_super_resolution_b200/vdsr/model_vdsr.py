@@ -89,14 +89,15 @@ class VdsrNet:
 
     # ------------------------------------------------------------------ inference
     def forward(self, sd: torch.Tensor, taps: dict | None = None, out: torch.Tensor | None = None, tile_rows: int | None = None,
-                rank: int = 0, world: int = 1) -> torch.Tensor:
+                rank: int = 0, world: int = 1, max_panel_w: int = MAX_PANEL_W) -> torch.Tensor:
         """sd fp32 [N,H,W,C] on device -> sr.  Frames wider than 254 px (or taller than `tile_rows`) are
         cut into halo-overlapped tiles; with world > 1 this rank computes only its shard of the tiles
         (tile-sharded multi-GPU inference, no collective; pixels it does not own are left untouched)."""
         n, H, W, C = sd.shape
         assert C == self.C
         a = self.arena
-        need_tiles = W > MAX_PANEL_W or (tile_rows is not None and H > tile_rows) or world > 1
+        assert max_panel_w <= MAX_PANEL_W
+        need_tiles = W > max_panel_w or (tile_rows is not None and H > tile_rows) or world > 1
         if out is None:
             out = torch.empty_like(sd)
         if not need_tiles:
@@ -113,11 +114,23 @@ class VdsrNet:
                 taps[f"conv.{self.L}"] = out - sd
             return out
         assert taps is None, "feature-map taps are only available for un-tiled frames"
-        Ht, Wt, tiles = plan_tiles(n, H, W, halo=self.L, max_w=MAX_PANEL_W, max_h=tile_rows)
-        tiles = shard_tiles(tiles, rank, world)
+        # Column seams: panels of one band overlap by one column per side and swap their seam columns after every layer
+        # (srk_fpa_halo_exchange) instead of recomputing a 20-px halo (16 % more pixels at 252-px panels).  That needs all
+        # panels of a band in this rank's shard and in one launch group; otherwise fall back to the receptive-field halo.
+        Ht, Wt, tiles = plan_tiles(n, H, W, halo=self.L, max_w=max_panel_w, max_h=tile_rows, halo_x=1)
+        per_band = len({t.x0 for t in tiles})
+        mine = shard_tiles(tiles, rank, world)
+        group = self._tile_group_size(Ht, Wt)
+        lo = (rank * len(tiles)) // world
+        exchange = per_band > 1 and lo % per_band == 0 and len(mine) % per_band == 0 and group >= len(mine)
+        if not exchange:
+            Ht, Wt, tiles = plan_tiles(n, H, W, halo=self.L, max_w=max_panel_w, max_h=tile_rows)
+            mine = shard_tiles(tiles, rank, world)
+            group = self._tile_group_size(Ht, Wt)
+        tiles = mine
         if not tiles:
             return out
-        group = self._tile_group_size(Ht, Wt)
+        max_cols = max(max(t.own_x0, Wt - t.own_x1) for t in tiles) * 2 if exchange else 0
         for g0 in range(0, len(tiles), group):
             chunk = tiles[g0:g0 + group]
             key = (tuple(t.as_tuple() for t in chunk), str(sd.device))
@@ -125,8 +138,12 @@ class VdsrNet:
             bufs = self._get_infer_bufs(len(chunk), Ht, Wt)
             t = ops.conv_first_tc(sd, self.wf(0), a.view(self._bname(0)), 3, "SAME", "relu", panels=panels, panel_hw=(Ht, Wt),
                                   out=bufs[0])
+            if exchange:  # the gather pads a panel's window edge with zeros: its seam columns come from the neighbour too
+                ops.fpa_halo_exchange(t, panels, max_cols)
             for i in range(1, self.L - 1):
                 t = ops.conv_tc(t, self.wf(i), a.view(self._bname(i)), 3, "relu", out=bufs[i % 2])
+                if exchange:
+                    ops.fpa_halo_exchange(t, panels, max_cols)
             ops.conv_tc_last(t, self.wf(self.L - 1), self.bias_last, 3, self.C, None, addend=sd, panels=panels, frame_shape=(n, H, W),
                              out=out)
         return out

@@ -64,6 +64,19 @@ def test_vdsr_tiled_equals_untiled_and_oracle(srk_ops):
     net.forward(x, out=out, tile_rows=40, rank=0, world=2)
     net.forward(x, out=out, tile_rows=40, rank=1, world=2)
     assert np.array_equal(out.cpu().numpy(), full)
+    # column panels that swap their seam columns after every layer (no recomputed halo): still bit-identical, alone, combined
+    # with row bands, and sharded band-wise over two ranks
+    assert np.array_equal(net.forward(x, max_panel_w=80).cpu().numpy(), full)
+    assert np.array_equal(net.forward(x, max_panel_w=72, tile_rows=56).cpu().numpy(), full)
+    out = torch.full_like(x, float("nan"))
+    net.forward(x, out=out, max_panel_w=72, tile_rows=56, rank=0, world=2)
+    net.forward(x, out=out, max_panel_w=72, tile_rows=56, rank=1, world=2)
+    assert np.array_equal(out.cpu().numpy(), full)
+    # a shard that splits a band falls back to receptive-field halos
+    out = torch.full_like(x, float("nan"))
+    for r in range(3):
+        net.forward(x, out=out, max_panel_w=80, rank=r, world=3)
+    assert np.array_equal(out.cpu().numpy(), full)
     # wide frame (column panels) against the oracle
     sdw = OM.synthetic_images(78, 1, 24, 600, 3)
     got = net.forward(torch.from_numpy(sdw).cuda()).cpu().numpy()
