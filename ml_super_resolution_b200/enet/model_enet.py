@@ -27,7 +27,7 @@ from .. import ops
 from ..initializers import ENET_G_LAYERS, enet_g_params, tf_conv_name
 from ..params import ParamArena
 from ..session import Handle
-from ..tiling import MAX_PANEL_W
+from ..tiling import MAX_PANEL_W, plan_tiles, shard_tiles
 
 
 class EnetGenerator:
@@ -68,23 +68,59 @@ class EnetGenerator:
         self.plan.run(self.arena.w)
         self.bias_last[:3].copy_(self.arena.view(self._b(len(ENET_G_LAYERS) - 1)))
 
-    def forward(self, sd: torch.Tensor, bq: torch.Tensor) -> torch.Tensor:
-        """sd fp32 [N,h,w,3], bq fp32 [N,4h,4w,3] -> sr = bq + generator(sd)."""
+    HALO = 13  # receptive-field radius in LR pixels: row bands recompute it, column panels exchange seams
+
+    def forward(self, sd: torch.Tensor, bq: torch.Tensor, out: torch.Tensor | None = None, tile_rows: int | None = None,
+                rank: int = 0, world: int = 1, max_panel_w: int = MAX_PANEL_W // 4) -> torch.Tensor:
+        """sd fp32 [N,h,w,3], bq fp32 [N,4h,4w,3] -> sr = bq + generator(sd).
+        Frames wider than 63 LR pixels (252 HR) are cut into column panels that swap their seam columns after every 3x3 layer
+        at all three resolutions (`srk_fpa_halo_exchange`), frames taller than `tile_rows` LR rows into row bands with a 13-px
+        halo; with world > 1 this rank computes whole bands of the tile list and writes only the pixels it owns."""
         n, h, w, _ = sd.shape
-        assert 4 * w <= MAX_PANEL_W, "EnhanceNet frames wider than 63 LR px need tiling (13-px LR halo) -- not wired up yet"
+        assert max_panel_w <= MAX_PANEL_W // 4
         a, W = self.arena, self.plan.views
-        t = ops.conv_first_tc(sd, W[self._idx[0]], a.view(self._b(0)), 3, "SAME", "relu")
+        if out is None:
+            out = torch.empty_like(bq)
+        need_tiles = w > max_panel_w or (tile_rows is not None and h > tile_rows) or world > 1
+        panels = [None, None, None]
+        max_cols = 0
+        if need_tiles:
+            Ht, Wt, tiles = plan_tiles(n, h, w, halo=self.HALO, max_w=max_panel_w, max_h=tile_rows, halo_x=1)
+            per_band = len({t.x0 for t in tiles})
+            lo = (rank * len(tiles)) // world
+            tiles = shard_tiles(tiles, rank, world)
+            assert lo % per_band == 0 and len(tiles) % per_band == 0, "a rank's shard must consist of whole row bands of panels"
+            if not tiles:
+                return out
+            key = (tuple(t.as_tuple() for t in tiles), str(sd.device))
+            cache = self.__dict__.setdefault("_panels", {})
+            if key not in cache:
+                cache[key] = [ops.make_panels([(t.frame,) + tuple(s * v for v in t.as_tuple()[1:]) for t in tiles], self.device)
+                              for s in (1, 2, 4)]
+            panels = cache[key]
+            max_cols = 2 * max(max(t.own_x0, Wt - t.own_x1) for t in tiles)
+            n_img, hh, ww = len(tiles), Ht, Wt
+        else:
+            n_img, hh, ww = n, h, w
+
+        def seam(t, level):  # refresh the panels' non-owned columns after a 3x3 layer
+            if need_tiles and max_cols > 0:
+                ops.fpa_halo_exchange(t, panels[level], max_cols << level)
+            return t
+
+        t = seam(ops.conv_first_tc(sd, W[self._idx[0]], a.view(self._b(0)), 3, "SAME", "relu", panels=panels[0],
+                                   panel_hw=(hh, ww) if need_tiles else None), 0)
         i = 1
         for _ in range(10):
-            x = ops.conv_tc(t, W[self._idx[i]], a.view(self._b(i)), 3, "relu")
+            x = seam(ops.conv_tc(t, W[self._idx[i]], a.view(self._b(i)), 3, "relu"), 0)
             t = ops.conv_tc(x, W[self._idx[i + 1]], a.view(self._b(i + 1)), 1, None, addend=t, relu_after_add=True)
             i += 2
-        for _ in range(2):
-            t = ops.conv_tc(ops.fpa_upsample2(t), W[self._idx[i]], a.view(self._b(i)), 3, "relu")
+        for level in (1, 2):
+            t = seam(ops.conv_tc(ops.fpa_upsample2(t), W[self._idx[i]], a.view(self._b(i)), 3, "relu"), level)
             i += 1
-        t = ops.conv_tc(t, W[self._idx[i]], a.view(self._b(i)), 3, "relu")
-        return ops.conv_tc_last(t, W[self._idx[i + 1]], self.bias_last, 3, 3, None, addend=bq)
-
+        t = seam(ops.conv_tc(t, W[self._idx[i]], a.view(self._b(i)), 3, "relu"), 2)
+        return ops.conv_tc_last(t, W[self._idx[i + 1]], self.bias_last, 3, 3, None, addend=bq, panels=panels[2],
+                                frame_shape=(n, 4 * h, 4 * w) if need_tiles else None, out=out)
 
     # ------------------------------------------------------------------------------------------ training
     def _enable_training(self, n, h, w):
