@@ -112,6 +112,7 @@ struct ConvTcCfg {
   static constexpr int kGroups = kSets * kHalves;   // lane-exchange groups (4 quadrant warps each): 16 epilogue warps
   static constexpr int kColPass = 16;               // accumulator columns a thread handles per pass
   static_assert(kGroups == 4, "named barriers 1..4 serve the exchange groups");
+  static_assert(kAccStages % kSets == 0, "an accumulator stage is always drained by the same epilogue set (barrier parities are waited in that set's tile order)");
   static constexpr int kEpiThreads = 128 * kGroups;
   static constexpr int kIssuers = 2;                // MMA issuer warps (tiles round-robin); must divide kAccStages so that
                                                     // an accumulator stage is always driven by the same issuer (its
@@ -813,10 +814,15 @@ struct ConvGatherCfg {
   static constexpr int kKP = (kKT + 15) / 16 * 16;
   static constexpr int kBlocks = (kKP + 63) / 64;       // 64-element K blocks (128-byte rows)
   static constexpr int kABytes = kBlocks * 128 * 128;    // one A stage
-  static constexpr int kAStages = kBlocks <= 2 ? 4 : 2;
+  // Gather groups take tiles round-robin; three groups (12 warps, 32 warps per CTA) where one 16 KB im2col stage per tile
+  // leaves room for six stages.  A stage must always be filled by the same group and consumed by the same MMA issuer
+  // (their barrier parities are waited in that role's own tile order): kAStages is a multiple of both counts.
+  static constexpr int kGatherGroups = kBlocks == 1 ? 3 : 2;
+  static constexpr int kAStages = kBlocks == 1 ? 6 : (kBlocks == 2 ? 4 : 2);
+  static_assert(kAStages % kGatherGroups == 0 && kAStages % 2 == 0, "stage ownership");
   static constexpr int kWBytes = kBlocks * 64 * 128;
   static constexpr int kAcc = 4;
-  static constexpr int kEpiThreads = 512, kGatherThreads = 128, kGatherGroups = 2;  // each group gathers every other tile
+  static constexpr int kEpiThreads = 512, kGatherThreads = 128;
   static constexpr int kThreads = 128 + kEpiThreads + kGatherGroups * kGatherThreads;
   static constexpr int kOffW = 0;
   static constexpr int kOffA = kWBytes;
@@ -962,32 +968,55 @@ __global__ void __launch_bounds__(ConvGatherCfg<KS, CIN>::kThreads, 1) conv_gath
           const int y = pyy - 1 - gp.po, x = px - gp.po;  // top-left source pixel (panel-local)
           const float* frame = gp.x + (int64_t(fn) * gp.FH + y0) * gp.FW * CIN + int64_t(x0) * CIN;
           uint8_t* arow = a_ptr + st * L::kABytes + r * 128;
-          // per-tap row/column validity and clamped offsets (KS each)
-          int rofs[KS], cofs[KS];
-          bool rok[KS], cok[KS];
+          const bool interior = y >= 0 && y + KS <= gp.Hin && x >= 0 && x + KS <= gp.Win;
+          if (interior) {
+            // every tap lies inside the panel window (all but the border pixels): plain loads at constant offsets from
+            // KS row pointers, no clamps and no selects
+            const float* row0 = frame + (int64_t(y) * gp.FW + x) * CIN;
+            const int rs = gp.FW * CIN;
 #pragma unroll
-          for (int u = 0; u < KS; ++u) {
-            const int sy = y + u, sx = x + u;
-            rok[u] = sy >= 0 && sy < gp.Hin;
-            cok[u] = sx >= 0 && sx < gp.Win;
-            rofs[u] = min(max(sy, 0), gp.Hin - 1) * gp.FW * CIN;
-            cofs[u] = min(max(sx, 0), gp.Win - 1) * CIN;
-          }
+            for (int c8 = 0; c8 < L::kKP / 8; ++c8) {
+              float f[8];
 #pragma unroll
-          for (int c8 = 0; c8 < L::kKP / 8; ++c8) {
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int k = c8 * 8 + j;
-              f[j] = 0.f;
-              if (k < L::kKT) {
-                const int tap = k / CIN, ci = k % CIN, u = tap / KS, v = tap % KS;
-                const float val = SRK_ABLATE(p, 128) ? float(k) : __ldg(frame + rofs[u] + cofs[v] + ci);
-                f[j] = (rok[u] && cok[v]) ? val : 0.f;
+              for (int j = 0; j < 8; ++j) {
+                const int k = c8 * 8 + j;
+                f[j] = 0.f;
+                if (k < L::kKT) {
+                  const int tap = k / CIN, ci = k % CIN, u = tap / KS, v = tap % KS;
+                  f[j] = __ldg(row0 + u * rs + v * CIN + ci);
+                }
               }
+              const uint4 q4 = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+              *reinterpret_cast<uint4*>(arow + (c8 / 8) * (128 * 128) + (((c8 % 8) ^ (r & 7)) << 4)) = q4;
             }
-            const uint4 q4 = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-            *reinterpret_cast<uint4*>(arow + (c8 / 8) * (128 * 128) + (((c8 % 8) ^ (r & 7)) << 4)) = q4;
+          } else {
+            // per-tap row/column validity and clamped offsets (KS each)
+            int rofs[KS], cofs[KS];
+            bool rok[KS], cok[KS];
+#pragma unroll
+            for (int u = 0; u < KS; ++u) {
+              const int sy = y + u, sx = x + u;
+              rok[u] = sy >= 0 && sy < gp.Hin;
+              cok[u] = sx >= 0 && sx < gp.Win;
+              rofs[u] = min(max(sy, 0), gp.Hin - 1) * gp.FW * CIN;
+              cofs[u] = min(max(sx, 0), gp.Win - 1) * CIN;
+            }
+#pragma unroll
+            for (int c8 = 0; c8 < L::kKP / 8; ++c8) {
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int k = c8 * 8 + j;
+                f[j] = 0.f;
+                if (k < L::kKT) {
+                  const int tap = k / CIN, ci = k % CIN, u = tap / KS, v = tap % KS;
+                  const float val = __ldg(frame + rofs[u] + cofs[v] + ci);
+                  f[j] = (rok[u] && cok[v]) ? val : 0.f;
+                }
+              }
+              const uint4 q4 = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+              *reinterpret_cast<uint4*>(arow + (c8 / 8) * (128 * 128) + (((c8 % 8) ^ (r & 7)) << 4)) = q4;
+            }
           }
         }
         fence_proxy_async_smem();
