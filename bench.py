@@ -459,13 +459,13 @@ def enet_train_workload(args, rank, world):
     a = net.arena
     t = [0]
 
-    def step():
-        # forward_backward needs d(sr): one generator forward feeds the loss kernel, then forward+backward (the forward is
-        # recomputed inside: 1/3 of the step's FLOPs; a fused loss hook would remove it)
-        sr = net.forward(sd, bq)
+    def loss_head(sr):  # runs between the generator's forward and backward passes
         loss.zero_()
         ops.mse_fwd_bwd(sr, hd, loss, dsr)
-        net.forward_backward(sd, bq, dsr)
+        return dsr
+
+    def step():
+        net.forward_backward(sd, bq, loss_head)
         if world > 1:
             torch.distributed.all_reduce(a.g)
         t[0] += 1
@@ -476,10 +476,10 @@ def enet_train_workload(args, rank, world):
     net.forward_backward(sd, bq, hd)  # allocate the training buffers outside the timed region
     ms, clocks = timed_steps(step, args.steps, args.warmup, world, ClockSampler(torch.cuda.current_device()) if rank == 0 else None)
     value = ENET_BATCH * world * args.steps / ms * 1e3
-    flops_per_patch = 3.617e9 * 4  # fwd (loss) + fwd + dgrad + wgrad, SURVEY 8 row a5: 3.617 GFLOP fwd/patch
+    flops_per_patch = 3.617e9 * 3  # fwd + dgrad + wgrad, SURVEY 8 row a5: 3.617 GFLOP fwd/patch
     pk = peaks()
     tf = value * flops_per_patch / 1e12 / world
-    roofline = {"bound": "tensor", "kernel": "whole generator step (25 fwd + 24 dgrad + 25 wgrad tcgen05 convs, forward run twice)", "achieved": round(tf, 1),
+    roofline = {"bound": "tensor", "kernel": "whole generator step (25 fwd + 24 dgrad + 25 wgrad tcgen05 convs)", "achieved": round(tf, 1),
                 "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": round(tf / pk["tf_sust"], 4), "traffic": None, "peak_source": pk["src"]}
     n_launch = launches_of(step) * args.steps
     sd_h, bq_h, hd_h = sd.cpu().pin_memory(), bq.cpu().pin_memory(), hd.cpu().pin_memory()
@@ -537,7 +537,7 @@ def run_reference(args, rank, world):
     elif args.workload == "enet_train":
         steps = max(1, min(args.steps, 3))
         v, dt = enet_train_cpu(steps, threads)
-        unit, metric, sample = "patches/s", "EnhanceNet generator training patches/s", f"{steps} fwd+bwd step(s) of 4 32x32->128x128 patches (GPU arm: 64/step, + loss forward + Adam)"
+        unit, metric, sample = "patches/s", "EnhanceNet generator training patches/s", f"{steps} fwd+bwd step(s) of 4 32x32->128x128 patches (GPU arm: 64/step, + MSE head + Adam)"
         cfg = {"workload": "EnhanceNet generator forward+backward, synthetic 32x32->128x128 patches (CPU restatement, torch-CPU fp32 autograd)"}
     elif args.workload == "srcnn_train":
         steps = max(1, min(args.steps, 10))

@@ -167,9 +167,10 @@ class EnetGenerator:
         self._tb["plan"].run(a.w)
         return self._tb
 
-    def forward_backward(self, sd: torch.Tensor, bq: torch.Tensor, dsr: torch.Tensor):
-        """Generator forward, then its backward for the upstream gradient dsr = d(loss)/d(sr): fills the gradient arena
-        (`arena.g`, every kernel and bias of the 25 layers) and returns sr."""
+    def forward_backward(self, sd: torch.Tensor, bq: torch.Tensor, dsr):
+        """Generator forward, then its backward for the upstream gradient d(loss)/d(sr): fills the gradient arena
+        (`arena.g`, every kernel and bias of the 25 layers) and returns sr.  `dsr` is that gradient as a tensor, or a
+        callable `dsr = f(sr)` evaluated on the forward result (the loss head), so one forward serves loss and backward."""
         n, h, w, _ = sd.shape
         assert 4 * w <= MAX_PANEL_W
         b, a = self._enable_training(n, h, w), self.arena
@@ -188,6 +189,8 @@ class EnetGenerator:
         ops.conv_tc(b["u2"], V[fw[22]], bias(22), 3, "relu", out=b["m2"])
         ops.conv_tc(b["m2"], V[fw[23]], bias(23), 3, "relu", out=b["m3"])
         ops.conv_tc_last(b["m3"], V[fw[24]], self.bias_last, 3, 3, None, addend=bq, out=b["sr"])
+        if callable(dsr):
+            dsr = dsr(b["sr"])
         # ---- backward
         ws, st = b["ws"], b["st"]
         slot = {"hi": 0, "mid": 0, "lo": 0}
