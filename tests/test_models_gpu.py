@@ -258,6 +258,11 @@ def test_srcnn_train_step_matches_oracle(srk_ops, channels, S, batch):
     # the inference path sees the trained parameters
     sr = net.forward(net.degrade(hit)).cpu().numpy()
     assert np.abs(sr - OM.srcnn_forward(p64, lo)).max() <= TOL_BF16
+    # CUDA-graph replay of the step follows the eager trajectory (same kernels; only atomics order may differ)
+    net2 = SrcnnNet(params, channels)
+    gstep = net2.make_graphed_step(hit.clone())
+    graphed = [float(gstep(1e-3)) for _ in range(4)]
+    assert np.allclose(graphed, ours, rtol=2e-3), (graphed, ours)
 
 
 def test_enet_generator_backward_matches_oracle(srk_ops):
