@@ -235,3 +235,15 @@ def test_first_and_last_layer_wgrad(srk_ops):
     _, gw2, gb2 = O.conv2d_backward(x2, np.zeros((3, 3, 64, 3)), np.zeros(3), dy2, "SAME", None)
     np.testing.assert_allclose(dw2.cpu().numpy(), gw2, rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(db2.cpu().numpy(), gb2, rtol=1e-4, atol=1e-5)
+
+
+def test_random_shape_sweep(srk_ops):
+    """25 random geometries (1..5 images, 3..1500 rows, 3..253 columns) through the 64->64, 64->32, 1x1, last-layer, first-layer
+    and weight-gradient kernels against torch conv2d on the same bf16-rounded operands: covers 1-tile CTAs, panels at
+    the width limit and the barrier round-robins (tools/stress_conv.py)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "stress_conv.py"), "7", "25"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "stress OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
