@@ -314,6 +314,15 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
     for (int pass = 0; pass < PASSES; ++pass) {
       const int col0 = (half * PASSES + pass) * CP;
       const uint32_t taddr = tmem + acc * KN + col0 + (uint32_t(quad * 32) << 16);
+      // data-gradient mask (saved activation of the producing layer): requested before the accumulator is read so that its
+      // L2 latency hides under the TMEM loads, the lane exchange and the shuffles
+      uint4 mpre[CP >= 8 ? CP / 8 : 1];
+      const bool mask_fast = EPI == EPI_FPA && p.mask_src && p.mask_kind == SRK_ACT_RELU && !p.addend_fpa && valid;
+      if (mask_fast) {
+        const uint4* m = reinterpret_cast<const uint4*>(p.mask_src + size_t(prow) * NP + col0);
+#pragma unroll
+        for (int j = 0; j < CP / 8; ++j) mpre[j] = __ldg(m + j);
+      }
       float blk[KS][CP];
 #pragma unroll
       for (int b = 0; b < KS; ++b) {
@@ -458,11 +467,10 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, const EpiCt
                 pk[c] = *reinterpret_cast<const uint32_t*>(&h);
               }
             }
-            if (p.mask_src) {
-              const uint4* m = reinterpret_cast<const uint4*>(p.mask_src + size_t(prow) * NP + col0);
+            if (mask_fast) {
 #pragma unroll
               for (int j = 0; j < CP / 8; ++j) {
-                const uint4 mv = __ldg(m + j);
+                const uint4 mv = mpre[j];
                 const uint32_t w4[4] = {mv.x, mv.y, mv.z, mv.w};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
