@@ -246,6 +246,37 @@ __global__ void fpa_to_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int C, i
     y[i] = __bfloat162float(x[(n * S + int64_t(yy + 1) * Wp + xx) * C + c]);
   }
 }
+// Cp % 8 == 0: one thread converts 8 channels of one pixel row and writes them with a single 16-byte store
+__global__ void __launch_bounds__(256) nhwc_to_fpa_vec8_kernel(const float* __restrict__ x, int C, int Cp, int n_img, int H, int W,
+                                                               int64_t rows_valid, uint4* __restrict__ y) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int cpr = Cp / 8;
+  const int64_t total = rows_valid * cpr;
+  const uint32_t Wp = W + 1, H1 = H + 1;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const uint32_t prow = uint32_t(i / cpr);  // rows_valid < 2^31 (checked by the caller)
+    const int c0 = int(i - int64_t(prow) * cpr) * 8;
+    const uint32_t q = prow / Wp, xx = prow - q * Wp;
+    const uint32_t n = q / H1, yy = q - n * H1;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = 0.f;
+    if (xx < uint32_t(W) && yy > 0 && c0 < C) {
+      const float* src = x + ((int64_t(n) * H + (yy - 1)) * int64_t(W) + xx) * C;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c0 + j < C) f[j] = __ldg(src + c0 + j);
+    }
+    uint4 o;
+    __nv_bfloat162 h;
+    h = __floats2bfloat162_rn(f[0], f[1]); o.x = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(f[2], f[3]); o.y = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(f[4], f[5]); o.z = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(f[6], f[7]); o.w = *reinterpret_cast<uint32_t*>(&h);
+    y[i] = o;
+  }
+}
 __global__ void nhwc_to_fpa_kernel(const float* __restrict__ x, int C, int Cp, int n_img, int H, int W, int64_t rows_valid,
                                    __nv_bfloat16* __restrict__ y) {
   pdl_wait();
@@ -504,6 +535,13 @@ extern "C" int srk_fpa_to_nhwc(srk_handle_t h, const void* x_fpa, int C, int n_i
 extern "C" int srk_nhwc_to_fpa_pad(srk_handle_t h, const float* x, int C, int Cp, int n_img, int H, int W, void* y_fpa, srk_stream_t stream) {
   SRK_REQUIRE(h && x && y_fpa && Cp >= C && C > 0, "srk_nhwc_to_fpa_pad: bad argument");
   const FpaGeom g = fpa_geom(n_img, H, W);
+  if (Cp % 8 == 0 && g.rows_valid < (int64_t(1) << 31)) {
+    const int64_t total8 = g.rows_valid * (Cp / 8);
+    const int grid8 = int(std::min<int64_t>((total8 + 255) / 256, int64_t(h->num_sms) * 16));
+    SRK_CHECK_CUDA(launch_pdl(nhwc_to_fpa_vec8_kernel, dim3(grid8), dim3(256), 0, as_stream(stream), x, C, Cp, n_img, H, W, g.rows_valid,
+                              static_cast<uint4*>(y_fpa)));
+    return 0;
+  }
   const int64_t total = g.rows_valid * Cp;
   const int grid = int(std::min<int64_t>((total + 255) / 256, int64_t(h->num_sms) * 16));
   SRK_CHECK_CUDA(launch_pdl(nhwc_to_fpa_kernel, dim3(grid), dim3(256), 0, as_stream(stream), x, C, Cp, n_img, H, W, g.rows_valid,
