@@ -64,8 +64,12 @@ __global__ void pack_weights_batched_kernel(const float* __restrict__ arena, con
   for (int i = threadIdx.x; i < n_jobs; i += blockDim.x) s_jobs[i] = jobs[i];
   __syncthreads();
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-    int j = 0;
-    while (j + 1 < n_jobs && s_jobs[j + 1].elem_begin <= i) ++j;
+    int j = 0, hi = n_jobs - 1;  // last job whose first element is <= i (binary search: a model has up to ~50 jobs)
+    while (j < hi) {
+      const int mid = (j + hi + 1) >> 1;
+      if (s_jobs[mid].elem_begin <= i) j = mid;
+      else hi = mid - 1;
+    }
     const srk_pack_job jb = s_jobs[j];
     const int e = int(i - jb.elem_begin);
     const float* w = arena + jb.src_offset;
