@@ -15,10 +15,10 @@ from ml_super_resolution_b200.espcn.model_espcn import EspcnNet  # noqa: E402
 from ml_super_resolution_b200.tiling import plan_tiles  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else "f2"
-sets = 2 if which in ("c64", "f1") else 4
+sets = 2 if which in ("c64", "f1", "train") else 4
 g = torch.Generator(device="cuda").manual_seed(0)
-if which == "c64":
-    N, H, W = 64, 240, 240
+if which in ("c64", "train"):
+    N, H, W = (64, 240, 240) if which == "c64" else (64, 41, 41)
     x = ops.fpa_empty(N, H, W, 64)
     x.data.normal_(generator=g)
     y = ops.fpa_empty(N, H, W, 64)
@@ -53,6 +53,16 @@ rc = raw.srk_debug_trace_read(buf.ctypes.data_as(C.c_void_p))
 assert rc == 0, rc
 T = buf.reshape(24, 256).astype(np.int64)
 t0 = T[3, 0]
+if which == "train":
+    nt = int((T[3] > 0).sum())
+    k0 = T[20, 0]
+    print(f"train shape: CTA 0 has {nt} tiles; cycles from kernel entry: pdl_wait passed {T[20,1]-k0}, weights+first data -> first MMA issued {T[2,0]-k0}, "
+          f"first commit {T[3,0]-k0}, first acc full {T[4,0]-k0}, last commit {T[3,nt-1]-k0}, last tile epilogue done {T[7,nt-1]-k0}, "
+          f"last store freed {T[9,nt-1]-k0}, CTA exit {T[20,2]-k0}")
+    print("  tile 0 seen ready at", int(T[1, 0] - k0), "; chunk TMA issue times:", [int(T[0, i] - k0) for i in range(10) if T[0, i]])
+    print("  per-tile commit times:", [int(T[3, i] - k0) for i in range(nt)])
+    print("  per-tile epilogue done:", [int(T[7, i] - k0) for i in range(nt)])
+    sys.exit(0)
 names = ["load-issued(chunk)", "mma:data-ready", "mma:acc-free", "mma:committed", "epi:acc-full", "epi:tmem-read", "epi:passes-done",
          "epi:tile-done", "store:staged", "store:freed"]
 lo, hi = 24, 48
