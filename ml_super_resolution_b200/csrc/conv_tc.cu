@@ -657,8 +657,10 @@ __global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS, EPI>::kThreads, 1) conv
     tma_prefetch_desc(&p.map_w);
     if (EPI == EPI_FPA) tma_prefetch_desc(&p.map_out);
   }
+  if (threadIdx.x == 0) SRK_TRACE_EV(20, 0);
   pdl_wait();               // predecessor kernels are complete and their writes visible from here on
   pdl_launch_dependents();  // the next kernel may start filling SMs as our CTAs retire
+  if (threadIdx.x == 0) SRK_TRACE_EV(20, 1);
   if (threadIdx.x < NP) s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
   if (EPI == EPI_NHWC && threadIdx.x < NP) {
     // output offset of packed channel c relative to pixel (Y*r, X*r, 0): depth_to_space index, -1 = padding channel
@@ -798,6 +800,7 @@ __global__ void __launch_bounds__(ConvTcCfg<CIN, NP, KS, EPI>::kThreads, 1) conv
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) SRK_TRACE_EV(20, 2);
   if (warp == 1) tmem_dealloc<L::kTmemCols>(tmem);
 }
 
