@@ -290,7 +290,30 @@ def vdsr_train_workload(args, rank, world):
     ms_e, _ = timed_steps(e2e_step, max(2, args.steps // 2), 2, world, None)
     e2e = {"value": round(TRAIN_BATCH * world * max(2, args.steps // 2) / ms_e * 1e3, 1), "unit": "patches/s",
            "h2d_bytes_per_step": 2 * sd_h.numel() * 4, "d2h_bytes_per_step": 4}
+    # ---- the same step fed by the device-resident input pipeline (crop + flip + degrade from a uint8 image
+    # pool in HBM, prefetched on a side stream) instead of a fixed batch; and the pipeline alone
+    from ml_super_resolution_b200.vdsr import dataset as D
+    rs = np.random.RandomState(7 + rank)
+    pool = D.DevicePool([rs.randint(0, 256, (256, 256, 3)).astype(np.uint8) for _ in range(64)])
+    gen = D.image_batches(pool, [2.0, 3.0, 4.0], TRAIN_PATCH, TRAIN_BATCH, rng=rs)
+
+    def fed_step():
+        s_, h_ = next(gen)
+        sd.copy_(s_)
+        hd.copy_(h_)
+        gstep(5e-5)
+
+    def pipe_step():
+        next(gen)
+
+    n_fed = max(5, args.steps // 2)
+    ms_fed, _ = timed_steps(fed_step, n_fed, 3, world, None)
+    ms_pipe, _ = timed_steps(pipe_step, n_fed, 3, world, None)
+    pipeline = {"train_patches_per_s_fed_by_device_pipeline": round(TRAIN_BATCH * world * n_fed / ms_fed * 1e3, 1),
+                "pipeline_alone_patches_per_s": round(TRAIN_BATCH * world * n_fed / ms_pipe * 1e3, 1),
+                "pool": "64 synthetic 256x256x3 uint8 images resident in HBM; host draws the reference's random crops / flips / scales"}
     cfg = {"workload": f"VDSR-20 3x3-64 residual training, {TRAIN_BATCH} synthetic 41x41x3 patches/GPU, blur+bilinear 2/3/4x degrade, Adam",
+           "input_pipeline": pipeline,
            "global_batch": TRAIN_BATCH * world, "parallelism": f"dp{world}", "l2_policy": "saved activations 19 x 14.5 MB = 275 MB per step > 126 MB L2"}
     return dict(metric="VDSR-20 training patches/s", value=round(value, 1), unit="patches/s", ms=ms, clocks=clocks, roofline=roofline, e2e=e2e,
                 gpu_launches=n_launch, config=cfg, scaling="weak")
@@ -638,6 +661,13 @@ def main():
             if args.workload == "vdsr_train":
                 v, dt = vdsr_train_cpu(3, threads)
                 cpu = {"value": round(v, 2), "unit": "patches/s", "cores": threads, "kind": "port", "sample": f"3 fwd+bwd steps of 64 patches, {dt:.1f} s"}
+                from oracle import ops as O  # the reference's python input generator (numpy restatement), single-threaded as in the reference
+                rs = np.random.RandomState(7)
+                imgs = [rs.randint(0, 256, (256, 256, 3)).astype(np.uint8) for _ in range(8)]
+                g_cpu = O.vdsr_image_batches(imgs, [2.0, 3.0, 4.0], TRAIN_PATCH, TRAIN_BATCH, rs)
+                t0 = time.perf_counter()
+                next(g_cpu)
+                cpu["input_generator_patches_per_s"] = round(TRAIN_BATCH / (time.perf_counter() - t0), 1)
         line = {"metric": res["metric"], "value": res["value"], "unit": res["unit"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": round(res["ms"] / args.steps, 4), "higher_is_better": True, "scaling": res["scaling"], "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic", "config": res["config"], "clocks": res["clocks"], "e2e": res["e2e"],

@@ -174,6 +174,22 @@ int srk_pixel_unshuffle(srk_handle_t h, const float* x, int N, int H, int W, int
 /* TF1-legacy bicubic (A=-0.75, 1024-entry table, no half-pixel centres): srcnn/srcnn.py:89-93. */
 int srk_resize_bicubic_tf1(srk_handle_t h, const float* x, int N, int H, int W, int C, int OH, int OW,
                            float* y, srk_stream_t stream);
+/* Device-resident input pipeline: the training images stay in HBM as one uint8 pool; a batch is cut
+ * out of it by the same steps the reference's python generator performs per sample (vdsr/vdsr/dataset.py:95-116): random
+ * crop [y:y+S, x:x+S], optional horizontal flip, img_as_float32 (x/255), then -- after the degrade below -- x*2-1.
+ * out01 (optional) receives the [0,1] patch that srk_degrade_gauss_bilinear consumes, out_pm1 (optional) the [-1,1] one. */
+typedef struct {
+  int64_t offset;        /* byte offset of pixel (0,0,0) in the pool */
+  int32_t height, width; /* channels = C of the call */
+} srk_pool_image;
+typedef struct {
+  int32_t image, y, x, flip;
+} srk_crop;
+int srk_crop_flip_u8(srk_handle_t h, const uint8_t* pool, const srk_pool_image* images_device, const srk_crop* crops_device,
+                     int n, int S, int C, float* out01, float* out_pm1, srk_stream_t stream);
+/* y = x*a + b with two fp32 roundings (numpy semantics of `sd_image * 2.0 - 1.0`, vdsr/vdsr/dataset.py:113-115); y may be x. */
+int srk_affine_f32(srk_handle_t h, const float* x, size_t n, float a, float b, float* y, srk_stream_t stream);
+
 /* VDSR degrade pre-pass: gaussian(sigma=0.5(s-1), replicate) -> bilinear down to int(H/s) x int(W/s)
  * -> bilinear up (half-pixel, edge clamp), per-sample scale: vdsr/vdsr/dataset.py:13-38. */
 int srk_degrade_gauss_bilinear(srk_handle_t h, const float* hd, int N, int H, int W, int C,

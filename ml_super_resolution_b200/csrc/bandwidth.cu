@@ -382,6 +382,50 @@ extern "C" int srk_resize_bicubic_tf1(srk_handle_t h, const float* x, int N, int
   return 0;
 }
 
+// ------------------------------------------------------------------------------------ device-resident input pipeline
+// One thread per output element: random crop + horizontal flip of a uint8 image that lives in a device pool, cast to
+// float the way skimage.util.img_as_float32 does (x / 255 in fp32), and optionally the [-1,1] mapping x*2-1 with the two
+// roundings numpy performs (no FMA contraction).
+__global__ void __launch_bounds__(256) crop_flip_u8_kernel(const uint8_t* __restrict__ pool, const srk_pool_image* __restrict__ images,
+                                                           const srk_crop* __restrict__ crops, int n, int S, int C,
+                                                           float* __restrict__ out01, float* __restrict__ out_pm1) {
+  const int64_t total = int64_t(n) * S * S * C;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % C);
+    int64_t r = i / C;
+    const int x = int(r % S);
+    r /= S;
+    const int y = int(r % S), b = int(r / S);
+    const srk_crop cr = crops[b];
+    const srk_pool_image im = images[cr.image];
+    const int sx = cr.flip ? (cr.x + S - 1 - x) : (cr.x + x);
+    const float v = __fdiv_rn(float(pool[im.offset + (int64_t(cr.y + y) * im.width + sx) * C + c]), 255.f);
+    if (out01) out01[i] = v;
+    if (out_pm1) out_pm1[i] = __fadd_rn(__fmul_rn(v, 2.f), -1.f);
+  }
+}
+__global__ void __launch_bounds__(256) affine_kernel(const float* __restrict__ x, size_t n, float a, float b, float* __restrict__ y) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+    y[i] = __fadd_rn(__fmul_rn(x[i], a), b);
+}
+
+extern "C" int srk_crop_flip_u8(srk_handle_t h, const uint8_t* pool, const srk_pool_image* images_device, const srk_crop* crops_device,
+                                int n, int S, int C, float* out01, float* out_pm1, srk_stream_t stream) {
+  SRK_REQUIRE(h && pool && images_device && crops_device && (out01 || out_pm1) && n > 0 && S > 0 && C > 0, "srk_crop_flip_u8: bad argument");
+  const int64_t total = int64_t(n) * S * S * C;
+  crop_flip_u8_kernel<<<grid_for(h, total, 256), 256, 0, as_stream(stream)>>>(pool, images_device, crops_device, n, S, C, out01, out_pm1);
+  SRK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int srk_affine_f32(srk_handle_t h, const float* x, size_t n, float a, float b, float* y, srk_stream_t stream) {
+  SRK_REQUIRE(h && x && y, "srk_affine_f32: null argument");
+  if (n == 0) return 0;
+  affine_kernel<<<grid_for(h, int64_t(n), 256), 256, 0, as_stream(stream)>>>(x, n, a, b, y);
+  SRK_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int srk_degrade_gauss_bilinear(srk_handle_t h, const float* hd, int N, int H, int W, int C, const float* scale_per_sample,
                                           float* sd, srk_stream_t stream) {
   SRK_REQUIRE(h && hd && sd && scale_per_sample, "srk_degrade_gauss_bilinear: null argument");

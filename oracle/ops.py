@@ -312,6 +312,47 @@ def hd_image_to_sd_image(hd_image: np.ndarray, scaling_factor: float) -> np.ndar
     return resize_bilinear_edge(sd, hd_h, hd_w)
 
 
+def vdsr_image_batches(images, scaling_factors, image_size, batch_size, rng):
+    """vdsr/vdsr/dataset.py:41-128 `image_batches` with the directory replaced by its decoded uint8 images (the order of
+    `images` stands for `tf.gfile.ListDirectory`): same random-number call sequence on `rng` (a numpy RandomState standing for
+    the global `np.random`), same numpy / skimage arithmetic (img_as_float32 = x/255 in fp32; the degrade runs in fp64 and the
+    stacked batch is float64 like the reference's).  Endless generator of (sd_images, hd_images)."""
+    if scaling_factors is None or len(scaling_factors) <= 0:
+        scaling_factors = [2.0, 3.0, 4.0]
+    if any([s <= 1 for s in scaling_factors]):
+        raise Exception('invalide scaling factors')
+    order = list(range(len(images)))
+
+    def image_indices():
+        while True:
+            rng.shuffle(order)
+            for i in order:
+                yield i
+
+    gen = image_indices()
+    sd_images, hd_images = [], []
+    while True:
+        hd_image = images[next(gen)]
+        h, w, c = hd_image.shape
+        if h < image_size or w < image_size or c != 3:
+            continue
+        x = rng.randint(w - image_size)
+        y = rng.randint(h - image_size)
+        hd_image = hd_image[y:y + image_size, x:x + image_size, :]
+        if 1 == rng.choice([0, 1]):
+            hd_image = hd_image[:, ::-1, :]
+        hd_image = np.divide(hd_image, 255, dtype=np.float32)  # skimage.util.img_as_float32 of a uint8 image
+        scaling_factor = rng.choice(scaling_factors)
+        sd_image = hd_image_to_sd_image(hd_image, scaling_factor)
+        sd_image = sd_image * 2.0 - 1.0
+        hd_image = hd_image * 2.0 - 1.0
+        sd_images.append(sd_image)
+        hd_images.append(hd_image)
+        if len(sd_images) == batch_size:
+            yield np.stack(sd_images, axis=0), np.stack(hd_images, axis=0)
+            sd_images, hd_images = [], []
+
+
 def espcn_lr_from_hr(hr_image: np.ndarray, r: int) -> np.ndarray:
     """espcn/espcn/experiment_test.py:76-87: gaussian sigma=0.5(r-1) then stride-r decimation
     at offset r//2.  `hr_image` already in [-1,1]."""

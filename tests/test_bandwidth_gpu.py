@@ -91,3 +91,23 @@ def test_fpa_upsample2_and_backward(srk_ops):
     dx = srk_ops.fpa_to_nhwc(srk_ops.fpa_upsample2_bwd(srk_ops.fpa_from_nhwc(_dev(dy)))).cpu().numpy()
     ref = dy.reshape(2, 5, 2, 7, 2, 64).sum(axis=(2, 4))
     np.testing.assert_allclose(dx, ref, rtol=2.0 ** -7, atol=1e-3)
+
+
+def test_vdsr_device_input_pipeline_matches_reference_generator(srk_ops):
+    """batches cut from the device-resident image pool equal the reference's python generator for the same
+    seed -- hd bit for bit (crop, flip, x/255, x*2-1 in fp32), sd within the degrade kernel's fp32 tolerance -- with and
+    without the prefetch stream (vdsr/vdsr/dataset.py:41-128)."""
+    from ml_super_resolution_b200.vdsr import dataset as D
+    rng = np.random.default_rng(9)
+    images = [rng.integers(0, 256, (int(rng.integers(45, 90)), int(rng.integers(45, 120)), 3), dtype=np.uint8) for _ in range(7)]
+    images.append(rng.integers(0, 256, (30, 200, 3), dtype=np.uint8))  # too small: the generator must skip it
+    ref = O.vdsr_image_batches(images, [2.0, 3.0, 4.0], 41, 6, np.random.RandomState(123))
+    for prefetch in (False, True):
+        ref = O.vdsr_image_batches(images, [2.0, 3.0, 4.0], 41, 6, np.random.RandomState(123))
+        got = D.image_batches(images, [2.0, 3.0, 4.0], 41, 6, seed=123, prefetch=prefetch)
+        for _ in range(4):
+            sd_r, hd_r = next(ref)
+            sd_g, hd_g = next(got)
+            torch.cuda.current_stream().synchronize()
+            assert np.array_equal(hd_g.cpu().numpy(), hd_r.astype(np.float32))
+            assert np.abs(sd_g.cpu().numpy() - sd_r).max() <= 1e-5
