@@ -311,3 +311,24 @@ def test_enet_generator_tiled_equals_untiled(srk_ops):
     got = net.forward(torch.from_numpy(sdw).cuda(), torch.from_numpy(bqw).cuda()).cpu().numpy()
     ref = OM.enet_generator_forward(params, sdw, bqw)
     assert np.abs(got - ref).max() <= TOL_BF16 * max(1.0, np.abs(ref - bqw).max())
+
+
+def test_espcn_trains_from_reference_tfrecords(srk_ops, tmp_path):
+    """patch pairs written in the reference's TFRecord layout feed EspcnNet.train_step through the
+    prefetching device iterator; the first step's loss equals the oracle's on the same (decoded) batch."""
+    from ml_super_resolution_b200.espcn import dataset as ED
+    from ml_super_resolution_b200.espcn.model_espcn import EspcnNet
+    params = _trained_like(OM.espcn_init(seed=12, scaling_factor=3, channels=3), scale=4.0)
+    lrs = OM.synthetic_images(61, 8, 17, 17, 3)
+    hrs = O.pixel_unshuffle(OM.synthetic_images(62, 8, 51, 51, 3), 3)
+    for i in range(8):
+        ED.write_patch(str(tmp_path / f"{i:03d}.tfrecord"), lrs[i], hrs[i])
+    it = ED.build_image_batch_iterator(str(tmp_path), batch_size=8, upscaling_factor=3, seed=0, device="cuda")
+    lr_d, hr_d = next(it)
+    assert lr_d.shape == (8, 17, 17, 3) and hr_d.shape == (8, 17, 17, 27)
+    net = EspcnNet(params, 3, 3)
+    loss = float(net.train_step(lr_d, hr_d, 1e-3))
+    ref_loss, _, _ = OM.espcn_loss_and_grads(params, lr_d.cpu().numpy(), hr_d.cpu().numpy())
+    assert abs(loss - ref_loss) <= 2e-3 * ref_loss
+    lr2, _ = next(it)  # second epoch batch arrives through the other buffer set
+    assert lr2.shape == (8, 17, 17, 3)
