@@ -234,6 +234,24 @@ int srk_momentum_clip_step(srk_handle_t h, float* w, const float* g, float* accu
  * 3x3 layer sees exact neighbours at the panel seam.  max_cols >= the largest number of non-owned columns of any panel. */
 int srk_fpa_halo_exchange(srk_handle_t h, void* x_fpa, int C, const srk_panel* panels, int n_img, int H, int W,
                           int max_cols, srk_stream_t stream);
+/* ---- evaluation post-pass ---------------------------------------------------------------------
+ * tf.image.psnr(a, b, max_val) per image over H,W,C: 20 log10(max_val) - 10 log10(mean((a-b)^2))
+ *   vdsr/vdsr/experiment_evaluate.py:57-58 (max_val 2.0), espcn/espcn/experiment_test.py:52 (1.0).
+ * workspace: n_img doubles of device scratch; out: n_img floats. */
+int srk_psnr(srk_handle_t h, const float* a, const float* b, int n_img, int64_t numel_per_image, float max_val,
+             double* workspace, float* out, srk_stream_t stream);
+/* tf.image.ssim(a, b, max_val) per image: 11x11 gaussian window (sigma 1.5), VALID, k1 = 0.01, k2 = 0.03, mean over window
+ * positions and channels (TF 1.8 _ssim_helper: luminance * contrast-structure).  a, b fp32 NHWC [n_img,H,W,C], H,W >= 11.
+ *   vdsr/vdsr/experiment_evaluate.py:59-60, espcn/espcn/experiment_test.py:53. */
+int srk_ssim(srk_handle_t h, const float* a, const float* b, int n_img, int H, int W, int C, float max_val,
+             double* workspace, float* out, srk_stream_t stream);
+/* Y of tf.image.rgb_to_yuv applied to clip(x*scale+bias, clip_lo, clip_hi): espcn/espcn/experiment_test.py:32-48 remaps
+ * [-1,1] -> [0,1] (scale 0.5, bias 0.5), clips, and scores the Y channel.  x: [n_pixels,3], y: [n_pixels]. */
+int srk_rgb_to_y(srk_handle_t h, const float* x, int64_t n_pixels, float scale, float bias, float clip_lo, float clip_hi,
+                 float* y, srk_stream_t stream);
+/* tf.saturate_cast(x*scale + bias, uint8) (clamp to [0,255], truncate): vdsr/vdsr/experiment_resolve.py:65-67. */
+int srk_saturate_cast_u8(srk_handle_t h, const float* x, size_t n, float scale, float bias, uint8_t* y, srk_stream_t stream);
+
 /* FPA (bf16, C ch) <-> fp32 NHWC [n_img,H,W,C] converters (feature-map taps `conv.N:0`, tests). */
 int srk_fpa_to_nhwc(srk_handle_t h, const void* x_fpa, int C, int n_img, int H, int W, float* y,
                     srk_stream_t stream);

@@ -63,6 +63,10 @@ SIGNATURES = {
     "srk_l2norm_rows_mean_fwd_bwd": (_I, [_P, _P, _P, _I, _I, _P, _P, _I, _P]),
     "srk_adam_step": (_I, [_P, _P, _P, _P, _P, _SZ, _F, _F, _F, _F, _I64, _F, _P, _P]),
     "srk_momentum_clip_step": (_I, [_P, _P, _P, _P, _SZ, _F, _F, _F, _F, _P, _P]),
+    "srk_psnr": (_I, [_P, _P, _P, _I, _I64, _F, _P, _P, _P]),
+    "srk_ssim": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P]),
+    "srk_rgb_to_y": (_I, [_P, _P, _I64, _F, _F, _F, _F, _P, _P]),
+    "srk_saturate_cast_u8": (_I, [_P, _P, _SZ, _F, _F, _P, _P]),
     "srk_crop_flip_u8": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "srk_affine_f32": (_I, [_P, _P, _SZ, _F, _F, _P, _P]),
     "srk_fpa_halo_exchange": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _P]),

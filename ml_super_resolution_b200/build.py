@@ -8,7 +8,7 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libsrk.so")
-SOURCES = ["api.cu", "conv_tc.cu", "conv_small.cu", "bandwidth.cu", "wgrad_tc.cu"]
+SOURCES = ["api.cu", "conv_tc.cu", "conv_small.cu", "bandwidth.cu", "wgrad_tc.cu", "metrics.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
 

@@ -392,6 +392,58 @@ def psnr(a, b, max_val: float) -> np.ndarray:
     return 20.0 * math.log10(max_val) - 10.0 * np.log10(mse)
 
 
+def ssim_tf(a, b, max_val: float) -> np.ndarray:
+    """tf.image.ssim per image (TF 1.8 image_ops_impl._ssim_helper / _ssim_per_channel): 11x11 gaussian window with
+    sigma 1.5 (softmax-normalised outer product), VALID depthwise filtering of x, y, x*y and x^2+y^2, k1 = 0.01, k2 = 0.03,
+    luminance * contrast-structure averaged over window positions, then over channels.
+    vdsr/vdsr/experiment_evaluate.py:59-60 (max_val 2.0); espcn/espcn/experiment_test.py:53 (1.0)."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    size, sigma = 11, 1.5
+    coords = np.arange(size, dtype=np.float64) - (size - 1) / 2.0
+    g = np.exp(-(coords ** 2) / (2.0 * sigma * sigma))
+    g /= g.sum()
+
+    def reducer(t):  # [N,H,W,C] -> VALID separable gaussian
+        t = np.lib.stride_tricks.sliding_window_view(t, size, axis=1) @ g      # [N,H-10,W,C]
+        return np.lib.stride_tricks.sliding_window_view(t, size, axis=2) @ g   # [N,H-10,W-10,C]
+
+    c1, c2 = (0.01 * max_val) ** 2, (0.03 * max_val) ** 2
+    mean0, mean1 = reducer(a), reducer(b)
+    num0 = mean0 * mean1 * 2.0
+    den0 = mean0 ** 2 + mean1 ** 2
+    luminance = (num0 + c1) / (den0 + c1)
+    num1 = reducer(a * b) * 2.0
+    den1 = reducer(a ** 2 + b ** 2)
+    cs = (num1 - num0 + c2) / (den1 - den0 + c2)
+    return (luminance * cs).mean(axis=(1, 2)).mean(axis=-1)
+
+
+def rgb_to_yuv_y(rgb) -> np.ndarray:
+    """First channel of tf.image.rgb_to_yuv (kernel column [0.299, 0.587, 0.114]); espcn/espcn/experiment_test.py:45-49."""
+    rgb = np.asarray(rgb, np.float64)
+    return rgb[..., 0] * 0.299 + rgb[..., 1] * 0.587 + rgb[..., 2] * 0.114
+
+
+def espcn_scores(sr_packed, hr_packed, scaling_factor: int, score_space: str = "rgb"):
+    """espcn/espcn/experiment_test.py:30-53: remap [-1,1] -> [0,1], clip, optionally reinterpret the packed tensor
+    [N,h,w,3r^2] as [N,h,w*r^2,3] and keep Y, then psnr / ssim with max_val 1.0.  Returns (psnrs, ssims)."""
+    sr = np.clip(np.asarray(sr_packed, np.float64) * 0.5 + 0.5, 0.0, 1.0)
+    hr = np.clip(np.asarray(hr_packed, np.float64) * 0.5 + 0.5, 0.0, 1.0)
+    if score_space == "y":
+        n, h, w, _ = hr.shape
+        w2 = w * scaling_factor ** 2
+        sr = rgb_to_yuv_y(sr.reshape(-1, h, w2, 3))[..., None]
+        hr = rgb_to_yuv_y(hr.reshape(-1, h, w2, 3))[..., None]
+    return psnr(hr, sr, 1.0), ssim_tf(hr, sr, 1.0)
+
+
+def saturate_cast_u8(x, scale=127.5, bias=127.5) -> np.ndarray:
+    """tf.saturate_cast(x * 127.5 + 127.5, tf.uint8) in fp32 (vdsr/vdsr/experiment_resolve.py:65-67): clamp, then truncate."""
+    v = np.asarray(x, np.float32) * np.float32(scale) + np.float32(bias)
+    return np.clip(v, 0.0, 255.0).astype(np.uint8)
+
+
 # ------------------------------------------------------------------------------------------
 # optimisers (TF formulas, SURVEY A.8)
 # ------------------------------------------------------------------------------------------

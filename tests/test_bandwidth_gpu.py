@@ -3,6 +3,7 @@ import numpy as np
 import pytest
 import torch
 
+from oracle import models as OM
 from oracle import ops as O
 
 pytestmark = pytest.mark.gpu
@@ -111,3 +112,24 @@ def test_vdsr_device_input_pipeline_matches_reference_generator(srk_ops):
             torch.cuda.current_stream().synchronize()
             assert np.array_equal(hd_g.cpu().numpy(), hd_r.astype(np.float32))
             assert np.abs(sd_g.cpu().numpy() - sd_r).max() <= 1e-5
+
+
+def test_evaluation_post_pass(srk_ops):
+    """psnr / ssim per image (max_val 2.0 on [-1,1] images and 1.0 in ESPCN's clipped packed space, RGB and
+    Y), and the saturate-cast uint8 hand-off, against the restated tf.image semantics."""
+    from ml_super_resolution_b200 import metrics as M
+    hd = OM.synthetic_images(91, 3, 57, 83, 3)
+    sr = np.clip(hd + 0.05 * np.random.default_rng(1).standard_normal(hd.shape).astype(np.float32), -1.2, 1.2).astype(np.float32)
+    a, b = _dev(hd), _dev(sr)
+    np.testing.assert_allclose(M.psnr(a, b, 2.0).cpu().numpy(), O.psnr(hd, sr, 2.0), rtol=0, atol=2e-4)
+    np.testing.assert_allclose(M.ssim(a, b, 2.0).cpu().numpy(), O.ssim_tf(hd, sr, 2.0), rtol=0, atol=2e-5)
+    # ESPCN: packed space, both score spaces
+    hrp = O.pixel_unshuffle(OM.synthetic_images(92, 2, 51, 66, 3), 3)
+    srp = (hrp + 0.03 * np.random.default_rng(2).standard_normal(hrp.shape)).astype(np.float32)
+    for space in ("rgb", "y"):
+        p, s = M.espcn_scores(_dev(srp), _dev(np.ascontiguousarray(hrp)), 3, space)
+        rp, rs = O.espcn_scores(srp, hrp, 3, space)
+        np.testing.assert_allclose(p.cpu().numpy(), rp, rtol=0, atol=3e-4)
+        np.testing.assert_allclose(s.cpu().numpy(), rs, rtol=0, atol=3e-5)
+    x = np.linspace(-1.3, 1.3, 4001, dtype=np.float32)
+    assert np.array_equal(M.saturate_cast_u8(_dev(x)).cpu().numpy(), O.saturate_cast_u8(x))

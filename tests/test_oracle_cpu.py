@@ -116,3 +116,16 @@ def test_models_golden_and_losses():
     pg = OM.enet_g_init(seed=1)
     assert len(pg) == 50 and OM.enet_generator_forward(pg, np.zeros((1, 4, 4, 3)), np.zeros((1, 16, 16, 3))).shape == (1, 16, 16, 3)
     assert O.psnr(np.zeros((1, 2, 2, 1)), np.full((1, 2, 2, 1), 0.2), 2.0)[0] == pytest.approx(20.0)
+
+
+def test_ssim_restatement_properties():
+    """tf.image.ssim restatement: identical images score 1, the score is symmetric, and a uniform image pair reduces to
+    the closed-form luminance term (2 m1 m2 + c1) / (m1^2 + m2^2 + c1)."""
+    x = OM.synthetic_images(5, 2, 24, 31, 3)
+    y = np.roll(x, 3, axis=2)
+    assert np.allclose(O.ssim_tf(x, x, 2.0), 1.0)
+    assert np.allclose(O.ssim_tf(x, y, 2.0), O.ssim_tf(y, x, 2.0))
+    a, b = np.full((1, 12, 12, 1), 0.25), np.full((1, 12, 12, 1), 0.5)
+    c1 = (0.01 * 1.0) ** 2
+    assert np.allclose(O.ssim_tf(a, b, 1.0), (2 * 0.25 * 0.5 + c1) / (0.25 ** 2 + 0.5 ** 2 + c1))
+    assert np.array_equal(O.saturate_cast_u8(np.array([-2.0, -1.0, 0.0, 1.0, 2.0], np.float32)), np.array([0, 0, 127, 255, 255], np.uint8))
