@@ -247,3 +247,38 @@ def test_random_shape_sweep(srk_ops):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "stress_conv.py"), "7", "25"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "stress OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_edge_geometries_and_error_behaviour(srk_ops):
+    """Degenerate geometries the flat-stream kernels must still get right (1x1 and 1-row images, the 254-px width limit, one
+    image smaller than a tile), the residual-junction data gradient, and the error contract: every refusal is an SrkError with
+    text from srk_last_error (the analogue of TF raising at session.run), never a crash or a silent fallback."""
+    from ml_super_resolution_b200._ffi import SrkError
+    import torch.nn.functional as F
+    g = torch.Generator(device="cuda").manual_seed(5)
+    w = torch.randn((3, 3, 64, 64), device="cuda", generator=g) * 0.04
+    b = torch.randn(64, device="cuda", generator=g) * 0.1
+    wp = srk_ops.pack_conv_weights(w)
+    for (n, H, W) in [(1, 1, 1), (3, 1, 7), (2, 5, 1), (1, 2, 254), (1, 300, 254)]:
+        x = torch.randn((n, H, W, 64), device="cuda", generator=g)
+        got = srk_ops.fpa_to_nhwc(srk_ops.conv_tc(srk_ops.fpa_from_nhwc(x), wp, b, 3, "relu"))
+        ref = torch.relu(F.conv2d(x.to(torch.bfloat16).float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float().permute(3, 2, 0, 1), b, padding=1))
+        assert float((got - ref.permute(0, 2, 3, 1)).abs().max()) <= 2e-2 * max(1.0, float(ref.abs().max())), (n, H, W)
+    # (conv + skip gradient) * relu'(saved activation): EnhanceNet's residual junction
+    x = torch.randn((2, 9, 11, 64), device="cuda", generator=g)
+    skip = torch.randn((2, 9, 11, 64), device="cuda", generator=g)
+    saved = torch.randn((2, 9, 11, 64), device="cuda", generator=g)
+    got = srk_ops.fpa_to_nhwc(srk_ops.conv_tc(srk_ops.fpa_from_nhwc(x), wp, None, 3, None, mask_src=srk_ops.fpa_from_nhwc(saved), mask_kind="relu",
+                                              addend=srk_ops.fpa_from_nhwc(skip), relu_after_add=2))
+    conv = F.conv2d(x.to(torch.bfloat16).float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float().permute(3, 2, 0, 1), None, padding=1).permute(0, 2, 3, 1)
+    ref = (conv + skip.to(torch.bfloat16).float()) * (saved.to(torch.bfloat16).float() > 0)
+    assert float((got - ref).abs().max()) <= 3e-2
+    # refusals
+    wide = srk_ops.fpa_empty(1, 4, 300, 64)
+    with pytest.raises(SrkError, match="too large|column panels"):
+        srk_ops.conv_tc(wide, wp, b, 3, "relu")
+    with pytest.raises(SrkError, match="unsupported"):
+        srk_ops.conv_tc(srk_ops.fpa_empty(1, 4, 4, 64), torch.zeros((49, 64, 64), dtype=torch.bfloat16, device="cuda"), b, 7, "relu")
+    with pytest.raises(SrkError, match="smaller than the 11x11"):
+        from ml_super_resolution_b200 import metrics as M
+        M.ssim(torch.zeros((1, 8, 8, 3), device="cuda"), torch.zeros((1, 8, 8, 3), device="cuda"), 2.0)
