@@ -252,6 +252,10 @@ int srk_rgb_to_y(srk_handle_t h, const float* x, int64_t n_pixels, float scale, 
 /* tf.saturate_cast(x*scale + bias, uint8) (clamp to [0,255], truncate): vdsr/vdsr/experiment_resolve.py:65-67. */
 int srk_saturate_cast_u8(srk_handle_t h, const float* x, size_t n, float scale, float bias, uint8_t* y, srk_stream_t stream);
 
+/* 8x8 mosaic of a 64-channel feature map x fp32 [H,W,64] -> uint8 [8H, 8W]: channel ch at grid cell (ch/8, ch%8),
+ * saturate_cast(x*127.5+127.5) (vdsr/vdsr/experiment_feature_map_visualize.py:80-110). */
+int srk_feature_mosaic_u8(srk_handle_t h, const float* x, int H, int W, uint8_t* y, srk_stream_t stream);
+
 /* FPA (bf16, C ch) <-> fp32 NHWC [n_img,H,W,C] converters (feature-map taps `conv.N:0`, tests). */
 int srk_fpa_to_nhwc(srk_handle_t h, const void* x_fpa, int C, int n_img, int H, int W, float* y,
                     srk_stream_t stream);

@@ -130,6 +130,19 @@ __global__ void __launch_bounds__(256) saturate_u8_kernel(const float* __restric
   }
 }
 
+// 8x8 mosaic of the 64 feature maps of one image: channel ch goes to grid cell (ch / 8, ch % 8), saturate-cast like the images
+__global__ void __launch_bounds__(256) feature_mosaic_kernel(const float* __restrict__ x, int H, int W, uint8_t* __restrict__ y) {
+  const int64_t total = int64_t(64) * H * W;
+  const int OW = 8 * W;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int ox = int(i % OW);
+    const int oy = int(i / OW);
+    const int ch = (oy / H) * 8 + ox / W, yy = oy % H, xx = ox % W;
+    const float v = __fadd_rn(__fmul_rn(x[(int64_t(yy) * W + xx) * 64 + ch], 127.5f), 127.5f);
+    y[i] = uint8_t(fminf(fmaxf(v, 0.f), 255.f));
+  }
+}
+
 static inline int grid1(srk_ctx* h, int64_t items, int block, int per_sm) {
   const int64_t g = (items + block - 1) / block;
   const int64_t cap = int64_t(h->num_sms) * per_sm;
@@ -182,6 +195,13 @@ extern "C" int srk_saturate_cast_u8(srk_handle_t h, const float* x, size_t n, fl
   SRK_REQUIRE(h && x && y, "srk_saturate_cast_u8: null argument");
   if (n == 0) return 0;
   saturate_u8_kernel<<<grid1(h, int64_t(n), 256, 16), 256, 0, as_stream(stream)>>>(x, n, scale, bias, y);
+  SRK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int srk_feature_mosaic_u8(srk_handle_t h, const float* x, int H, int W, uint8_t* y, srk_stream_t stream) {
+  SRK_REQUIRE(h && x && y && H > 0 && W > 0, "srk_feature_mosaic_u8: bad argument");
+  feature_mosaic_kernel<<<grid1(h, int64_t(64) * H * W, 256, 16), 256, 0, as_stream(stream)>>>(x, H, W, y);
   SRK_LAUNCH_CHECK();
   return 0;
 }

@@ -63,3 +63,14 @@ def saturate_cast_u8(x: torch.Tensor, scale: float = 127.5, bias: float = 127.5)
     check(_ffi.lib().srk_saturate_cast_u8(ops.handle(), ops._ptr(x), x.numel(), float(scale), float(bias), ops._ptr(y), ops._stream()),
           "srk_saturate_cast_u8")
     return y
+
+
+def feature_mosaic_u8(feature_map: torch.Tensor) -> torch.Tensor:
+    """`encode_feature_map` of vdsr/vdsr/experiment_feature_map_visualize.py:80-110 up to the PNG encoder: fp32 [1,H,W,64] (a
+    `conv.N` / `relu.N` tap of VdsrNet.forward) -> uint8 [8H, 8W, 1], the 64 maps in an 8x8 grid."""
+    x = ops._f32(feature_map)
+    assert x.shape[0] == 1 and x.shape[3] == 64
+    _, h, w, _ = x.shape
+    y = torch.empty((8 * h, 8 * w, 1), dtype=torch.uint8, device=x.device)
+    check(_ffi.lib().srk_feature_mosaic_u8(ops.handle(), ops._ptr(x), h, w, ops._ptr(y), ops._stream()), "srk_feature_mosaic_u8")
+    return y

@@ -444,6 +444,15 @@ def saturate_cast_u8(x, scale=127.5, bias=127.5) -> np.ndarray:
     return np.clip(v, 0.0, 255.0).astype(np.uint8)
 
 
+def feature_mosaic_u8(feature_map) -> np.ndarray:
+    """vdsr/vdsr/experiment_feature_map_visualize.py:80-110 `encode_feature_map` before encode_png: split the 64 channels,
+    concat 8 per row along the width, rows along the height, saturate_cast(x*127.5+127.5)."""
+    t = np.asarray(feature_map, np.float32)[0]
+    maps = np.split(t, 64, axis=-1)
+    rows = [np.concatenate(maps[i:i + 8], axis=1) for i in range(0, 64, 8)]
+    return saturate_cast_u8(np.concatenate(rows, axis=0))
+
+
 # ------------------------------------------------------------------------------------------
 # optimisers (TF formulas, SURVEY A.8)
 # ------------------------------------------------------------------------------------------

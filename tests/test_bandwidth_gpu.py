@@ -133,3 +133,5 @@ def test_evaluation_post_pass(srk_ops):
         np.testing.assert_allclose(s.cpu().numpy(), rs, rtol=0, atol=3e-5)
     x = np.linspace(-1.3, 1.3, 4001, dtype=np.float32)
     assert np.array_equal(M.saturate_cast_u8(_dev(x)).cpu().numpy(), O.saturate_cast_u8(x))
+    fm = (np.random.default_rng(4).standard_normal((1, 13, 17, 64)) * 0.7).astype(np.float32)
+    assert np.array_equal(M.feature_mosaic_u8(_dev(fm)).cpu().numpy(), O.feature_mosaic_u8(fm))
