@@ -1086,10 +1086,14 @@ static int launch_conv_tc(srk_ctx* h, ConvTcParams& p, const void* x, const void
 }
 
 static int fill_geom(ConvTcParams& p, int n_img, int H, int W) {
+#ifdef SRK_TRACE
   {
-    const char* e = getenv("SRK_DBG");
+    const char* e = getenv("SRK_DBG");  // development builds only: epilogue ablation switches
     p.dbg = e ? atoi(e) : 0;
   }
+#else
+  p.dbg = 0;
+#endif
   SRK_REQUIRE(n_img > 0 && H > 0 && W > 0, "conv_tc: bad geometry n_img=%d H=%d W=%d", n_img, H, W);
   const FpaGeom g = fpa_geom(n_img, H, W);
   SRK_REQUIRE(g.rows_valid < (int64_t(1) << 30), "conv_tc: %lld rows exceed the 2^30 row limit", (long long)g.rows_valid);
