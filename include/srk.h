@@ -152,6 +152,13 @@ typedef struct {
   float* db;
   int32_t ci_n, co_n;
 } srk_wgrad_dst;
+/* All layers of one geometry in ONE weight-gradient launch + ONE reduce launch: x_fpas / dy_fpas are HOST arrays of n_layers
+ * device pointers (layer l: dW_l = X_l^T dY_l), workspace slices `layer_stride_bytes` apart (size them with
+ * srk_conv_wgrad_tc_workspace_bytes), destinations as for srk_wgrad_reduce_many.  Needs every layer's dY kept until the
+ * call (the training step stores them instead of ping-ponging two buffers). */
+int srk_conv_wgrad_tc_batched(srk_handle_t h, const void* const* x_fpas, const void* const* dy_fpas, int n_layers,
+                              int n_img, int H, int W, void* workspace, size_t layer_stride_bytes,
+                              const srk_wgrad_dst* dsts_device, int accumulate, srk_stream_t stream);
 int srk_wgrad_reduce_many(srk_handle_t h, const void* workspace_base, size_t layer_stride_bytes, int n_layers,
                           int n_img, int H, int W, const srk_wgrad_dst* dsts_device, int accumulate,
                           srk_stream_t stream);

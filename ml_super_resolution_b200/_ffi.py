@@ -49,6 +49,7 @@ SIGNATURES = {
     "srk_conv_tc_last": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P]),
     "srk_conv_wgrad_tc_workspace_bytes": (_SZ, [_P, _I, _I, _I]),
     "srk_conv_wgrad_tc": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _SZ, _P]),
+    "srk_conv_wgrad_tc_batched": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _SZ, _P, _I, _P]),
     "srk_wgrad_reduce_many": (_I, [_P, _P, _SZ, _I, _I, _I, _I, _P, _I, _P]),
     "srk_nhwc_to_fpa_pad": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "srk_conv_first_wgrad": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),

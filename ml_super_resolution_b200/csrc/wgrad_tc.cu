@@ -20,6 +20,8 @@
 //
 //   warp 0: TMA producer for X chunks (+ mirrors)      warp 6: TMA producer for dY chunks
 //   warp 1: TMEM allocator + single-thread MMA issuer  warps 2..5: epilogue
+#include <algorithm>
+
 #include "sm100_ptx.cuh"
 #include "srk_common.cuh"
 
@@ -54,7 +56,8 @@ struct WgSmem {
   static constexpr int kTotal = kOffTmemSlot + 16 + 1024;
 };
 
-__global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgradParams p) {
+// Body shared by the single-layer and the batched launch.  `mx` / `mdy` point into kernel-parameter (constant) space.
+__device__ __forceinline__ void wgrad_body(const WgradParams& p, const CUtensorMap* mx, const CUtensorMap* mdy, float* part) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t s_base = smem_u32(smem);
@@ -94,8 +97,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   fence_proxy_async_smem();
   if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.map_x);
-    tma_prefetch_desc(&p.map_dy);
+    tma_prefetch_desc(mx);
+    tma_prefetch_desc(mdy);
   }
   tc_fence_before();
   __syncthreads();
@@ -110,8 +113,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
           mbar_wait(bar_xempty(slot), (gen & 1) ^ 1);
           const bool mir = slot < p.mirror;
           mbar_arrive_expect_tx(bar_xfull(slot), kChunk * (mir ? 2 : 1));
-          tma_load_2d(s_x + slot * kChunk, &p.map_x, 0, c * 128, bar_xfull(slot));
-          if (mir) tma_load_2d(s_x + (R + slot) * kChunk, &p.map_x, 0, c * 128, bar_xfull(slot));
+          tma_load_2d(s_x + slot * kChunk, mx, 0, c * 128, bar_xfull(slot));
+          if (mir) tma_load_2d(s_x + (R + slot) * kChunk, mx, 0, c * 128, bar_xfull(slot));
         }
       }
     } else if (warp == 6) {
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
           const int j = k - k_begin, slot = j % kYRing, gen = j / kYRing;
           mbar_wait(bar_yempty(slot), (gen & 1) ^ 1);
           mbar_arrive_expect_tx(bar_yfull(slot), kYRows * 128);
-          tma_load_2d(s_y + slot * kYSlot, &p.map_dy, 0, k * 128 - 1, bar_yfull(slot));  // rows 128k-1 .. 128k+128 (OOB rows: zero)
+          tma_load_2d(s_y + slot * kYSlot, mdy, 0, k * 128 - 1, bar_yfull(slot));  // rows 128k-1 .. 128k+128 (OOB rows: zero)
         }
       }
     } else if (warp == 1) {
@@ -173,7 +176,6 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
       const int m = quad * 32 + lane;  // accumulator row
       mbar_wait(bar_done, 0);
       tc_fence_after();
-      float* part = p.partial + size_t(blockIdx.x) * kPartialFloats;
       // accumulator 0: rows (u = m>>6, ci), columns (N atom j -> v = 2-j, co); accumulator 1: rows 0..63 = (u = 2, ci),
       // rows 64..127 = the ones block (row 64, atom 1 = unshifted dY: the bias gradient)
 #pragma unroll 1
@@ -202,6 +204,25 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgradParams p) {
+  wgrad_body(p, &p.map_x, &p.map_dy, p.partial + size_t(blockIdx.x) * kPartialFloats);
+}
+
+// Batched form: blockIdx.y selects the layer (its own pair of tensor maps and workspace slice).  At the 64 x 41 x 41
+// training shape a single layer only has ~880 chunks of work: twenty separate launches each pay their fill and drain;
+// one launch over all layers keeps every SM busy for several waves of longer CTAs.
+constexpr int kMaxWgBatch = 32;
+struct alignas(64) WgradBatchParams {
+  WgradParams c;  // geometry; c.partial = workspace base
+  size_t layer_stride_floats;
+  CUtensorMap map_x[kMaxWgBatch];
+  CUtensorMap map_dy[kMaxWgBatch];
+};
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_batched_kernel(const __grid_constant__ WgradBatchParams bp) {
+  const int l = blockIdx.y;
+  wgrad_body(bp.c, &bp.map_x[l], &bp.map_dy[l], bp.c.partial + size_t(l) * bp.layer_stride_floats + size_t(blockIdx.x) * kPartialFloats);
 }
 
 // Deterministic second pass: dw/dbias = (accumulate ? dw : 0) + sum over CTA partials (fixed order).
@@ -298,6 +319,46 @@ extern "C" int srk_conv_wgrad_tc(srk_handle_t h, const void* x_fpa, const void* 
     WgradDst single{dw_hwio, dbias, 64, 64};
     SRK_CHECK_CUDA(launch_pdl(wgrad_reduce_kernel, dim3((kPartialFloats / 4 + 127) / 128, 1), dim3(128), 0, as_stream(stream),
                               static_cast<const float4*>(workspace), size_t(0), grid, static_cast<const WgradDst*>(nullptr), single, accumulate));
+  }
+  return 0;
+}
+
+extern "C" int srk_conv_wgrad_tc_batched(srk_handle_t h, const void* const* x_fpas, const void* const* dy_fpas, int n_layers, int n_img, int H,
+                                         int W, void* workspace, size_t layer_stride_bytes, const srk_wgrad_dst* dsts_device, int accumulate,
+                                         srk_stream_t stream) {
+  SRK_REQUIRE(h && x_fpas && dy_fpas && workspace && dsts_device && n_layers > 0, "srk_conv_wgrad_tc_batched: bad argument");
+  SRK_REQUIRE(layer_stride_bytes % 16 == 0 && reinterpret_cast<uintptr_t>(workspace) % 16 == 0, "srk_conv_wgrad_tc_batched: workspace alignment");
+  const FpaGeom g = fpa_geom(n_img, H, W);
+  SRK_REQUIRE(g.rows_valid < (int64_t(1) << 31), "srk_conv_wgrad_tc_batched: too many rows");
+  static bool attr_set = false;
+  if (!attr_set) {
+    SRK_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem::kTotal));
+    attr_set = true;
+  }
+  const int num_chunks = int((g.rows_valid + 127) / 128);
+  for (int l0 = 0; l0 < n_layers; l0 += kMaxWgBatch) {
+    const int nl = std::min(kMaxWgBatch, n_layers - l0);
+    WgradBatchParams bp{};
+    bp.c.partial = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + size_t(l0) * layer_stride_bytes);
+    bp.c.Wp = g.Wp;
+    bp.c.num_chunks = num_chunks;
+    bp.c.nb = (g.Wp + 1 + 127) / 128;
+    bp.c.mirror = (g.Wp + 16 + 127) / 128;
+    bp.c.ring = kXSlots - bp.c.mirror;
+    SRK_REQUIRE(bp.c.ring >= 2 * bp.c.nb + 2, "srk_conv_wgrad_tc_batched: image width %d too large for the flat-stream kernel", W);
+    bp.layer_stride_floats = layer_stride_bytes / sizeof(float);
+    // CTAs per layer: at least 8 chunks each, about five waves of the whole device over all layers
+    int cpl = std::min(wgrad_grid(h, num_chunks), std::max(1, (5 * h->num_sms) / nl));
+    SRK_REQUIRE(layer_stride_bytes >= size_t(cpl) * kPartialFloats * sizeof(float), "srk_conv_wgrad_tc_batched: layer stride smaller than one layer's partials");
+    for (int l = 0; l < nl; ++l) {
+      SRK_REQUIRE(x_fpas[l0 + l] && dy_fpas[l0 + l], "srk_conv_wgrad_tc_batched: null operand for layer %d", l0 + l);
+      if (int rc = make_tensor_map_2d(&bp.map_x[l], x_fpas[l0 + l], uint64_t(g.rows_valid), 64, 128)) return rc;
+      if (int rc = make_tensor_map_2d(&bp.map_dy[l], dy_fpas[l0 + l], uint64_t(g.rows_valid), 64, kYRows)) return rc;
+    }
+    SRK_CHECK_CUDA(launch_pdl(wgrad_tc_batched_kernel, dim3(cpl, nl), dim3(kWgThreads), size_t(WgSmem::kTotal), as_stream(stream), bp));
+    SRK_CHECK_CUDA(launch_pdl(wgrad_reduce_kernel, dim3((kPartialFloats / 4 + 127) / 128, nl), dim3(128), 0, as_stream(stream),
+                              reinterpret_cast<const float4*>(bp.c.partial), size_t(layer_stride_bytes / 16), cpl,
+                              reinterpret_cast<const WgradDst*>(dsts_device) + l0, WgradDst{}, accumulate));
   }
   return 0;
 }

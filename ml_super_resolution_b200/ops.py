@@ -253,6 +253,18 @@ def conv_wgrad_tc(x: Fpa, dy: Fpa, dw: torch.Tensor | None, dbias: torch.Tensor 
         _ffi.launch_count += 1  # the reduce kernel
 
 
+def conv_wgrad_tc_batched(xs, dys, workspace: torch.Tensor, layer_stride_bytes: int, dsts: torch.Tensor, accumulate=False) -> None:
+    """Weight gradients of len(xs) layers of one geometry with one wgrad launch + one reduce launch (srk_conv_wgrad_tc_batched)."""
+    n = len(xs)
+    assert n == len(dys) and n > 0
+    g = xs[0]
+    xp = (C.c_void_p * n)(*[x.data.data_ptr() for x in xs])
+    dp = (C.c_void_p * n)(*[d.data.data_ptr() for d in dys])
+    check(_ffi.lib().srk_conv_wgrad_tc_batched(handle(), xp, dp, n, g.n_img, g.H, g.W, _ptr(workspace), layer_stride_bytes, _ptr(dsts),
+                                               int(accumulate), _stream()), "srk_conv_wgrad_tc_batched")
+    _ffi.launch_count += 1  # the reduce kernel
+
+
 def make_wgrad_dsts(entries, device="cuda") -> torch.Tensor:
     """entries: iterable of (dw tensor, db tensor, ci_n, co_n) -> device array of srk_wgrad_dst."""
     arr = (_ffi.SrkWgradDst * len(entries))()

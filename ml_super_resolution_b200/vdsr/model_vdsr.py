@@ -176,7 +176,8 @@ class VdsrNet:
             self._train_bufs = {
                 "key": key,
                 "acts": [ops.fpa_empty(n, H, W, 64, self.device) for _ in range(self.L - 1)],
-                "dy": [ops.fpa_empty(n, H, W, 64, self.device) for _ in range(2)],
+                # every layer's dY is kept so that all weight gradients run in one batched launch after the dgrad chain
+                "dy": [ops.fpa_empty(n, H, W, 64, self.device) for _ in range(self.L - 1)],
                 "sr": torch.empty((n, H, W, self.C), dtype=torch.float32, device=self.device),
                 "dsr": torch.empty((n, H, W, self.C), dtype=torch.float32, device=self.device),
                 "loss": torch.zeros(2, dtype=torch.float32, device=self.device),  # [mse, l2 regulariser]
@@ -216,18 +217,17 @@ class VdsrNet:
         b["loss"].zero_()
         ops.mse_fwd_bwd(b["sr"], hd, b["loss"][0:1], b["dsr"], numel_total)
         ops.sumsq_masked(a.w, a.decay_mask, 0.5 * WEIGHT_DECAY, b["loss"][1:2])
-        # ---- backward: dgrad chain + one tensor-core wgrad per layer (partials), folded by a single reduce launch
-        stride = b["wg_stride"]
-        ws = lambda i: b["wg_ws"][i * stride:(i + 1) * stride]
+        # ---- backward: the dgrad chain stores every layer's dY; then ONE batched tensor-core wgrad launch over all layers
+        # (20 separate launches of ~880 chunks each paid 20 fills and drains) and ONE fixed-order reduce launch
         ops.nhwc_to_fpa_pad(b["dsr"], 64, out=b["dsr_fpa"])
-        ops.conv_wgrad_tc(acts[L - 2], b["dsr_fpa"], None, None, workspace=ws(L - 1))
-        d = ops.conv_first_tc(b["dsr"], self.wd(L - 1), None, 3, "SAME", None, out=dyb[0], mask_src=acts[L - 2], mask_kind="relu")
+        dys = [None] * L
+        dys[L - 1] = b["dsr_fpa"]
+        dys[L - 2] = ops.conv_first_tc(b["dsr"], self.wd(L - 1), None, 3, "SAME", None, out=dyb[L - 2], mask_src=acts[L - 2], mask_kind="relu")
         for i in range(L - 2, 0, -1):
-            ops.conv_wgrad_tc(acts[i - 1], d, None, None, workspace=ws(i))
-            d = ops.conv_tc(d, self.wd(i), None, 3, None, out=dyb[(L - 1 - i) % 2], mask_src=acts[i - 1], mask_kind="relu")
+            dys[i - 1] = ops.conv_tc(dys[i], self.wd(i), None, 3, None, out=dyb[i - 1], mask_src=acts[i - 1], mask_kind="relu")
         ops.nhwc_to_fpa_pad(sd, 64, out=b["sd_fpa"])
-        ops.conv_wgrad_tc(b["sd_fpa"], d, None, None, workspace=ws(0))
-        ops.wgrad_reduce_many(b["wg_ws"], stride, L, n, H, W, b["wg_dsts"])
+        xs = [b["sd_fpa"]] + [acts[i - 1] for i in range(1, L)]
+        ops.conv_wgrad_tc_batched(xs, dys, b["wg_ws"], b["wg_stride"], b["wg_dsts"])
         return b
 
     def apply_gradients(self, lr: float, use_adam=True, lr_t_dev: torch.Tensor | None = None):
