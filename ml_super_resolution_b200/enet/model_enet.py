@@ -158,7 +158,8 @@ class EnetGenerator:
             "key": key, "plan": plan, "fw": fw, "dg": dg, "geo": geo, "st": st, "tmp1": tmp1, "jobs": jobs,
             "t": [F("lo") for _ in range(11)], "hb": [F("lo") for _ in range(10)],
             "u1": F("mid"), "m1": F("mid"), "u2": F("hi"), "m2": F("hi"), "m3": F("hi"),
-            "dhi": [F("hi") for _ in range(2)], "dmid": [F("mid") for _ in range(2)], "dlo": [F("lo") for _ in range(3)],
+            # every layer's dY is kept: the weight gradients of a resolution run in one batched launch after the dgrad chain
+            "dhi": [F("hi") for _ in range(3)], "dmid": [F("mid") for _ in range(2)], "dlo": [F("lo") for _ in range(21)],
             "sdF": F("lo"), "dP": F("hi"),
             "ws": {g: torch.empty(st[g] * max(1, len(jobs[g])), dtype=torch.uint8, device=dev) for g in geo},
             "dsts": {g: ops.make_wgrad_dsts([(dw, gv(i, True), ci, co) for (i, dw, ci, co) in jobs[g]], dev) for g in geo},
@@ -191,40 +192,39 @@ class EnetGenerator:
         ops.conv_tc_last(b["m3"], V[fw[24]], self.bias_last, 3, 3, None, addend=bq, out=b["sr"])
         if callable(dsr):
             dsr = dsr(b["sr"])
-        # ---- backward
-        ws, st = b["ws"], b["st"]
-        slot = {"hi": 0, "mid": 0, "lo": 0}
+        # ---- backward: dgrad chain first (all dY kept), then one batched wgrad + reduce launch per resolution, in the order
+        # of b["jobs"] (hi: conv2d_24, 23, 22; mid: conv2d_21; lo: blocks 9..0 as (1x1, 3x3), then the first layer)
+        dhi, dmid, dlo = b["dhi"], b["dmid"], b["dlo"]
+        xs = {"hi": [], "mid": [], "lo": []}
+        dys = {"hi": [], "mid": [], "lo": []}
 
         def wgrad(g, x, dy):
-            o = slot[g] * st[g]
-            ops.conv_wgrad_tc(x, dy, None, None, workspace=ws[g][o:o + st[g]])
-            slot[g] += 1
+            xs[g].append(x)
+            dys[g].append(dy)
 
-        dhi, dmid, dlo = b["dhi"], b["dmid"], b["dlo"]
         ops.nhwc_to_fpa_pad(dsr, 64, out=b["dP"])
         wgrad("hi", b["m3"], b["dP"])                                                                            # conv2d_24
         d = ops.conv_first_tc(dsr, V[dg[24]], None, 3, "SAME", None, out=dhi[0], mask_src=b["m3"], mask_kind="relu")
         wgrad("hi", b["m2"], d)                                                                                  # conv2d_23
         d = ops.conv_tc(d, V[dg[23]], None, 3, None, out=dhi[1], mask_src=b["m2"], mask_kind="relu")
         wgrad("hi", b["u2"], d)                                                                                  # conv2d_22
-        d = ops.conv_tc(d, V[dg[22]], None, 3, None, out=dhi[0], mask_src=b["u2"], mask_kind="relu")
+        d = ops.conv_tc(d, V[dg[22]], None, 3, None, out=dhi[2], mask_src=b["u2"], mask_kind="relu")
         d = ops.fpa_upsample2_bwd(d, out=dmid[0])
         wgrad("mid", b["u1"], d)                                                                                 # conv2d_21
         d = ops.conv_tc(d, V[dg[21]], None, 3, None, out=dmid[1], mask_src=b["u1"], mask_kind="relu")
         ds = ops.fpa_upsample2_bwd(d, out=dlo[0])
-        cur = 0
+        nxt = 1
         for k in range(9, -1, -1):                                                                               # residual blocks, last first
             i = 1 + 2 * k
             wgrad("lo", b["hb"][k], ds)                                                                          # 1x1
-            dh = ops.conv_tc(ds, V[dg[i + 1]], None, 1, None, out=dlo[(cur + 1) % 3], mask_src=b["hb"][k], mask_kind="relu")
+            dh = ops.conv_tc(ds, V[dg[i + 1]], None, 1, None, out=dlo[nxt], mask_src=b["hb"][k], mask_kind="relu")
             wgrad("lo", t[k], dh)                                                                                # 3x3
-            ds = ops.conv_tc(dh, V[dg[i]], None, 3, None, out=dlo[(cur + 2) % 3], mask_src=t[k], mask_kind="relu", addend=ds, relu_after_add=2)
-            cur = (cur + 2) % 3
+            ds = ops.conv_tc(dh, V[dg[i]], None, 3, None, out=dlo[nxt + 1], mask_src=t[k], mask_kind="relu", addend=ds, relu_after_add=2)
+            nxt += 2
         ops.nhwc_to_fpa_pad(sd, 64, out=b["sdF"])
         wgrad("lo", b["sdF"], ds)                                                                                # conv2d (first layer)
         for g in ("hi", "mid", "lo"):
-            gh, gw = b["geo"][g]
-            ops.wgrad_reduce_many(ws[g], st[g], slot[g], n, gh, gw, b["dsts"][g])
+            ops.conv_wgrad_tc_batched(xs[g], dys[g], b["ws"][g], b["st"][g], b["dsts"][g])
         for k in range(10):
             a.view(self._k(2 + 2 * k), "g").copy_(b["tmp1"][k, 4].view(1, 1, 64, 64))
         return b["sr"]

@@ -206,22 +206,19 @@ class SrcnnNet:
         b["dpre_e"][:, 2:2 + bb, 2:2 + bb, :].copy_(b["dpre"])
         ops.nhwc_to_fpa_pad(b["dpre_e"], 64, out=b["dP3"])
         Wp1, rows1 = H1 + 1, b["t2"].data.shape[0]
-        for blk, (ca, cb) in enumerate(tap_block_centres(5)):   # 3x3 tap blocks centred at (-1|2, -1|2)
-            xs = self._shifted(b["t2_store"], b["margin1"], rows1, ca * Wp1 + cb, b["t2"])
-            ops.conv_wgrad_tc(xs, b["dP3"], None, None, workspace=b["ws1"][blk * b["st1"]:(blk + 1) * b["st1"]])
         d2 = ops.conv_first_tc(b["dpre_e"], V[ix["d3"]], None, 5, "SAME", None, out=b["d2"], mask_src=t2, mask_kind="relu")
-        ops.conv_wgrad_tc(t1, d2, None, None, workspace=b["ws1"][4 * b["st1"]:5 * b["st1"]])
         d1 = ops.conv_tc(d2, V[ix["d2"]], None, 1, None, out=b["d1"], mask_src=t1, mask_kind="relu")
-        ops.wgrad_reduce_many(b["ws1"], b["st1"], 5, n, H1, H1, b["dsts1"])
+        # the 5x5 kernel's four 3x3 tap blocks (centres -1|2) and the 1x1 kernel: one batched wgrad + reduce launch on G1
+        xs1 = [self._shifted(b["t2_store"], b["margin1"], rows1, ca * Wp1 + cb, b["t2"]) for (ca, cb) in tap_block_centres(5)] + [t1]
+        ops.conv_wgrad_tc_batched(xs1, [b["dP3"]] * 4 + [d2], b["ws1"], b["st1"], b["dsts1"])
         # d1 lives on G1; embed it 4 px inside G0 next to the input frame
         src = d1.data[: n * (H1 + 1) * (H1 + 1)].view(n, H1 + 1, H1 + 1, 64)[:, 1:, :H1]
         b["d1e"].data[: n * (S + 1) * (S + 1)].view(n, S + 1, S + 1, 64)[:, 5:5 + H1, 4:4 + H1].copy_(src)
         ops.nhwc_to_fpa_pad(lo, 64, out=b["loF"])
         Wp0, rows0 = S + 1, b["loF"].data.shape[0]
-        for blk, (ca, cb) in enumerate(tap_block_centres(9)):   # centres -3, 0, 3
-            xs = self._shifted(b["lo_store"], b["margin"], rows0, ca * Wp0 + cb, b["loF"])
-            ops.conv_wgrad_tc(xs, b["d1e"], None, None, workspace=b["ws0"][blk * b["st0"]:(blk + 1) * b["st0"]])
-        ops.wgrad_reduce_many(b["ws0"], b["st0"], 9, n, S, S, b["dsts0"])
+        # the 9x9 kernel's nine 3x3 tap blocks (centres -3, 0, 3): one batched launch on G0
+        xs0 = [self._shifted(b["lo_store"], b["margin"], rows0, ca * Wp0 + cb, b["loF"]) for (ca, cb) in tap_block_centres(9)]
+        ops.conv_wgrad_tc_batched(xs0, [b["d1e"]] * 9, b["ws0"], b["st0"], b["dsts0"])
         # assemble the kernel gradients from their 3x3 tap blocks
         g = lambda name: a.view(name, "g")  # noqa: E731
         g("patch_extraction/weights:0").copy_(assemble_tap_blocks(b["tmp1"], 9))
