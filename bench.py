@@ -182,7 +182,7 @@ def espcn_workload(args, rank, world):
         "espcn_f3_conv_tc_last(3x3,32->9,shuffle)": (k_f3, lr_px * (64 + 4 * C * SCALE * SCALE)),
     }
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of these three
-    # kernels at this exact shape (profiles/r1_ncu_espcn_kernels.txt): no wasted re-reads (traffic ~ algorithmic bytes)
+    # kernels at this exact shape (profiles/r1_ncu_espcn_kernels_v3.txt): no wasted re-reads (traffic ~ algorithmic bytes)
     ncu_traffic = {"espcn_f1_conv_first_tc(5x5,C->64,tanh)": 1.081e9, "espcn_f2_conv_tc(3x3,64->32,tanh)": 1.630e9,
                    "espcn_f3_conv_tc_last(3x3,32->9,shuffle)": 0.834e9}
     dom = max(kernels, key=lambda k: kernels[k][0])
