@@ -14,21 +14,22 @@
 // lanes of each window are recomputed by the neighbouring tile (1.6 % redundancy for K=3).
 //
 // Each persistent CTA owns a contiguous range of tiles and streams the input through a shared-memory ring
-// of 64-row chunks (one TMA load per chunk: every activation byte crosses L2->SMEM once); the A descriptors
+// of 64- or 128-row chunks (one TMA load per chunk: every activation byte crosses L2->SMEM once); the A descriptors
 // are row-shifted windows of that ring (probe-verified: SW128/SW64 descriptors accept any row shift with
 // base_offset 0; the ring's first 128 rows are mirrored behind its last slot so a window never wraps).  The
 // weights (K*K blocks of [NP][CIN] bf16, K-major) stay resident in shared memory.  Accumulators live in
-// TMEM (2-4 stages) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// TMEM (2-8 stages) so the epilogue of tile i overlaps the MMAs of the tiles behind it.
 //
-//   warp 0      : TMA producer (weights once, then the chunk ring)
-//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer
-//   warp 2      : TMA store issuer (waits for a full staging tile, stores it, frees the staging buffer)
-//   warps 4..   : epilogue, 4 warps (one per TMEM lane quadrant) for every 16 output channels, so each
-//                 SM sub-partition interleaves NP/16 epilogue warps and hides the tcgen05.ld / shuffle /
-//                 shared-memory latencies (a single warp per sub-partition left the tensor pipe 80 % idle:
-//                 profiles/r1_ncu_conv_tc_v2.txt): tcgen05.ld -> lane-shift add -> bias/activation/mask ->
-//                 bf16 -> swizzled smem -> TMA store, or fp32 NHWC scatter with residual add / panel crop /
-//                 pixel shuffle
+// Warp roles (20 warps; the single-thread roles sit above the epilogue warps):
+//   warps 0..15 : epilogue, in SETS sets that take tiles round-robin (2 sets x 4 TMEM lane quadrants x 2 column halves for
+//                 64-wide outputs, 4 sets x 4 quadrant warps for 32/16-wide ones): tcgen05.ld -> lane-shift add ->
+//                 bias/activation/mask -> bf16 -> swizzled smem -> TMA store; or fp32 NHWC with residual add / panel crop /
+//                 pixel shuffle, transposed through shared memory so that the global stores are coalesced
+//   warp 16     : TMA producer (chunk ring; a chunk's bytes are counted on the "ready" barrier of the first tile reading it)
+//   warps 17,19 : tcgen05.mma issuers taking alternate tiles (warp-convergent loops, one elected lane issues)
+//   warp 18     : TMA store issuer (waits for a full staging tile, stores it, frees the staging buffer)
+// The hand-over protocol (per-tile ready / done barriers) is described next to the kernel; profiles/r1_trace_conv_tc.txt
+// holds the in-kernel timelines it was derived from.
 #include <cstdlib>
 
 #include "sm100_ptx.cuh"
