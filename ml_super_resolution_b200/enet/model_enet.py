@@ -27,7 +27,7 @@ from .. import ops
 from ..initializers import ENET_G_LAYERS, enet_g_params, tf_conv_name
 from ..params import ParamArena
 from ..session import Handle
-from ..tiling import MAX_PANEL_W, plan_tiles, shard_tiles
+from ..tiling import MAX_PANEL_W, plan_seam_exchange
 
 
 class EnetGenerator:
@@ -75,7 +75,8 @@ class EnetGenerator:
         """sd fp32 [N,h,w,3], bq fp32 [N,4h,4w,3] -> sr = bq + generator(sd).
         Frames wider than 63 LR pixels (252 HR) are cut into column panels that swap their seam columns after every 3x3 layer
         at all three resolutions (`srk_fpa_halo_exchange`), frames taller than `tile_rows` LR rows into row bands with a 13-px
-        halo; with world > 1 this rank computes whole bands of the tile list and writes only the pixels it owns."""
+        halo; with world > 1 this rank computes its shard of the tile list and writes only the pixels it owns (seams are only exchanged
+        when the shard consists of whole bands; otherwise the column halo is recomputed as well)."""
         n, h, w, _ = sd.shape
         assert max_panel_w <= MAX_PANEL_W // 4
         a, W = self.arena, self.plan.views
@@ -85,11 +86,8 @@ class EnetGenerator:
         panels = [None, None, None]
         max_cols = 0
         if need_tiles:
-            Ht, Wt, tiles = plan_tiles(n, h, w, halo=self.HALO, max_w=max_panel_w, max_h=tile_rows, halo_x=1)
-            per_band = len({t.x0 for t in tiles})
-            lo = (rank * len(tiles)) // world
-            tiles = shard_tiles(tiles, rank, world)
-            assert lo % per_band == 0 and len(tiles) % per_band == 0, "a rank's shard must consist of whole row bands of panels"
+            Ht, Wt, tiles, exchange, max_cols = plan_seam_exchange(n, h, w, self.HALO, max_panel_w, tile_rows, rank, world)
+            # (exchange False: a band is split between ranks -> the plan carries the 13-px halo in x as well, no seam traffic)
             if not tiles:
                 return out
             key = (tuple(t.as_tuple() for t in tiles), str(sd.device))
@@ -98,7 +96,6 @@ class EnetGenerator:
                 cache[key] = [ops.make_panels([(t.frame,) + tuple(s * v for v in t.as_tuple()[1:]) for t in tiles], self.device)
                               for s in (1, 2, 4)]
             panels = cache[key]
-            max_cols = 2 * max(max(t.own_x0, Wt - t.own_x1) for t in tiles)
             n_img, hh, ww = len(tiles), Ht, Wt
         else:
             n_img, hh, ww = n, h, w

@@ -79,3 +79,25 @@ def shard_tiles(tiles, rank: int, world: int):
     lo = (rank * n) // world
     hi = ((rank + 1) * n) // world
     return tiles[lo:hi]
+
+
+def plan_seam_exchange(n_frames: int, FH: int, FW: int, halo: int, max_w: int | None, max_h: int | None, rank: int = 0, world: int = 1,
+                       group: int | None = None):
+    """Tile plan for the seam-exchange mode of tiled inference (`srk_fpa_halo_exchange`): column panels overlap by one column
+    per side and swap their seam columns after every layer, row bands keep the receptive-field `halo`.
+    Returns (Ht, Wt, tiles of this rank, exchange, max_cols).  `exchange` is False -- and the plan falls back to
+    receptive-field halos in both directions -- unless every row band of panels lies completely inside this rank's shard and
+    inside one launch group of `group` tiles (a panel must find both neighbours in the same FPA batch).
+    `max_cols` bounds the number of non-owned columns of any panel (argument of the exchange kernel)."""
+    Ht, Wt, tiles = plan_tiles(n_frames, FH, FW, halo, max_w, max_h, halo_x=1)
+    per_band = len({t.x0 for t in tiles})
+    mine = shard_tiles(tiles, rank, world)
+    # the mode is a property of the whole job: every rank must reach the same decision, so every shard boundary is checked
+    bounds = [(r * len(tiles)) // world for r in range(world + 1)]
+    largest = max(b1 - b0 for b0, b1 in zip(bounds, bounds[1:]))
+    exchange = per_band > 1 and all(b % per_band == 0 for b in bounds) and (group is None or group >= largest)
+    if not exchange:
+        Ht, Wt, tiles = plan_tiles(n_frames, FH, FW, halo, max_w, max_h)
+        mine = shard_tiles(tiles, rank, world)
+    max_cols = 2 * max((max(t.own_x0, Wt - t.own_x1) for t in mine), default=0) if exchange else 0
+    return Ht, Wt, mine, exchange, max_cols

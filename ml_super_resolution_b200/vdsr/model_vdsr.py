@@ -25,7 +25,7 @@ from .. import ops
 from ..initializers import tf_conv_name, vdsr_params
 from ..params import ParamArena
 from ..session import Handle, Placeholder
-from ..tiling import MAX_PANEL_W, plan_tiles, shard_tiles
+from ..tiling import MAX_PANEL_W, plan_seam_exchange, plan_tiles
 
 WEIGHT_DECAY = 1e-4  # tf.contrib.layers.l2_regularizer(0.0001), reference :34
 
@@ -117,20 +117,12 @@ class VdsrNet:
         # Column seams: panels of one band overlap by one column per side and swap their seam columns after every layer
         # (srk_fpa_halo_exchange) instead of recomputing a 20-px halo (16 % more pixels at 252-px panels).  That needs all
         # panels of a band in this rank's shard and in one launch group; otherwise fall back to the receptive-field halo.
-        Ht, Wt, tiles = plan_tiles(n, H, W, halo=self.L, max_w=max_panel_w, max_h=tile_rows, halo_x=1)
-        per_band = len({t.x0 for t in tiles})
-        mine = shard_tiles(tiles, rank, world)
+        Ht1, Wt1, _ = plan_tiles(n, H, W, halo=self.L, max_w=max_panel_w, max_h=tile_rows, halo_x=1)
+        Ht, Wt, tiles, exchange, max_cols = plan_seam_exchange(n, H, W, self.L, max_panel_w, tile_rows, rank, world,
+                                                               group=self._tile_group_size(Ht1, Wt1))
         group = self._tile_group_size(Ht, Wt)
-        lo = (rank * len(tiles)) // world
-        exchange = per_band > 1 and lo % per_band == 0 and len(mine) % per_band == 0 and group >= len(mine)
-        if not exchange:
-            Ht, Wt, tiles = plan_tiles(n, H, W, halo=self.L, max_w=max_panel_w, max_h=tile_rows)
-            mine = shard_tiles(tiles, rank, world)
-            group = self._tile_group_size(Ht, Wt)
-        tiles = mine
         if not tiles:
             return out
-        max_cols = max(max(t.own_x0, Wt - t.own_x1) for t in tiles) * 2 if exchange else 0
         for g0 in range(0, len(tiles), group):
             chunk = tiles[g0:g0 + group]
             key = (tuple(t.as_tuple() for t in chunk), str(sd.device))

@@ -138,3 +138,36 @@ def test_srcnn_tap_block_decomposition(k):
     for i in range(k):
         for j in range(k):
             assert float(full[i, j, 0, 0]) == float((i - h + 16) * 100 + (j - h + 16))
+
+
+@pytest.mark.parametrize("FH,FW,halo,max_w,max_h,world", [(2160, 3840, 20, 254, None, 1), (2160, 3840, 20, 254, 570, 4), (2160, 3840, 20, 254, 305, 8),
+                                                          (96, 200, 8, 80, None, 3), (96, 200, 8, 72, 56, 2), (270, 480, 13, 63, None, 1),
+                                                          (48, 56, 13, 40, None, 3), (48, 56, 13, 40, None, 2)])
+def test_seam_exchange_plan(FH, FW, halo, max_w, max_h, world):
+    """Seam-exchange tiling (srk_fpa_halo_exchange): exchange is only chosen when every rank holds whole row bands; in that mode
+    neighbouring panels of a band overlap by at least two columns, each non-owned column is owned by the direct neighbour,
+    and the owned rectangles of all ranks still partition the frame exactly once."""
+    from ml_super_resolution_b200.tiling import plan_seam_exchange
+    cover = np.zeros((FH, FW), np.int32)
+    modes = set()
+    for rank in range(world):
+        Ht, Wt, tiles, exchange, max_cols = plan_seam_exchange(1, FH, FW, halo, max_w, max_h, rank, world)
+        modes.add(exchange)
+        assert Wt <= max_w
+        for i, t in enumerate(tiles):
+            assert 0 <= t.x0 and t.x0 + Wt <= FW and 0 <= t.y0 and t.y0 + Ht <= FH
+            cover[t.y0 + t.own_y0:t.y0 + t.own_y1, t.x0 + t.own_x0:t.x0 + t.own_x1] += 1
+            if exchange:
+                assert t.own_x0 + (Wt - t.own_x1) <= max_cols
+                if t.own_x0 > 0:  # left seam: the previous tile is the same band's left neighbour and owns those columns
+                    p = tiles[i - 1]
+                    assert p.y0 == t.y0 and p.x0 + p.own_x0 <= t.x0 and t.x0 + t.own_x0 <= p.x0 + p.own_x1
+                if t.own_x1 < Wt:
+                    q = tiles[i + 1]
+                    assert q.y0 == t.y0 and q.x0 + q.own_x0 <= t.x0 + t.own_x1 and t.x0 + Wt <= q.x0 + q.own_x1
+    assert len(modes) == 1, "all ranks must agree on the mode"
+    assert (cover == 1).all()
+    if (FW, max_w, world) == (200, 80, 3):
+        assert modes == {False}  # three panels over three ranks: bands are split, receptive-field halos are used
+    if world in (1, 4, 8) and FW == 3840:
+        assert modes == {True}

@@ -306,6 +306,10 @@ def test_enet_generator_tiled_equals_untiled(srk_ops):
     for r in range(2):
         net.forward(sdt, bqt, out=out, max_panel_w=30, tile_rows=40, rank=r, world=2)
     assert np.array_equal(out.cpu().numpy(), full)
+    out = torch.full_like(bqt, float("nan"))  # a band split over three ranks: the column halo is recomputed instead of exchanged
+    for r in range(3):
+        net.forward(sdt, bqt, out=out, max_panel_w=40, rank=r, world=3)
+    assert np.array_equal(out.cpu().numpy(), full)
     sdw = OM.synthetic_images(46, 1, 16, 100, 3)
     bqw = OM.synthetic_images(47, 1, 64, 400, 3)
     got = net.forward(torch.from_numpy(sdw).cuda(), torch.from_numpy(bqw).cuda()).cpu().numpy()
