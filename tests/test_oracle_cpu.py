@@ -129,3 +129,26 @@ def test_ssim_restatement_properties():
     c1 = (0.01 * 1.0) ** 2
     assert np.allclose(O.ssim_tf(a, b, 1.0), (2 * 0.25 * 0.5 + c1) / (0.25 ** 2 + 0.5 ** 2 + c1))
     assert np.array_equal(O.saturate_cast_u8(np.array([-2.0, -1.0, 0.0, 1.0, 2.0], np.float32)), np.array([0, 0, 127, 255, 255], np.uint8))
+
+
+def test_ssim_restatement_against_scipy_filters():
+    """Independent check of the SSIM restatement: the window statistics computed with scipy.ndimage.correlate1d (interior =
+    VALID region) reproduce it to fp64 round-off."""
+    ndi = pytest.importorskip("scipy.ndimage")
+    x = OM.synthetic_images(6, 1, 40, 37, 2).astype(np.float64)
+    y = np.clip(x + 0.1 * np.random.default_rng(0).standard_normal(x.shape), -1, 1)
+    coords = np.arange(11) - 5.0
+    g = np.exp(-coords ** 2 / (2 * 1.5 ** 2))
+    g /= g.sum()
+
+    def filt(t):
+        t = ndi.correlate1d(t, g, axis=1, mode="constant")
+        t = ndi.correlate1d(t, g, axis=2, mode="constant")
+        return t[:, 5:-5, 5:-5, :]
+
+    c1, c2 = (0.01 * 2.0) ** 2, (0.03 * 2.0) ** 2
+    m0, m1 = filt(x), filt(y)
+    lum = (2 * m0 * m1 + c1) / (m0 ** 2 + m1 ** 2 + c1)
+    cs = (2 * filt(x * y) - 2 * m0 * m1 + c2) / (filt(x * x + y * y) - m0 ** 2 - m1 ** 2 + c2)
+    ref = (lum * cs).mean(axis=(1, 2)).mean(axis=-1)
+    assert np.allclose(O.ssim_tf(x, y, 2.0), ref, rtol=0, atol=1e-12)
