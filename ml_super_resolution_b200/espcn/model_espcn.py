@@ -231,10 +231,11 @@ def build_model(lr_source, scaling_factor=3, hr_target=None, params=None, channe
 
 
 def extract_weights(meta_path, ckpt_path):
-    """espcn/espcn/model_espcn.py:150-166 returns {tf_var_name: ndarray}.  Checkpoints here are `.npz`
-    files keyed by the same TF variable names (`meta_path` is accepted and ignored)."""
-    with np.load(ckpt_path) as z:
-        return {k: z[k] for k in z.files if k.endswith(("kernel:0", "bias:0"))}
+    """espcn/espcn/model_espcn.py:150-166 returns {tf_var_name: ndarray}.  `ckpt_path` is an `.npz` file keyed by the TF variable
+    names or a TensorFlow Saver checkpoint prefix (read without TensorFlow); `meta_path` is accepted and ignored: the graph is
+    rebuilt from the variable shapes, not imported."""
+    from ..params import load_params
+    return {k: v for k, v in load_params(ckpt_path).items() if k.endswith(("kernel:0", "bias:0"))}
 
 
 def build_test_model(meta_path, ckpt_path, device="cuda"):

@@ -68,3 +68,17 @@ class ParamArena:
 
     def save(self, path: str, **extra) -> None:
         np.savez(path, **self.to_numpy(), **extra)
+
+
+def load_params(ckpt_path: str) -> "OrderedDict[str, np.ndarray]":
+    """Weights of a checkpoint as {TF tensor name ('f1/kernel:0', ...): ndarray}: either this package's `.npz` (ParamArena.save)
+    or a TensorFlow Saver V2 checkpoint prefix (`model.ckpt-20000` with its `.index` / `.data-*` files), read without
+    TensorFlow by io/tf_checkpoint.py."""
+    import os
+    if ckpt_path.endswith(".npz") or (os.path.exists(ckpt_path) and not os.path.exists(ckpt_path + ".index")):
+        with np.load(ckpt_path) as z:
+            return OrderedDict((k, z[k]) for k in z.files)
+    if os.path.exists(ckpt_path + ".index"):
+        from .io.tf_checkpoint import load_checkpoint, to_params
+        return to_params(load_checkpoint(ckpt_path))
+    raise FileNotFoundError(f"{ckpt_path}: neither an .npz file nor a TensorFlow checkpoint prefix")

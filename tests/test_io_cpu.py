@@ -152,3 +152,18 @@ def test_tf_checkpoint_bundle_roundtrip_and_layout(tmp_path):
     block = entry(0, b"f1/bias", b"A") + entry(3, b"kernel", b"BB") + entry(1, b"2/bias", b"C")
     block += struct.pack("<I", 0) + struct.pack("<I", 1)
     assert list(K._block_entries(block)) == [(b"f1/bias", b"A"), (b"f1/kernel", b"BB"), (b"f2/bias", b"C")]
+
+
+def test_load_params_accepts_npz_and_tf_checkpoint(tmp_path):
+    """`extract_weights` / `build_test_model` take either an .npz keyed by TF tensor names or a Saver checkpoint prefix."""
+    from ml_super_resolution_b200.io import tf_checkpoint as K
+    from ml_super_resolution_b200.params import load_params
+    rng = np.random.default_rng(2)
+    w = {"f1/kernel:0": rng.standard_normal((5, 5, 3, 64)).astype(np.float32), "f1/bias:0": rng.standard_normal(64).astype(np.float32)}
+    np.savez(str(tmp_path / "w.npz"), **w)
+    K.save_checkpoint(str(tmp_path / "model.ckpt-7"), {k[:-2]: v for k, v in w.items()})
+    for path in (str(tmp_path / "w.npz"), str(tmp_path / "model.ckpt-7")):
+        got = load_params(path)
+        assert set(got) == set(w) and all(np.array_equal(got[k], w[k]) for k in w)
+    with pytest.raises(FileNotFoundError):
+        load_params(str(tmp_path / "nothing"))
