@@ -171,3 +171,27 @@ def test_seam_exchange_plan(FH, FW, halo, max_w, max_h, world):
         assert modes == {False}  # three panels over three ranks: bands are split, receptive-field halos are used
     if world in (1, 4, 8) and FW == 3840:
         assert modes == {True}
+
+
+def test_input_pipeline_draws_follow_the_reference_rng_sequence():
+    """The device input pipeline's host side must consume numpy's RandomState exactly like vdsr/vdsr/dataset.py:85-110
+    (shuffle per epoch; per sample randint(w-S), randint(h-S), choice([0,1]), choice(scales)): cropping / flipping with
+    its draws in numpy reproduces the restated generator's hd batch bit for bit, across an epoch boundary."""
+    from oracle import ops as O
+    sys_path_mod = __import__("importlib").import_module("ml_super_resolution_b200.vdsr.dataset")
+    rng = np.random.default_rng(4)
+    images = [rng.integers(0, 256, (int(rng.integers(42, 70)), int(rng.integers(42, 90)), 3), dtype=np.uint8) for _ in range(5)]
+    images.insert(2, rng.integers(0, 256, (20, 100, 3), dtype=np.uint8))  # skipped: smaller than the crop
+    S, B = 41, 4
+    ref = O.vdsr_image_batches(images, [2.0, 3.0, 4.0], S, B, np.random.RandomState(77))
+    draws = sys_path_mod.draw_samples([im.shape for im in images], [2.0, 3.0, 4.0], S, B, np.random.RandomState(77))
+    for _ in range(4):  # 16 samples > 5 usable images: crosses epoch boundaries (re-shuffles)
+        _, hd_ref = next(ref)
+        crops, scales = next(draws)
+        assert crops.shape == (B, 4) and scales.shape == (B,) and set(np.unique(scales)) <= {2.0, 3.0, 4.0}
+        for b, (i, y, x, flip) in enumerate(crops):
+            patch = images[i][y:y + S, x:x + S, :]
+            if flip:
+                patch = patch[:, ::-1, :]
+            hd = np.divide(patch, 255, dtype=np.float32) * 2.0 - 1.0
+            assert np.array_equal(hd.astype(np.float32), hd_ref[b].astype(np.float32))
