@@ -197,6 +197,18 @@ int srk_crop_flip_u8(srk_handle_t h, const uint8_t* pool, const srk_pool_image* 
 /* y = x*a + b with two fp32 roundings (numpy semantics of `sd_image * 2.0 - 1.0`, vdsr/vdsr/dataset.py:113-115); y may be x. */
 int srk_affine_f32(srk_handle_t h, const float* x, size_t n, float a, float b, float* y, srk_stream_t stream);
 
+/* EnhanceNet's input pipeline on the device (enet/enet/datasets.py:100-125): 128x128 uint8 crop, `scipy.misc.imresize` = Pillow's
+ * separable fixed-point resampler (25 % bilinear with antialiasing, then 400 % bicubic), and x.astype(float32)/127.5 - 1.
+ * srk_resample_u8: one or two passes (horizontal first, uint8 intermediate `tmp` [n,H,out_w,C]); kx/ky = int32 coefficients
+ * [out][ks] scaled by 2^22, bx/by = int32 (first input index, count) per output, both computed by the host exactly like
+ * Resample.c precompute_coeffs / normalize_coeffs_8bpc (ml_super_resolution_b200/enet/datasets.py). */
+int srk_crop_u8(srk_handle_t h, const uint8_t* pool, const srk_pool_image* images_device, const srk_crop* crops_device,
+                int n, int S, int C, uint8_t* out, srk_stream_t stream);
+int srk_resample_u8(srk_handle_t h, const uint8_t* x, int n, int H, int W, int C, int out_h, int out_w,
+                    const int32_t* kx, const int32_t* bx, int ksx, const int32_t* ky, const int32_t* by, int ksy,
+                    uint8_t* tmp, uint8_t* y, srk_stream_t stream);
+int srk_u8_to_pm1(srk_handle_t h, const uint8_t* x, size_t n, float* y, srk_stream_t stream);
+
 /* VDSR degrade pre-pass: gaussian(sigma=0.5(s-1), replicate) -> bilinear down to int(H/s) x int(W/s)
  * -> bilinear up (half-pixel, edge clamp), per-sample scale: vdsr/vdsr/dataset.py:13-38. */
 int srk_degrade_gauss_bilinear(srk_handle_t h, const float* hd, int N, int H, int W, int C,

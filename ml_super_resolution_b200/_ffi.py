@@ -69,6 +69,9 @@ SIGNATURES = {
     "srk_rgb_to_y": (_I, [_P, _P, _I64, _F, _F, _F, _F, _P, _P]),
     "srk_saturate_cast_u8": (_I, [_P, _P, _SZ, _F, _F, _P, _P]),
     "srk_feature_mosaic_u8": (_I, [_P, _P, _I, _I, _P, _P]),
+    "srk_crop_u8": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
+    "srk_resample_u8": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P, _P]),
+    "srk_u8_to_pm1": (_I, [_P, _P, _SZ, _P, _P]),
     "srk_crop_flip_u8": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "srk_affine_f32": (_I, [_P, _P, _SZ, _F, _F, _P, _P]),
     "srk_fpa_halo_exchange": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _P]),

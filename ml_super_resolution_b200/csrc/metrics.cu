@@ -143,6 +143,56 @@ __global__ void __launch_bounds__(256) feature_mosaic_kernel(const float* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------ PIL-style uint8 resampling (EnhanceNet input pipeline)
+// One pass of Pillow's separable fixed-point resampler (libImaging/Resample.c, 8 bits per channel): out = clip8((2^21 +
+// sum_k pixel[lo + k] * coeff[o][k]) >> 22), coefficients and bounds precomputed by the host exactly like precompute_coeffs /
+// normalize_coeffs_8bpc.  `along_x` selects the horizontal (over W) or the vertical (over H) pass; x: [n, H, W, C].
+__global__ void __launch_bounds__(256) resample_u8_kernel(const uint8_t* __restrict__ x, int n, int H, int W, int C, int out_size, int along_x,
+                                                          const int32_t* __restrict__ kk, const int32_t* __restrict__ bounds, int ksize,
+                                                          uint8_t* __restrict__ y) {
+  const int OH = along_x ? H : out_size, OW = along_x ? out_size : W;
+  const int64_t total = int64_t(n) * OH * OW * C;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % C);
+    int64_t r = i / C;
+    const int ox = int(r % OW);
+    r /= OW;
+    const int oy = int(r % OH), b = int(r / OH);
+    const int o = along_x ? ox : oy;
+    const int lo = bounds[2 * o], cnt = bounds[2 * o + 1];
+    const int32_t* k = kk + int64_t(o) * ksize;
+    int acc = 1 << 21;
+    if (along_x) {
+      const uint8_t* src = x + ((int64_t(b) * H + oy) * W + lo) * C + c;
+      for (int j = 0; j < cnt; ++j) acc += int(src[int64_t(j) * C]) * k[j];
+    } else {
+      const uint8_t* src = x + ((int64_t(b) * H + lo) * W + ox) * C + c;
+      for (int j = 0; j < cnt; ++j) acc += int(src[int64_t(j) * W * C]) * k[j];
+    }
+    acc >>= 22;
+    y[i] = uint8_t(acc < 0 ? 0 : (acc > 255 ? 255 : acc));
+  }
+}
+__global__ void __launch_bounds__(256) crop_u8_kernel(const uint8_t* __restrict__ pool, const srk_pool_image* __restrict__ images,
+                                                      const srk_crop* __restrict__ crops, int n, int S, int C, uint8_t* __restrict__ out) {
+  const int64_t total = int64_t(n) * S * S * C;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % C);
+    int64_t r = i / C;
+    const int x = int(r % S);
+    r /= S;
+    const int y = int(r % S), b = int(r / S);
+    const srk_crop cr = crops[b];
+    const srk_pool_image im = images[cr.image];
+    const int sx = cr.flip ? (cr.x + S - 1 - x) : (cr.x + x);
+    out[i] = pool[im.offset + (int64_t(cr.y + y) * im.width + sx) * C + c];
+  }
+}
+__global__ void __launch_bounds__(256) u8_to_pm1_kernel(const uint8_t* __restrict__ x, size_t n, float* __restrict__ y) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+    y[i] = __fadd_rn(__fdiv_rn(float(x[i]), 127.5f), -1.f);  // x.astype(float32) / 127.5 - 1.0
+}
+
 static inline int grid1(srk_ctx* h, int64_t items, int block, int per_sm) {
   const int64_t g = (items + block - 1) / block;
   const int64_t cap = int64_t(h->num_sms) * per_sm;
@@ -202,6 +252,46 @@ extern "C" int srk_saturate_cast_u8(srk_handle_t h, const float* x, size_t n, fl
 extern "C" int srk_feature_mosaic_u8(srk_handle_t h, const float* x, int H, int W, uint8_t* y, srk_stream_t stream) {
   SRK_REQUIRE(h && x && y && H > 0 && W > 0, "srk_feature_mosaic_u8: bad argument");
   feature_mosaic_kernel<<<grid1(h, int64_t(64) * H * W, 256, 16), 256, 0, as_stream(stream)>>>(x, H, W, y);
+  SRK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int srk_resample_u8(srk_handle_t h, const uint8_t* x, int n, int H, int W, int C, int out_h, int out_w, const int32_t* kx,
+                               const int32_t* bx, int ksx, const int32_t* ky, const int32_t* by, int ksy, uint8_t* tmp, uint8_t* y,
+                               srk_stream_t stream) {
+  SRK_REQUIRE(h && x && y && n > 0 && H > 0 && W > 0 && C > 0 && out_h > 0 && out_w > 0, "srk_resample_u8: bad argument");
+  const bool hx = out_w != W, vy = out_h != H;
+  SRK_REQUIRE((!hx || (kx && bx && ksx > 0)) && (!vy || (ky && by && ksy > 0)), "srk_resample_u8: missing coefficient table");
+  SRK_REQUIRE(!(hx && vy) || tmp, "srk_resample_u8: a two-pass resize needs the [n,H,out_w,C] intermediate");
+  cudaStream_t s = as_stream(stream);
+  const uint8_t* src = x;
+  if (hx) {
+    uint8_t* dst = vy ? tmp : y;
+    resample_u8_kernel<<<grid1(h, int64_t(n) * H * out_w * C, 256, 16), 256, 0, s>>>(src, n, H, W, C, out_w, 1, kx, bx, ksx, dst);
+    SRK_LAUNCH_CHECK();
+    src = dst;
+  }
+  if (vy) {
+    resample_u8_kernel<<<grid1(h, int64_t(n) * out_h * out_w * C, 256, 16), 256, 0, s>>>(src, n, H, out_w, C, out_h, 0, ky, by, ksy, y);
+    SRK_LAUNCH_CHECK();
+  } else if (!hx) {
+    SRK_CHECK_CUDA(cudaMemcpyAsync(y, x, size_t(n) * H * W * C, cudaMemcpyDeviceToDevice, s));
+  }
+  return 0;
+}
+
+extern "C" int srk_crop_u8(srk_handle_t h, const uint8_t* pool, const srk_pool_image* images_device, const srk_crop* crops_device, int n, int S,
+                           int C, uint8_t* out, srk_stream_t stream) {
+  SRK_REQUIRE(h && pool && images_device && crops_device && out && n > 0 && S > 0 && C > 0, "srk_crop_u8: bad argument");
+  crop_u8_kernel<<<grid1(h, int64_t(n) * S * S * C, 256, 16), 256, 0, as_stream(stream)>>>(pool, images_device, crops_device, n, S, C, out);
+  SRK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int srk_u8_to_pm1(srk_handle_t h, const uint8_t* x, size_t n, float* y, srk_stream_t stream) {
+  SRK_REQUIRE(h && x && y, "srk_u8_to_pm1: null argument");
+  if (n == 0) return 0;
+  u8_to_pm1_kernel<<<grid1(h, int64_t(n), 256, 16), 256, 0, as_stream(stream)>>>(x, n, y);
   SRK_LAUNCH_CHECK();
   return 0;
 }

@@ -444,6 +444,125 @@ def saturate_cast_u8(x, scale=127.5, bias=127.5) -> np.ndarray:
     return np.clip(v, 0.0, 255.0).astype(np.uint8)
 
 
+# ------------------------------------------------------------------------------------------
+# PIL / scipy.misc.imresize on uint8 (EnhanceNet's input pipeline, enet/enet/datasets.py:112-113)
+# ------------------------------------------------------------------------------------------
+# `scipy.misc.imresize(arr, percent, interp)` of a uint8 RGB array is `PIL.Image.fromarray(arr).resize(size, resample)` with
+# size = (arr.shape[:2][::-1] * percent / 100).astype(int), default interp 'bilinear'.  Pillow resamples separably, first
+# horizontally then vertically, with fixed-point coefficients (libImaging/Resample.c): PINNED against the Pillow installed in
+# this environment by tests/test_oracle_cpu.py.
+PIL_PRECISION_BITS = 32 - 8 - 2
+
+
+def _pil_bilinear(x):
+    x = abs(x)
+    return 1.0 - x if x < 1.0 else 0.0
+
+
+def _pil_bicubic(x):
+    a = -0.5
+    x = abs(x)
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+PIL_FILTERS = {"bilinear": (_pil_bilinear, 1.0), "bicubic": (_pil_bicubic, 2.0)}
+
+
+def pil_resample_coeffs(in_size: int, out_size: int, interp: str):
+    """Resample.c precompute_coeffs + normalize_coeffs_8bpc -> (ksize, bounds int32 [out,2] = (xmin, count), kk int32 [out,ksize])."""
+    filt, fsupport = PIL_FILTERS[interp]
+    scale = in_size / out_size
+    filterscale = max(scale, 1.0)
+    support = fsupport * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), np.int32)
+    kk = np.zeros((out_size, ksize), np.int32)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        w = [filt((x + xmin - center + 0.5) * ss) for x in range(xmax)]
+        ww = 0.0
+        for v in w:
+            ww += v
+        if ww != 0.0:
+            w = [v / ww for v in w]
+        bounds[xx] = (xmin, xmax)
+        for x, v in enumerate(w):
+            kk[xx, x] = int(-0.5 + v * (1 << PIL_PRECISION_BITS)) if v < 0 else int(0.5 + v * (1 << PIL_PRECISION_BITS))
+    return ksize, bounds, kk
+
+
+def pil_resize_u8(img: np.ndarray, out_h: int, out_w: int, interp: str) -> np.ndarray:
+    """PIL.Image.resize of a uint8 HWC image: horizontal pass to a uint8 intermediate, then vertical pass; each output is
+    clip8((2^21 + sum pixel * coeff) >> 22)."""
+    img = np.asarray(img, np.uint8)
+    h, w, c = img.shape
+
+    def one_pass(src, in_size, out_size, axis):
+        if in_size == out_size:
+            return src
+        _, bounds, kk = pil_resample_coeffs(in_size, out_size, interp)
+        src = np.moveaxis(src, axis, 0).astype(np.int64)
+        out = np.empty((out_size,) + src.shape[1:], np.uint8)
+        for xx in range(out_size):
+            x0, n = bounds[xx]
+            acc = (1 << (PIL_PRECISION_BITS - 1)) + np.tensordot(kk[xx, :n].astype(np.int64), src[x0:x0 + n], axes=(0, 0))
+            out[xx] = np.clip(acc >> PIL_PRECISION_BITS, 0, 255).astype(np.uint8)
+        return np.moveaxis(out, 0, axis)
+
+    tmp = one_pass(img, w, out_w, 1)
+    return one_pass(tmp, h, out_h, 0)
+
+
+def imresize_percent(arr: np.ndarray, percent: int, interp: str = "bilinear") -> np.ndarray:
+    """scipy.misc.imresize(arr, percent, interp) for a uint8 HWC array (SciPy <= 1.2: PIL based)."""
+    h, w = arr.shape[:2]
+    ow, oh = (np.array([w, h]) * percent / 100.0).astype(int)
+    return pil_resize_u8(arr, int(oh), int(ow), interp)
+
+
+def enet_batch(images, crops):
+    """enet/enet/datasets.py:100-125 for given crop origins [(image, y, x), ...]: 128x128 crop, sd = imresize(hd, 25),
+    bq = imresize(sd, 400, 'bicubic'), all three mapped by x.astype(float32) / 127.5 - 1.0.  -> (sd, bq, hd) float32."""
+    sd_images, bq_images, hd_images = [], [], []
+    for (i, y, x) in crops:
+        hd = images[i][y:y + 128, x:x + 128, :]
+        sd = imresize_percent(hd, 25)
+        bq = imresize_percent(sd, 400, "bicubic")
+        sd_images.append(sd.astype(np.float32) / 127.5 - 1.0)
+        bq_images.append(bq.astype(np.float32) / 127.5 - 1.0)
+        hd_images.append(hd.astype(np.float32) / 127.5 - 1.0)
+    return np.stack(sd_images), np.stack(bq_images), np.stack(hd_images)
+
+
+def enet_image_batches(images, batch_size, rng):
+    """enet/enet/datasets.py:78-127 `image_batches` with the directory replaced by its decoded uint8 images: shuffle per epoch,
+    per sample x = randint(128) then y = randint(128), 128x128 crop; endless generator of (sd, bq, hd)."""
+    order = list(range(len(images)))
+
+    def indices():
+        while True:
+            rng.shuffle(order)
+            for i in order:
+                yield i
+
+    gen = indices()
+    while True:
+        crops = []
+        for _ in range(batch_size):
+            i = next(gen)
+            x = rng.randint(128)
+            y = rng.randint(128)
+            crops.append((i, y, x))
+        yield enet_batch(images, crops)
+
+
 def feature_mosaic_u8(feature_map) -> np.ndarray:
     """vdsr/vdsr/experiment_feature_map_visualize.py:80-110 `encode_feature_map` before encode_png: split the 64 channels,
     concat 8 per row along the width, rows along the height, saturate_cast(x*127.5+127.5)."""

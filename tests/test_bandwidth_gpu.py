@@ -135,3 +135,18 @@ def test_evaluation_post_pass(srk_ops):
     assert np.array_equal(M.saturate_cast_u8(_dev(x)).cpu().numpy(), O.saturate_cast_u8(x))
     fm = (np.random.default_rng(4).standard_normal((1, 13, 17, 64)) * 0.7).astype(np.float32)
     assert np.array_equal(M.feature_mosaic_u8(_dev(fm)).cpu().numpy(), O.feature_mosaic_u8(fm))
+
+
+def test_enet_device_input_pipeline_is_bit_identical_to_pillow_path(srk_ops):
+    """EnhanceNet's batches cut and resized on the device (uint8 crop, Pillow-arithmetic 25 % bilinear and 400 % bicubic,
+    /127.5 - 1) equal the restated reference generator bit for bit (the restatement itself is pinned against Pillow in the
+    CPU suite); enet/enet/datasets.py:78-127."""
+    from ml_super_resolution_b200.enet import datasets as ED
+    rng = np.random.default_rng(21)
+    images = [rng.integers(0, 256, (int(rng.integers(256, 300)), int(rng.integers(256, 330)), 3), dtype=np.uint8) for _ in range(3)]
+    ref = O.enet_image_batches(images, 5, np.random.RandomState(9))
+    got = ED.image_batches(images, 4, 5, seed=9)
+    for _ in range(3):
+        sd_r, bq_r, hd_r = next(ref)
+        sd_g, bq_g, hd_g = next(got)
+        assert np.array_equal(hd_g.cpu().numpy(), hd_r) and np.array_equal(sd_g.cpu().numpy(), sd_r) and np.array_equal(bq_g.cpu().numpy(), bq_r)

@@ -195,3 +195,13 @@ def test_input_pipeline_draws_follow_the_reference_rng_sequence():
                 patch = patch[:, ::-1, :]
             hd = np.divide(patch, 255, dtype=np.float32) * 2.0 - 1.0
             assert np.array_equal(hd.astype(np.float32), hd_ref[b].astype(np.float32))
+
+
+def test_enet_resample_tables_match_the_pinned_restatement():
+    """The product's host-side Pillow coefficient tables (enet/datasets.py) equal the oracle's, which is pinned against Pillow."""
+    from oracle import ops as O
+    from ml_super_resolution_b200.enet.datasets import resample_tables
+    for (i, o, interp) in [(128, 32, "bilinear"), (32, 128, "bicubic"), (91, 40, "bilinear"), (40, 91, "bicubic")]:
+        ks, b, k = resample_tables(i, o, interp)
+        ks2, b2, k2 = O.pil_resample_coeffs(i, o, interp)
+        assert ks == ks2 and np.array_equal(b, b2) and np.array_equal(k, k2)

@@ -152,3 +152,25 @@ def test_ssim_restatement_against_scipy_filters():
     cs = (2 * filt(x * y) - 2 * m0 * m1 + c2) / (filt(x * x + y * y) - m0 ** 2 - m1 ** 2 + c2)
     ref = (lum * cs).mean(axis=(1, 2)).mean(axis=-1)
     assert np.allclose(O.ssim_tf(x, y, 2.0), ref, rtol=0, atol=1e-12)
+
+
+def test_pil_resize_restatement_is_pinned_against_pillow():
+    """EnhanceNet's input pipeline resizes uint8 patches with scipy.misc.imresize = PIL.Image.resize
+    (enet/enet/datasets.py:112-113).  The restatement of Pillow's fixed-point separable resampler must match the Pillow
+    installed here BIT FOR BIT: the 128->32 bilinear (antialiased) and 32->128 bicubic cases the reference uses, plus odd sizes."""
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(11)
+    cases = [((128, 128), (32, 32), "bilinear"), ((32, 32), (128, 128), "bicubic"), ((57, 91), (23, 40), "bilinear"),
+             ((23, 40), (57, 91), "bicubic"), ((64, 48), (17, 48), "bicubic"), ((40, 40), (40, 13), "bilinear")]
+    res = {"bilinear": Image.BILINEAR, "bicubic": Image.BICUBIC}
+    for (h, w), (oh, ow), interp in cases:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        ref = np.asarray(Image.fromarray(img).resize((ow, oh), resample=res[interp]))
+        got = O.pil_resize_u8(img, oh, ow, interp)
+        assert np.array_equal(got, ref), (h, w, oh, ow, interp, int(np.abs(got.astype(int) - ref.astype(int)).max()))
+    hd = rng.integers(0, 256, (128, 128, 3), dtype=np.uint8)
+    sd = np.asarray(Image.fromarray(hd).resize((32, 32), resample=Image.BILINEAR))
+    bq = np.asarray(Image.fromarray(sd).resize((128, 128), resample=Image.BICUBIC))
+    s, b, h_ = O.enet_batch([hd], [(0, 0, 0)])
+    assert np.array_equal(s[0], sd.astype(np.float32) / 127.5 - 1.0) and np.array_equal(b[0], bq.astype(np.float32) / 127.5 - 1.0)
+    assert np.array_equal(h_[0], hd.astype(np.float32) / 127.5 - 1.0)
