@@ -5,12 +5,16 @@ TEST INFRASTRUCTURE ONLY.  Nothing in the product package
 `tests/`, `__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline` /
 `--impl reference` legs.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures
- and its arithmetic lives in un-vendored TensorFlow 1.8 /
-scikit-image 0.14 / PIL, none of which can be installed in this image.  The
+PARITY UNPINNED, with one exception: the reference ships no tests, golden vectors
+or fixtures and its arithmetic lives in un-vendored
+TensorFlow 1.8 / scikit-image 0.14, which cannot be installed in this image.  The
 oracle restates the published semantics of those ops and
 is cross-validated internally (torch fp64 conv vs explicit numpy im2col GEMM vs
-finite differences; bilinear vs cv2.INTER_LINEAR; pixel-shuffle vs the
-reference's own numpy pack/unpack code paths restated verbatim).
+finite differences; bilinear vs cv2.INTER_LINEAR; SSIM vs scipy.ndimage filters;
+pixel-shuffle vs the reference's own numpy pack/unpack code paths restated
+verbatim; the tf.train.Example wire codec vs the protobuf runtime).
+PINNED: Pillow IS present here, and `ops.pil_resize_u8` -- what
+`scipy.misc.imresize` does in EnhanceNet's input pipeline -- is checked bit for
+bit against it (tests/test_oracle_cpu.py).
 """
 from . import ops, models  # noqa: F401
