@@ -15,6 +15,8 @@ pixel-shuffle vs the reference's own numpy pack/unpack code paths restated
 verbatim; the tf.train.Example wire codec vs the protobuf runtime).
 PINNED: Pillow IS present here, and `ops.pil_resize_u8` -- what
 `scipy.misc.imresize` does in EnhanceNet's input pipeline -- is checked bit for
-bit against it (tests/test_oracle_cpu.py).
+bit against it (tests/test_oracle_cpu.py); the gaussian of the degrade pre-pass is
+checked to 1e-12 against `scipy.ndimage.gaussian_filter(mode='nearest',
+truncate=4.0)`, the very call `skimage.filters.gaussian` delegates to.
 """
 from . import ops, models  # noqa: F401
