@@ -86,7 +86,7 @@ def lib() -> C.CDLL:
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise SrkError(f"{LIB_PATH} is missing: build it with __graft_entry__.build(); there is no CPU fallback")
-        l = C.CDLL(os.environ.get("SRK_LIB_OVERRIDE") or LIB_PATH)  # override: development builds (tools/trace_conv.py)
+        l = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(l, name)
             fn.restype = res

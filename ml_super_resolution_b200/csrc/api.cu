@@ -30,7 +30,22 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-int make_tensor_map_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint32_t cols, uint32_t box_rows) {
+int check_device(srk_ctx* h) {
+  SRK_REQUIRE(h != nullptr, "libsrk: null handle");
+  int cur = -1;
+  SRK_CHECK_CUDA(cudaGetDevice(&cur));
+  SRK_REQUIRE(cur == h->device, "libsrk handle belongs to device %d but the current device is %d (one handle per device)", h->device, cur);
+  return 0;
+}
+
+int make_tensor_map_2d(srk_ctx* h, CUtensorMap* out, const void* gptr, uint64_t rows, uint32_t cols, uint32_t box_rows) {
+  const srk_tmap_key key{gptr, rows, cols, box_rows, cols, 2};
+  auto it = h->tmaps.find(key);
+  if (it != h->tmaps.end()) {
+    *out = it->second;
+    return 0;
+  }
+  if (h->tmaps.size() > 4096) h->tmaps.clear();  // bounded: a long-lived handle that sees ever new buffers starts over
   EncodeTiledFn enc = encode_fn();
   SRK_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
   const uint32_t row_bytes = cols * 2;
@@ -51,6 +66,7 @@ int make_tensor_map_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint32
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SRK_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (ptr %p rows %llu cols %u)", int(r), gptr,
               (unsigned long long)rows, cols);
+  h->tmaps.emplace(key, *out);
   return 0;
 }
 

@@ -51,10 +51,9 @@ __global__ void pixel_shuffle_kernel(const float* __restrict__ x, int N, int H, 
 constexpr int kBicubicTableSize = 1 << 10;
 __constant__ float c_bicubic[(kBicubicTableSize + 1) * 2];
 
-static int ensure_bicubic_table() {
-  static std::once_flag once;
-  static cudaError_t err = cudaSuccess;
-  std::call_once(once, [] {
+static int ensure_bicubic_table(srk_ctx* h) {  // a __constant__ symbol exists once per device: uploaded once per handle
+  cudaError_t err = cudaSuccess;
+  if (first_use(h, reinterpret_cast<const void*>(&c_bicubic))) {
     // TF-1.x InitCoeffsTable: double arithmetic on a float abscissa, rounded to float on store.
     static float tab[(kBicubicTableSize + 1) * 2];
     static const double A = -0.75;
@@ -65,7 +64,7 @@ static int ensure_bicubic_table() {
       tab[i * 2 + 1] = float(((A * x - 5 * A) * x + 8 * A) * x - 4 * A);
     }
     err = cudaMemcpyToSymbol(c_bicubic, tab, sizeof tab);
-  });
+  }
   SRK_CHECK_CUDA(err);
   return 0;
 }
@@ -356,6 +355,7 @@ using namespace srk;
 
 extern "C" int srk_pixel_shuffle(srk_handle_t h, const float* x, int N, int H, int W, int C, int r, float* y, srk_stream_t stream) {
   SRK_REQUIRE(h && x && y && r >= 1, "srk_pixel_shuffle: bad argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   const int64_t total = int64_t(N) * H * W * C * r * r;
   if (total == 0) return 0;
   pixel_shuffle_kernel<<<grid_for(h, total, 256), 256, 0, as_stream(stream)>>>(x, N, H, W, C, r, y, 0);
@@ -365,6 +365,7 @@ extern "C" int srk_pixel_shuffle(srk_handle_t h, const float* x, int N, int H, i
 extern "C" int srk_pixel_unshuffle(srk_handle_t h, const float* x, int N, int H, int W, int C, int r, float* y, srk_stream_t stream) {
   // x: [N, H*r, W*r, C] -> y: [N, H, W, C*r*r]
   SRK_REQUIRE(h && x && y && r >= 1, "srk_pixel_unshuffle: bad argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   const int64_t total = int64_t(N) * H * W * C * r * r;
   if (total == 0) return 0;
   pixel_shuffle_kernel<<<grid_for(h, total, 256), 256, 0, as_stream(stream)>>>(x, N, H, W, C, r, y, 1);
@@ -375,7 +376,8 @@ extern "C" int srk_pixel_unshuffle(srk_handle_t h, const float* x, int N, int H,
 extern "C" int srk_resize_bicubic_tf1(srk_handle_t h, const float* x, int N, int H, int W, int C, int OH, int OW, float* y,
                                       srk_stream_t stream) {
   SRK_REQUIRE(h && x && y && OH > 0 && OW > 0, "srk_resize_bicubic_tf1: bad argument");
-  if (int rc = ensure_bicubic_table()) return rc;
+  if (int rc_dev = check_device(h)) return rc_dev;
+  if (int rc = ensure_bicubic_table(h)) return rc;
   const int64_t total = int64_t(N) * OH * OW * C;
   resize_bicubic_kernel<<<grid_for(h, total, 256), 256, 0, as_stream(stream)>>>(x, N, H, W, C, OH, OW, y);
   SRK_LAUNCH_CHECK();
@@ -412,6 +414,7 @@ __global__ void __launch_bounds__(256) affine_kernel(const float* __restrict__ x
 extern "C" int srk_crop_flip_u8(srk_handle_t h, const uint8_t* pool, const srk_pool_image* images_device, const srk_crop* crops_device,
                                 int n, int S, int C, float* out01, float* out_pm1, srk_stream_t stream) {
   SRK_REQUIRE(h && pool && images_device && crops_device && (out01 || out_pm1) && n > 0 && S > 0 && C > 0, "srk_crop_flip_u8: bad argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   const int64_t total = int64_t(n) * S * S * C;
   crop_flip_u8_kernel<<<grid_for(h, total, 256), 256, 0, as_stream(stream)>>>(pool, images_device, crops_device, n, S, C, out01, out_pm1);
   SRK_LAUNCH_CHECK();
@@ -420,6 +423,7 @@ extern "C" int srk_crop_flip_u8(srk_handle_t h, const uint8_t* pool, const srk_p
 
 extern "C" int srk_affine_f32(srk_handle_t h, const float* x, size_t n, float a, float b, float* y, srk_stream_t stream) {
   SRK_REQUIRE(h && x && y, "srk_affine_f32: null argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   if (n == 0) return 0;
   affine_kernel<<<grid_for(h, int64_t(n), 256), 256, 0, as_stream(stream)>>>(x, n, a, b, y);
   SRK_LAUNCH_CHECK();
@@ -429,14 +433,12 @@ extern "C" int srk_affine_f32(srk_handle_t h, const float* x, size_t n, float a,
 extern "C" int srk_degrade_gauss_bilinear(srk_handle_t h, const float* hd, int N, int H, int W, int C, const float* scale_per_sample,
                                           float* sd, srk_stream_t stream) {
   SRK_REQUIRE(h && hd && sd && scale_per_sample, "srk_degrade_gauss_bilinear: null argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   SRK_REQUIRE(H <= 512 && W <= 512, "srk_degrade_gauss_bilinear: patch %dx%d exceeds 512 (per-patch kernel)", H, W);
   const int smem = 2 * H * W * 4;
   SRK_REQUIRE(smem <= h->smem_optin - 16 * 1024, "srk_degrade_gauss_bilinear: patch %dx%d does not fit shared memory", H, W);
-  static int attr_smem = 0;
-  if (smem > attr_smem && smem > 48 * 1024) {
-    SRK_CHECK_CUDA(cudaFuncSetAttribute(degrade_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
-  }
+  if (smem > 48 * 1024 && first_use(h, reinterpret_cast<const void*>(&degrade_kernel)))  // raised once, to the device's limit
+    SRK_CHECK_CUDA(cudaFuncSetAttribute(degrade_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin - 16 * 1024));
   degrade_kernel<<<N * C, 256, smem, as_stream(stream)>>>(hd, N, H, W, C, scale_per_sample, sd);
   SRK_LAUNCH_CHECK();
   return 0;
@@ -444,6 +446,7 @@ extern "C" int srk_degrade_gauss_bilinear(srk_handle_t h, const float* hd, int N
 
 extern "C" int srk_fpa_upsample2(srk_handle_t h, const void* x_fpa, int n_img, int H, int W, void* y_fpa, srk_stream_t stream) {
   SRK_REQUIRE(h && x_fpa && y_fpa, "srk_fpa_upsample2: null argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   const FpaGeom go = fpa_geom(n_img, 2 * H, 2 * W);
   fpa_upsample2_kernel<<<grid_for(h, go.rows_valid * 8, 256), 256, 0, as_stream(stream)>>>(
       static_cast<const uint4*>(x_fpa), n_img, H, W, static_cast<uint4*>(y_fpa), go.rows_valid);
@@ -452,6 +455,7 @@ extern "C" int srk_fpa_upsample2(srk_handle_t h, const void* x_fpa, int n_img, i
 }
 extern "C" int srk_fpa_upsample2_bwd(srk_handle_t h, const void* dy_fpa, int n_img, int H, int W, void* dx_fpa, srk_stream_t stream) {
   SRK_REQUIRE(h && dy_fpa && dx_fpa, "srk_fpa_upsample2_bwd: null argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   const FpaGeom gi = fpa_geom(n_img, H, W);
   fpa_upsample2_bwd_kernel<<<grid_for(h, gi.rows_valid * 8, 256), 256, 0, as_stream(stream)>>>(
       static_cast<const uint4*>(dy_fpa), n_img, H, W, static_cast<uint4*>(dx_fpa), gi.rows_valid);
@@ -462,6 +466,7 @@ extern "C" int srk_fpa_upsample2_bwd(srk_handle_t h, const void* dy_fpa, int n_i
 extern "C" int srk_mse_fwd_bwd(srk_handle_t h, const float* sr, const float* hd, size_t numel, double numel_total, float* loss_accum,
                                float* dsr, srk_stream_t stream) {
   SRK_REQUIRE(h && sr && hd && loss_accum, "srk_mse_fwd_bwd: null argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   SRK_REQUIRE((reinterpret_cast<uintptr_t>(sr) | reinterpret_cast<uintptr_t>(hd) | reinterpret_cast<uintptr_t>(dsr)) % 16 == 0,
               "srk_mse_fwd_bwd: pointers must be 16-byte aligned");
   if (numel == 0) return 0;
@@ -474,6 +479,7 @@ extern "C" int srk_mse_fwd_bwd(srk_handle_t h, const float* sr, const float* hd,
 extern "C" int srk_l2norm_rows_mean_fwd_bwd(srk_handle_t h, const float* sr, const float* hd, int rows, int cols, float* loss_accum,
                                             float* dsr, int sr_act, srk_stream_t stream) {
   SRK_REQUIRE(h && sr && hd && loss_accum && rows > 0 && cols > 0, "srk_l2norm_rows_mean_fwd_bwd: bad argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   SRK_REQUIRE(sr_act == SRK_ACT_NONE || sr_act == SRK_ACT_TANH, "srk_l2norm_rows_mean_fwd_bwd: sr_act must be NONE or TANH");
   l2norm_rows_kernel<<<rows, 256, 0, as_stream(stream)>>>(sr, hd, rows, cols, loss_accum, dsr, sr_act);
   SRK_LAUNCH_CHECK();
@@ -483,6 +489,7 @@ extern "C" int srk_l2norm_rows_mean_fwd_bwd(srk_handle_t h, const float* sr, con
 extern "C" int srk_adam_step(srk_handle_t h, float* w, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2,
                              float eps, int64_t t, float weight_decay, const float* decay_mask, srk_stream_t stream) {
   SRK_REQUIRE(h && w && g && m && v && t >= 1, "srk_adam_step: bad argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   if (n == 0) return 0;
   const double lr_t = double(lr) * sqrt(1.0 - pow(double(beta2), double(t))) / (1.0 - pow(double(beta1), double(t)));
   adam_kernel<<<grid_for(h, int64_t(n), 256), 256, 0, as_stream(stream)>>>(w, g, m, v, n, float(lr_t), nullptr, beta1, beta2, eps,
@@ -494,6 +501,7 @@ extern "C" int srk_adam_step(srk_handle_t h, float* w, const float* g, float* m,
 extern "C" int srk_momentum_clip_step(srk_handle_t h, float* w, const float* g, float* accum, size_t n, float lr, float momentum,
                                       float gradient_cap, float weight_decay, const float* decay_mask, srk_stream_t stream) {
   SRK_REQUIRE(h && w && g && accum && lr > 0.f, "srk_momentum_clip_step: bad argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   if (n == 0) return 0;
   momentum_clip_kernel<<<grid_for(h, int64_t(n), 256), 256, 0, as_stream(stream)>>>(w, g, accum, n, lr, momentum, gradient_cap / lr,
                                                                                    weight_decay, decay_mask);
@@ -504,6 +512,7 @@ extern "C" int srk_momentum_clip_step(srk_handle_t h, float* w, const float* g, 
 extern "C" int srk_adam_step_dev(srk_handle_t h, float* w, const float* g, float* m, float* v, size_t n, const float* lr_t_device,
                                  float beta1, float beta2, float eps, float weight_decay, const float* decay_mask, srk_stream_t stream) {
   SRK_REQUIRE(h && w && g && m && v && lr_t_device, "srk_adam_step_dev: bad argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   if (n == 0) return 0;
   adam_kernel<<<grid_for(h, int64_t(n), 256), 256, 0, as_stream(stream)>>>(w, g, m, v, n, 0.f, lr_t_device, beta1, beta2, eps,
                                                                          weight_decay, decay_mask);

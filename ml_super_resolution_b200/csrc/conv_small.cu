@@ -223,13 +223,10 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const ConvFirstParams p
 }
 
 template <int KS, int CIN>
-static int launch_conv_first(const ConvFirstParams& p, cudaStream_t s) {
+static int launch_conv_first(srk_ctx* h, const ConvFirstParams& p, cudaStream_t s) {
   const int smem = KS * KS * CIN * 64 * 4;
-  static bool attr_set = false;
-  if (!attr_set && smem > 48 * 1024) {
+  if (smem > 48 * 1024 && first_use(h, reinterpret_cast<const void*>(&conv_first_kernel<KS, CIN>)))
     SRK_CHECK_CUDA(cudaFuncSetAttribute(conv_first_kernel<KS, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
   const int grid = int((p.rows_valid + 127) / 128);
   conv_first_kernel<KS, CIN><<<grid, 128, smem, s>>>(p);
   SRK_LAUNCH_CHECK();
@@ -425,6 +422,7 @@ using namespace srk;
 extern "C" int srk_pack_conv_weights(srk_handle_t h, const float* w_hwio, int k, int cin, int cout, int mode, int np, int cinp,
                                      void* packed_bf16, srk_stream_t stream) {
   SRK_REQUIRE(h && w_hwio && packed_bf16, "srk_pack_conv_weights: null argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   if (mode == SRK_PACK_FIRST || mode == SRK_PACK_FIRST_ROT180T) {
     // one job through the batched kernel (jobs array passed by value through a tiny device copy is avoided: use the single-job kernel)
     const int kt = (mode == SRK_PACK_FIRST) ? k * k * cin : k * k * cout;
@@ -448,6 +446,7 @@ extern "C" int srk_conv_first(srk_handle_t h, const float* x, int n_frames, int 
                               const float* bias, int k, int pad_mode, int act, const srk_panel* panels, int n_img, int H,
                               int W, void* y_fpa, const void* relu_mask_src, srk_stream_t stream) {
   SRK_REQUIRE(h && x && w_hwio && y_fpa, "srk_conv_first: null argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   const int halo = (pad_mode == SRK_PAD_VALID) ? k - 1 : 0;
   SRK_REQUIRE(panels || (n_frames == n_img && FH == H + halo && FW == W + halo),
               "srk_conv_first: without panels the frame (%dx%d) must match the output geometry (%dx%d, k=%d)", FH, FW, H, W, k);
@@ -472,7 +471,7 @@ extern "C" int srk_conv_first(srk_handle_t h, const float* x, int n_frames, int 
   p.act = act;
   cudaStream_t s = as_stream(stream);
 #define SRK_CASE(KS, CIN) \
-  if (k == KS && cin == CIN) return launch_conv_first<KS, CIN>(p, s);
+  if (k == KS && cin == CIN) return launch_conv_first<KS, CIN>(h, p, s);
   SRK_CASE(3, 1) SRK_CASE(3, 3) SRK_CASE(5, 1) SRK_CASE(5, 3) SRK_CASE(9, 1) SRK_CASE(9, 3)
 #undef SRK_CASE
   set_error("srk_conv_first: unsupported (k=%d, cin=%d)", k, cin);
@@ -520,6 +519,7 @@ __global__ void __launch_bounds__(256) fpa_halo_exchange_kernel(__nv_bfloat16* _
 extern "C" int srk_fpa_halo_exchange(srk_handle_t h, void* x_fpa, int C, const srk_panel* panels, int n_img, int H, int W, int max_cols,
                                      srk_stream_t stream) {
   SRK_REQUIRE(h && x_fpa && panels && C % 8 == 0 && max_cols > 0, "srk_fpa_halo_exchange: bad argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   const int64_t total = int64_t(n_img) * H * max_cols * (C / 8);
   const int grid = int(std::min<int64_t>((total + 255) / 256, int64_t(h->num_sms) * 8));
   fpa_halo_exchange_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<__nv_bfloat16*>(x_fpa), C, panels, n_img, H, W, max_cols);
@@ -529,6 +529,7 @@ extern "C" int srk_fpa_halo_exchange(srk_handle_t h, void* x_fpa, int C, const s
 
 extern "C" int srk_fpa_to_nhwc(srk_handle_t h, const void* x_fpa, int C, int n_img, int H, int W, float* y, srk_stream_t stream) {
   SRK_REQUIRE(h && x_fpa && y, "srk_fpa_to_nhwc: null argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   const int64_t total = int64_t(n_img) * H * W * C;
   const int grid = int(std::min<int64_t>((total + 255) / 256, int64_t(h->num_sms) * 16));
   fpa_to_nhwc_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(x_fpa), C, n_img, H, W, y);
@@ -538,6 +539,7 @@ extern "C" int srk_fpa_to_nhwc(srk_handle_t h, const void* x_fpa, int C, int n_i
 
 extern "C" int srk_nhwc_to_fpa_pad(srk_handle_t h, const float* x, int C, int Cp, int n_img, int H, int W, void* y_fpa, srk_stream_t stream) {
   SRK_REQUIRE(h && x && y_fpa && Cp >= C && C > 0, "srk_nhwc_to_fpa_pad: bad argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   const FpaGeom g = fpa_geom(n_img, H, W);
   if (Cp % 8 == 0 && g.rows_valid < (int64_t(1) << 31)) {
     const int64_t total8 = g.rows_valid * (Cp / 8);
@@ -554,12 +556,14 @@ extern "C" int srk_nhwc_to_fpa_pad(srk_handle_t h, const float* x, int C, int Cp
 }
 
 extern "C" int srk_nhwc_to_fpa(srk_handle_t h, const float* x, int C, int n_img, int H, int W, void* y_fpa, srk_stream_t stream) {
+  if (int rc_dev = check_device(h)) return rc_dev;
   return srk_nhwc_to_fpa_pad(h, x, C, C, n_img, H, W, y_fpa, stream);
 }
 
 extern "C" int srk_conv_first_wgrad(srk_handle_t h, const float* x, int n_img, int H, int W, int cin, int k, const void* dy_fpa,
                                     float* dw_hwio, float* dbias, srk_stream_t stream) {
   SRK_REQUIRE(h && x && dy_fpa && dw_hwio && dbias, "srk_conv_first_wgrad: null argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   const int64_t npix = int64_t(n_img) * H * W;
   SRK_REQUIRE(npix < (int64_t(1) << 31), "srk_conv_first_wgrad: too many pixels");
   const int grid = int(std::min<int64_t>((npix + 63) / 64, int64_t(h->num_sms)));
@@ -580,6 +584,7 @@ extern "C" int srk_conv_first_wgrad(srk_handle_t h, const float* x, int n_img, i
 extern "C" int srk_conv_last_wgrad(srk_handle_t h, const void* x_fpa, const float* dy, int n_img, int H, int W, int cout,
                                    float* dw_hwio, float* dbias, srk_stream_t stream) {
   SRK_REQUIRE(h && x_fpa && dy && dw_hwio && dbias, "srk_conv_last_wgrad: null argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   const int64_t npix = int64_t(n_img) * H * W;
   SRK_REQUIRE(npix < (int64_t(1) << 31), "srk_conv_last_wgrad: too many pixels");
   const int grid = int(std::min<int64_t>((npix + 63) / 64, int64_t(h->num_sms)));
@@ -600,6 +605,7 @@ extern "C" int srk_conv_last_wgrad(srk_handle_t h, const void* x_fpa, const floa
 extern "C" int srk_pack_conv_weights_batched(srk_handle_t h, const float* arena, const srk_pack_job* jobs_device, int n_jobs,
                                              int64_t total_elems, void* out_base, srk_stream_t stream) {
   SRK_REQUIRE(h && arena && jobs_device && out_base && n_jobs > 0 && n_jobs <= 256, "srk_pack_conv_weights_batched: bad argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   const int grid = int(std::min<int64_t>((total_elems + 255) / 256, int64_t(h->num_sms) * 8));
   SRK_CHECK_CUDA(launch_pdl(pack_weights_batched_kernel, dim3(grid), dim3(256), n_jobs * sizeof(srk_pack_job), as_stream(stream), arena,
                             jobs_device, n_jobs, total_elems, static_cast<uint8_t*>(out_base)));
@@ -609,6 +615,7 @@ extern "C" int srk_pack_conv_weights_batched(srk_handle_t h, const float* arena,
 extern "C" int srk_sumsq_masked(srk_handle_t h, const float* w, const float* mask, size_t n, float scale, float* out_accum,
                                 srk_stream_t stream) {
   SRK_REQUIRE(h && w && out_accum, "srk_sumsq_masked: null argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   if (n == 0) return 0;
   const int grid = int(std::min<int64_t>((int64_t(n) + 255) / 256, int64_t(h->num_sms) * 4));
   sumsq_masked_kernel<<<grid, 256, 0, as_stream(stream)>>>(w, mask, n, scale, out_accum);

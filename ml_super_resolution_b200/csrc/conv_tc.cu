@@ -1045,16 +1045,13 @@ __global__ void __launch_bounds__(ConvGatherCfg<KS, CIN>::kThreads, 1) conv_gath
 template <int KS, int CIN>
 static int launch_conv_gather(srk_ctx* h, ConvGatherParams& gp, const void* w_packed, void* y_fpa, cudaStream_t stream) {
   using L = ConvGatherCfg<KS, CIN>;
-  static bool attr_set = false;
   SRK_REQUIRE(L::kTotal <= h->smem_optin, "conv_first_tc: needs %d B smem, device allows %d", L::kTotal, h->smem_optin);
-  if (!attr_set) {
+  if (first_use(h, reinterpret_cast<const void*>(&conv_gather_tc_kernel<KS, CIN>)))
     SRK_CHECK_CUDA(cudaFuncSetAttribute(conv_gather_tc_kernel<KS, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    attr_set = true;
-  }
   ConvTcParams& p = gp.tc;
   p.num_tiles = int((p.rows_valid + 127) / 128);
-  if (int rc = make_tensor_map_2d(&p.map_w, w_packed, uint64_t(L::kBlocks * 64), 64, 64)) return rc;
-  if (int rc = make_tensor_map_2d(&p.map_out, y_fpa, uint64_t(p.rows_valid), 64, 128)) return rc;
+  if (int rc = make_tensor_map_2d(h, &p.map_w, w_packed, uint64_t(L::kBlocks * 64), 64, 64)) return rc;
+  if (int rc = make_tensor_map_2d(h, &p.map_out, y_fpa, uint64_t(p.rows_valid), 64, 128)) return rc;
   const int grid = p.num_tiles < h->num_sms ? p.num_tiles : h->num_sms;
   SRK_CHECK_CUDA(launch_pdl(conv_gather_tc_kernel<KS, CIN>, dim3(grid), dim3(L::kThreads), L::kTotal, stream, gp));
   return 0;
@@ -1064,22 +1061,19 @@ static int launch_conv_gather(srk_ctx* h, ConvGatherParams& gp, const void* w_pa
 template <int CIN, int NP, int KS, int EPI>
 static int launch_conv_tc(srk_ctx* h, ConvTcParams& p, const void* x, const void* w_packed, void* y_fpa, cudaStream_t stream) {
   using L = ConvTcCfg<CIN, NP, KS, EPI>;
-  static bool attr_set = false;
   SRK_REQUIRE(L::kTotal <= h->smem_optin, "conv_tc: needs %d B smem, device allows %d", L::kTotal, h->smem_optin);
-  if (!attr_set) {
+  if (first_use(h, reinterpret_cast<const void*>(&conv_tc_kernel<CIN, NP, KS, EPI>)))
     SRK_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<CIN, NP, KS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    attr_set = true;
-  }
   p.num_tiles = int((p.rows_valid + L::kTileStride - 1) / L::kTileStride);
   constexpr int kChunkRows = L::kChunkRows;
   const int span_chunks = (2 * L::kHalo * p.Wp + 128 + kChunkRows - 1) / kChunkRows + 1;
   SRK_REQUIRE(span_chunks + 2 <= L::kRingSlots,
               "conv_tc: image width %d too large for the %dx%d flat-stream kernel (a tile needs %d chunks resident, ring holds %d); "
               "split the frame into column panels", p.W, KS, KS, span_chunks, L::kRingSlots);
-  if (int rc = make_tensor_map_2d(&p.map_in, x, uint64_t(p.rows_valid), CIN, kChunkRows)) return rc;
-  if (int rc = make_tensor_map_2d(&p.map_w, w_packed, uint64_t(KS * KS * NP), CIN, NP)) return rc;
+  if (int rc = make_tensor_map_2d(h, &p.map_in, x, uint64_t(p.rows_valid), CIN, kChunkRows)) return rc;
+  if (int rc = make_tensor_map_2d(h, &p.map_w, w_packed, uint64_t(KS * KS * NP), CIN, NP)) return rc;
   if (EPI == EPI_FPA) {
-    if (int rc = make_tensor_map_2d(&p.map_out, y_fpa, uint64_t(p.rows_valid), NP, L::kTileStride)) return rc;
+    if (int rc = make_tensor_map_2d(h, &p.map_out, y_fpa, uint64_t(p.rows_valid), NP, L::kTileStride)) return rc;
   }
   const int grid = p.num_tiles < h->num_sms ? p.num_tiles : h->num_sms;
   SRK_CHECK_CUDA(launch_pdl(conv_tc_kernel<CIN, NP, KS, EPI>, dim3(grid), dim3(L::kThreads), L::kTotal, stream, p));
@@ -1121,6 +1115,7 @@ extern "C" int srk_conv_tc(srk_handle_t h, const void* x_fpa, int cin_p, const v
                            int cout_p, int act, int n_img, int H, int W, void* y_fpa, const void* mask_src,
                            int mask_kind, const void* addend_fpa, int relu_after_add, srk_stream_t stream) {
   SRK_REQUIRE(h && x_fpa && w_packed && y_fpa, "srk_conv_tc: null argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   ConvTcParams p{};
   if (int rc = fill_geom(p, n_img, H, W)) return rc;
   p.bias = bias;
@@ -1149,6 +1144,7 @@ extern "C" int srk_conv_tc_last(srk_handle_t h, const void* x_fpa, int cin_p, co
                                 int n_frames, int FH, int FW, int shuffle_r, const float* addend, float* out,
                                 srk_stream_t stream) {
   SRK_REQUIRE(h && x_fpa && w_packed && out, "srk_conv_tc_last: null argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   SRK_REQUIRE(shuffle_r >= 1 && cout % (shuffle_r * shuffle_r) == 0, "srk_conv_tc_last: cout %d not divisible by r^2 (r=%d)", cout, shuffle_r);
   SRK_REQUIRE(cout <= cout_p, "srk_conv_tc_last: cout %d > cout_p %d", cout, cout_p);
   SRK_REQUIRE(panels || (n_frames == n_img && FH == H && FW == W), "srk_conv_tc_last: without panels the frame must equal the FPA geometry");
@@ -1182,6 +1178,7 @@ extern "C" int srk_conv_first_tc(srk_handle_t h, const float* x, int n_frames, i
                                  const float* bias, int k, int pad_mode, int act, const srk_panel* panels, int n_img, int H, int W,
                                  void* y_fpa, const void* mask_src, int mask_kind, srk_stream_t stream) {
   SRK_REQUIRE(h && x && w_packed && y_fpa, "srk_conv_first_tc: null argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   const int halo = (pad_mode == SRK_PAD_VALID) ? k - 1 : 0;
   SRK_REQUIRE(panels || (n_frames == n_img && FH == H + halo && FW == W + halo),
               "srk_conv_first_tc: without panels the frame (%dx%d) must match the output geometry (%dx%d, k=%d)", FH, FW, H, W, k);

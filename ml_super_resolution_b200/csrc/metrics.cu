@@ -206,6 +206,7 @@ using namespace srk;
 extern "C" int srk_psnr(srk_handle_t h, const float* a, const float* b, int n_img, int64_t numel_per_image, float max_val, double* workspace,
                         float* out, srk_stream_t stream) {
   SRK_REQUIRE(h && a && b && workspace && out && n_img > 0 && numel_per_image > 0, "srk_psnr: bad argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   cudaStream_t s = as_stream(stream);
   SRK_CHECK_CUDA(cudaMemsetAsync(workspace, 0, sizeof(double) * n_img, s));
   const int gx = grid1(h, numel_per_image, 256, 8) / (n_img > 1 ? (n_img > 8 ? 8 : n_img) : 1) + 1;
@@ -219,6 +220,7 @@ extern "C" int srk_psnr(srk_handle_t h, const float* a, const float* b, int n_im
 extern "C" int srk_ssim(srk_handle_t h, const float* a, const float* b, int n_img, int H, int W, int C, float max_val, double* workspace,
                         float* out, srk_stream_t stream) {
   SRK_REQUIRE(h && a && b && workspace && out && n_img > 0 && C > 0, "srk_ssim: bad argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   SRK_REQUIRE(H >= kWin && W >= kWin, "srk_ssim: image %dx%d smaller than the 11x11 window", H, W);
   SRK_REQUIRE(int64_t(n_img) * C <= 65535, "srk_ssim: n_img * C exceeds the grid limit");
   cudaStream_t s = as_stream(stream);
@@ -235,6 +237,7 @@ extern "C" int srk_ssim(srk_handle_t h, const float* a, const float* b, int n_im
 extern "C" int srk_rgb_to_y(srk_handle_t h, const float* x, int64_t n_pixels, float scale, float bias, float clip_lo, float clip_hi, float* y,
                             srk_stream_t stream) {
   SRK_REQUIRE(h && x && y, "srk_rgb_to_y: null argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   if (n_pixels == 0) return 0;
   rgb_to_y_kernel<<<grid1(h, n_pixels, 256, 16), 256, 0, as_stream(stream)>>>(x, n_pixels, clip_lo, clip_hi, scale, bias, y);
   SRK_LAUNCH_CHECK();
@@ -243,6 +246,7 @@ extern "C" int srk_rgb_to_y(srk_handle_t h, const float* x, int64_t n_pixels, fl
 
 extern "C" int srk_saturate_cast_u8(srk_handle_t h, const float* x, size_t n, float scale, float bias, uint8_t* y, srk_stream_t stream) {
   SRK_REQUIRE(h && x && y, "srk_saturate_cast_u8: null argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   if (n == 0) return 0;
   saturate_u8_kernel<<<grid1(h, int64_t(n), 256, 16), 256, 0, as_stream(stream)>>>(x, n, scale, bias, y);
   SRK_LAUNCH_CHECK();
@@ -251,6 +255,7 @@ extern "C" int srk_saturate_cast_u8(srk_handle_t h, const float* x, size_t n, fl
 
 extern "C" int srk_feature_mosaic_u8(srk_handle_t h, const float* x, int H, int W, uint8_t* y, srk_stream_t stream) {
   SRK_REQUIRE(h && x && y && H > 0 && W > 0, "srk_feature_mosaic_u8: bad argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   feature_mosaic_kernel<<<grid1(h, int64_t(64) * H * W, 256, 16), 256, 0, as_stream(stream)>>>(x, H, W, y);
   SRK_LAUNCH_CHECK();
   return 0;
@@ -260,6 +265,7 @@ extern "C" int srk_resample_u8(srk_handle_t h, const uint8_t* x, int n, int H, i
                                const int32_t* bx, int ksx, const int32_t* ky, const int32_t* by, int ksy, uint8_t* tmp, uint8_t* y,
                                srk_stream_t stream) {
   SRK_REQUIRE(h && x && y && n > 0 && H > 0 && W > 0 && C > 0 && out_h > 0 && out_w > 0, "srk_resample_u8: bad argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   const bool hx = out_w != W, vy = out_h != H;
   SRK_REQUIRE((!hx || (kx && bx && ksx > 0)) && (!vy || (ky && by && ksy > 0)), "srk_resample_u8: missing coefficient table");
   SRK_REQUIRE(!(hx && vy) || tmp, "srk_resample_u8: a two-pass resize needs the [n,H,out_w,C] intermediate");
@@ -283,6 +289,7 @@ extern "C" int srk_resample_u8(srk_handle_t h, const uint8_t* x, int n, int H, i
 extern "C" int srk_crop_u8(srk_handle_t h, const uint8_t* pool, const srk_pool_image* images_device, const srk_crop* crops_device, int n, int S,
                            int C, uint8_t* out, srk_stream_t stream) {
   SRK_REQUIRE(h && pool && images_device && crops_device && out && n > 0 && S > 0 && C > 0, "srk_crop_u8: bad argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   crop_u8_kernel<<<grid1(h, int64_t(n) * S * S * C, 256, 16), 256, 0, as_stream(stream)>>>(pool, images_device, crops_device, n, S, C, out);
   SRK_LAUNCH_CHECK();
   return 0;
@@ -290,6 +297,7 @@ extern "C" int srk_crop_u8(srk_handle_t h, const uint8_t* pool, const srk_pool_i
 
 extern "C" int srk_u8_to_pm1(srk_handle_t h, const uint8_t* x, size_t n, float* y, srk_stream_t stream) {
   SRK_REQUIRE(h && x && y, "srk_u8_to_pm1: null argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   if (n == 0) return 0;
   u8_to_pm1_kernel<<<grid1(h, int64_t(n), 256, 16), 256, 0, as_stream(stream)>>>(x, n, y);
   SRK_LAUNCH_CHECK();

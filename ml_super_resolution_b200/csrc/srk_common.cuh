@@ -3,6 +3,9 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
+#include <unordered_map>
+#include <unordered_set>
 #include <utility>
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -10,10 +13,35 @@
 
 #include "../../include/srk.h"
 
+// Key of one cached tensor map: everything cuTensorMapEncodeTiled is given.
+struct srk_tmap_key {
+  const void* ptr;
+  uint64_t rows;
+  uint32_t cols, box_rows, box_cols, elem_bytes;
+  bool operator==(const srk_tmap_key& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && box_rows == o.box_rows && box_cols == o.box_cols && elem_bytes == o.elem_bytes;
+  }
+};
+struct srk_tmap_key_hash {
+  size_t operator()(const srk_tmap_key& k) const {
+    uint64_t h = reinterpret_cast<uint64_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+    h ^= (k.rows + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= ((uint64_t(k.cols) << 40) ^ (uint64_t(k.box_rows) << 20) ^ (uint64_t(k.box_cols) << 4) ^ k.elem_bytes) * 0xC2B2AE3D27D4EB4Full;
+    return size_t(h);
+  }
+};
+
+// One handle per device (include/srk.h): everything CUDA keeps PER DEVICE -- kernel attributes, __constant__ uploads, encoded
+// tensor maps -- is remembered here, never in process-wide statics, so that a second handle on another GPU of the same process
+// sets its own.  Not thread-safe per handle.
 struct srk_ctx {
   int device;
   int num_sms;
   int smem_optin;
+  std::unordered_set<const void*> once;  // kernels whose attributes are set / tables that are uploaded on this device
+  std::unordered_map<srk_tmap_key, CUtensorMap, srk_tmap_key_hash> tmaps;
+  void* comm = nullptr;      // ncclComm_t once srk_comm_init has run (collective.cu)
+  void* comm_lib = nullptr;  // dlopen handle of libnccl
 };
 
 namespace srk {
@@ -65,8 +93,16 @@ inline FpaGeom fpa_geom(int n_img, int H, int W) {
 }
 
 // 2-D bf16 row-major tensor map [rows][cols], box {cols, box_rows}, swizzle chosen from the row bytes
-// (128 B -> SW128, 64 B -> SW64, 32 B -> SW32).  Returns 0 on success.
-int make_tensor_map_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint32_t cols, uint32_t box_rows);
+// (128 B -> SW128, 64 B -> SW64, 32 B -> SW32).  Returns 0 on success.  The encoded map is cached in the handle (a model
+// replays the same few buffers every step, and cuTensorMapEncodeTiled costs microseconds of host time per call).
+int make_tensor_map_2d(srk_ctx* h, CUtensorMap* out, const void* gptr, uint64_t rows, uint32_t cols, uint32_t box_rows);
+
+// true exactly once per (handle, key): guards per-device one-time work such as cudaFuncSetAttribute or a __constant__ upload
+inline bool first_use(srk_ctx* h, const void* key) { return h->once.insert(key).second; }
+
+// Every compute entry point runs on the handle's device; a caller that switched the current device gets an error, not a
+// launch on the wrong GPU.
+int check_device(srk_ctx* h);
 
 inline cudaStream_t as_stream(srk_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

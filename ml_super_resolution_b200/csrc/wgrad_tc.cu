@@ -293,6 +293,7 @@ extern "C" size_t srk_conv_wgrad_tc_workspace_bytes(srk_handle_t h, int n_img, i
 extern "C" int srk_conv_wgrad_tc(srk_handle_t h, const void* x_fpa, const void* dy_fpa, int n_img, int H, int W, float* dw_hwio,
                                  float* dbias, int accumulate, void* workspace, size_t workspace_bytes, srk_stream_t stream) {
   SRK_REQUIRE(h && x_fpa && dy_fpa && workspace && (dw_hwio == nullptr || dbias != nullptr), "srk_conv_wgrad_tc: null argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   SRK_REQUIRE((reinterpret_cast<uintptr_t>(dw_hwio) | reinterpret_cast<uintptr_t>(dbias) | reinterpret_cast<uintptr_t>(workspace)) % 16 == 0,
               "srk_conv_wgrad_tc: dw, dbias and workspace must be 16-byte aligned");
   const FpaGeom g = fpa_geom(n_img, H, W);
@@ -307,13 +308,10 @@ extern "C" int srk_conv_wgrad_tc(srk_handle_t h, const void* x_fpa, const void* 
   SRK_REQUIRE(p.ring >= 2 * p.nb + 2, "srk_conv_wgrad_tc: image width %d too large for the flat-stream kernel", W);
   const int grid = wgrad_grid(h, p.num_chunks);
   SRK_REQUIRE(workspace_bytes >= size_t(grid) * kPartialFloats * sizeof(float), "srk_conv_wgrad_tc: workspace too small (%zu B)", workspace_bytes);
-  if (int rc = make_tensor_map_2d(&p.map_x, x_fpa, uint64_t(g.rows_valid), 64, 128)) return rc;
-  if (int rc = make_tensor_map_2d(&p.map_dy, dy_fpa, uint64_t(g.rows_valid), 64, kYRows)) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (int rc = make_tensor_map_2d(h, &p.map_x, x_fpa, uint64_t(g.rows_valid), 64, 128)) return rc;
+  if (int rc = make_tensor_map_2d(h, &p.map_dy, dy_fpa, uint64_t(g.rows_valid), 64, kYRows)) return rc;
+  if (first_use(h, reinterpret_cast<const void*>(&wgrad_tc_kernel)))
     SRK_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem::kTotal));
-    attr_set = true;
-  }
   SRK_CHECK_CUDA(launch_pdl(wgrad_tc_kernel, dim3(grid), dim3(kWgThreads), size_t(WgSmem::kTotal), as_stream(stream), p));
   if (dw_hwio) {
     WgradDst single{dw_hwio, dbias, 64, 64};
@@ -327,14 +325,12 @@ extern "C" int srk_conv_wgrad_tc_batched(srk_handle_t h, const void* const* x_fp
                                          int W, void* workspace, size_t layer_stride_bytes, const srk_wgrad_dst* dsts_device, int accumulate,
                                          srk_stream_t stream) {
   SRK_REQUIRE(h && x_fpas && dy_fpas && workspace && dsts_device && n_layers > 0, "srk_conv_wgrad_tc_batched: bad argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   SRK_REQUIRE(layer_stride_bytes % 16 == 0 && reinterpret_cast<uintptr_t>(workspace) % 16 == 0, "srk_conv_wgrad_tc_batched: workspace alignment");
   const FpaGeom g = fpa_geom(n_img, H, W);
   SRK_REQUIRE(g.rows_valid < (int64_t(1) << 31), "srk_conv_wgrad_tc_batched: too many rows");
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (first_use(h, reinterpret_cast<const void*>(&wgrad_tc_batched_kernel)))
     SRK_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem::kTotal));
-    attr_set = true;
-  }
   const int num_chunks = int((g.rows_valid + 127) / 128);
   for (int l0 = 0; l0 < n_layers; l0 += kMaxWgBatch) {
     const int nl = std::min(kMaxWgBatch, n_layers - l0);
@@ -353,8 +349,8 @@ extern "C" int srk_conv_wgrad_tc_batched(srk_handle_t h, const void* const* x_fp
     SRK_REQUIRE(layer_stride_bytes >= size_t(cpl) * kPartialFloats * sizeof(float), "srk_conv_wgrad_tc_batched: layer stride smaller than one layer's partials");
     for (int l = 0; l < nl; ++l) {
       SRK_REQUIRE(x_fpas[l0 + l] && dy_fpas[l0 + l], "srk_conv_wgrad_tc_batched: null operand for layer %d", l0 + l);
-      if (int rc = make_tensor_map_2d(&bp.map_x[l], x_fpas[l0 + l], uint64_t(g.rows_valid), 64, 128)) return rc;
-      if (int rc = make_tensor_map_2d(&bp.map_dy[l], dy_fpas[l0 + l], uint64_t(g.rows_valid), 64, kYRows)) return rc;
+      if (int rc = make_tensor_map_2d(h, &bp.map_x[l], x_fpas[l0 + l], uint64_t(g.rows_valid), 64, 128)) return rc;
+      if (int rc = make_tensor_map_2d(h, &bp.map_dy[l], dy_fpas[l0 + l], uint64_t(g.rows_valid), 64, kYRows)) return rc;
     }
     SRK_CHECK_CUDA(launch_pdl(wgrad_tc_batched_kernel, dim3(cpl, nl), dim3(kWgThreads), size_t(WgSmem::kTotal), as_stream(stream), bp));
     SRK_CHECK_CUDA(launch_pdl(wgrad_reduce_kernel, dim3((kPartialFloats / 4 + 127) / 128, nl), dim3(128), 0, as_stream(stream),
@@ -367,6 +363,7 @@ extern "C" int srk_conv_wgrad_tc_batched(srk_handle_t h, const void* const* x_fp
 extern "C" int srk_wgrad_reduce_many(srk_handle_t h, const void* workspace_base, size_t layer_stride_bytes, int n_layers, int n_img, int H,
                                      int W, const srk_wgrad_dst* dsts_device, int accumulate, srk_stream_t stream) {
   SRK_REQUIRE(h && workspace_base && dsts_device && n_layers > 0, "srk_wgrad_reduce_many: bad argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
   SRK_REQUIRE(layer_stride_bytes % 16 == 0, "srk_wgrad_reduce_many: layer stride must be a multiple of 16 bytes");
   static_assert(sizeof(srk_wgrad_dst) == sizeof(WgradDst), "ABI struct mismatch");
   const FpaGeom g = fpa_geom(n_img, H, W);

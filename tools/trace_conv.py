@@ -1,6 +1,7 @@
-"""In-kernel timeline of conv_tc_kernel's warp roles on CTA 0 (development tool; needs libsrk_trace.so built by
-ml_super_resolution_b200.build.build_trace_library()).  Run on the GPU box:
-    SRK_LIB_OVERRIDE=ml_super_resolution_b200/libsrk_trace.so python tools/trace_conv.py [f2|f3|c64]
+"""In-kernel timeline of conv_tc_kernel's warp roles on CTA 0 (development tool).  Build the trace library here with
+ml_super_resolution_b200.build.build_trace_library() (-> ml_super_resolution_b200/build/libsrk_trace.so, -DSRK_TRACE), then on the
+GPU box:  python tools/trace_conv.py [f2|f3|c64|train]
+The product loader knows nothing about the trace build: this tool points _ffi.LIB_PATH at it before the first load.
 """
 import ctypes as C
 import os
@@ -10,7 +11,11 @@ import numpy as np
 import torch
 
 sys.path.insert(0, "/root/repo")
-from ml_super_resolution_b200 import _ffi, ops  # noqa: E402
+from ml_super_resolution_b200 import _ffi  # noqa: E402
+
+TRACE_LIB = os.path.join(os.path.dirname(_ffi.LIB_PATH), "build", "libsrk_trace.so")
+_ffi.LIB_PATH = TRACE_LIB
+from ml_super_resolution_b200 import ops  # noqa: E402
 from ml_super_resolution_b200.espcn.model_espcn import EspcnNet  # noqa: E402
 from ml_super_resolution_b200.tiling import plan_tiles  # noqa: E402
 
@@ -48,7 +53,7 @@ for _ in range(3):
     run()
 torch.cuda.synchronize()
 buf = np.zeros(24 * 256, dtype=np.uint64)
-raw = C.CDLL(os.environ["SRK_LIB_OVERRIDE"])
+raw = C.CDLL(TRACE_LIB)
 rc = raw.srk_debug_trace_read(buf.ctypes.data_as(C.c_void_p))
 assert rc == 0, rc
 T = buf.reshape(24, 256).astype(np.int64)
