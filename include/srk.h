@@ -132,6 +132,34 @@ int srk_conv_tc_last(srk_handle_t h, const void* x_fpa, int cin_p, const void* w
                      const srk_panel* panels, int n_frames, int FH, int FW, int shuffle_r,
                      const float* addend, float* out, srk_stream_t stream);
 
+/* ---- model-level fast path: the whole ESPCN test graph in ONE persistent kernel (csrc/espcn_fused.cu) -------------------
+ *   replaces, for one `session.run(sr_results)` of the constant-weight test graph,
+ *     tf.nn.conv2d(.., f1) + bias_add + tanh ; tf.nn.conv2d(.., f2) + bias_add + tanh ; tf.nn.conv2d(.., f3) + bias_add
+ *                                                                   espcn/espcn/model_espcn.py:117-134
+ *   and (shuffle != 0) the host un-pack np.split / reshape / concatenate of espcn/espcn/experiment_test.py:173-177,
+ *   and (out_kind == SRK_OUT_U8) the uint8 conversion of the written image, :179-184 (tf.saturate_cast semantics).
+ * The two intermediate activations never leave the SM (tensor memory); HBM sees the LR frame once and the result once.
+ * net: device pointers to the packed kernels the layer-by-layer path uses as well --
+ *   w1_packed srk_pack_conv_weights(f1 [5,5,C,64],  SRK_PACK_FIRST)              bf16 [ceil(25C/64)][64][64]
+ *   w2_packed srk_pack_conv_weights(f2 [3,3,64,32], SRK_PACK_FWD, np 32, cinp 64) bf16 [9][32][64]
+ *   w3_packed srk_pack_conv_weights(f3 [3,3,32,C*r^2], SRK_PACK_FWD, np = C*r^2 rounded up to 16, cinp 32)
+ *   b1 [64], b2 [32], b3 [C*r^2] fp32.
+ * lr: fp32 NHWC [n,H,W,C] (C = 1 or 3).  Rows [y_begin, y_end) of every frame are produced (a rank's row band in tiled
+ * multi-GPU inference; the 4 LR rows above / below the band are read from `lr`, which therefore addresses whole frames);
+ * out addresses whole frames too: fp32 or uint8 [n, H*r, W*r, C] (shuffle) or [n, H, W, C*r^2] (packed, shuffle = 0). */
+enum { SRK_OUT_F32 = 0, SRK_OUT_U8 = 1 };
+typedef struct {
+  const void* w1_packed;
+  const void* w2_packed;
+  const void* w3_packed;
+  const float* b1;
+  const float* b2;
+  const float* b3;
+  int32_t channels, scaling_factor;
+} srk_espcn_net;
+int srk_espcn_forward(srk_handle_t h, const srk_espcn_net* net, const float* lr, int n, int H, int W, int y_begin,
+                      int y_end, int shuffle, int out_kind, void* out, srk_stream_t stream);
+
 /* Weight gradient of a 3x3 64->64 layer on tensor cores: dW[u,v,ci,co] = sum_p x[p+(u-1)*Wp+(v-1)][ci]
  * * dy[p][co], dbias[co] = sum_p dy[p][co].  Split over CTAs along the pixel axis; every CTA stores its
  * partial [9*64*64+64] block into `workspace` and a second kernel sums the partials in a fixed order

@@ -29,6 +29,11 @@ class SrkPanel(C.Structure):
                 ("own_y1", C.c_int32), ("own_x0", C.c_int32), ("own_x1", C.c_int32), ("reserved", C.c_int32)]
 
 
+class SrkEspcnNet(C.Structure):
+    _fields_ = [("w1_packed", C.c_void_p), ("w2_packed", C.c_void_p), ("w3_packed", C.c_void_p), ("b1", C.c_void_p),
+                ("b2", C.c_void_p), ("b3", C.c_void_p), ("channels", C.c_int32), ("scaling_factor", C.c_int32)]
+
+
 _P, _I, _F, _SZ, _I64, _D = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_int64, C.c_double
 
 # name -> (restype, argtypes); mirrors include/srk.h declaration by declaration
@@ -74,6 +79,7 @@ SIGNATURES = {
     "srk_u8_to_pm1": (_I, [_P, _P, _SZ, _P, _P]),
     "srk_crop_flip_u8": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "srk_affine_f32": (_I, [_P, _P, _SZ, _F, _F, _P, _P]),
+    "srk_espcn_forward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "srk_fpa_halo_exchange": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _P]),
     "srk_fpa_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
     "srk_nhwc_to_fpa": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),

@@ -56,15 +56,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");                              // re-polling (spinning epilogue warps starved the MMA issuers of issue slots)
   return ok != 0;
 }
-// Bounded wait: traps (kernel error, not a hang) if the barrier never flips.
+// Bounded wait: traps (kernel error, not a hang) if the barrier never flips.  The printf diagnostic is compiled only into
+// development builds (-DSRK_WAIT_DIAG): every inlined call site costs ~20 instructions of the instruction cache the
+// warp-specialised kernels are short of; a plain trap is one instruction.
+#ifdef SRK_WAIT_DIAG
+static __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+  printf("srk: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+  __trap();
+}
+#else
+__device__ __forceinline__ void mbar_timeout(uint32_t, uint32_t) { __trap(); }
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t n = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++n > SRK_WAIT_BOUND) {
-      printf("srk: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x,
-             threadIdx.x, bar, parity);
-      __trap();
-    }
+    if (++n > SRK_WAIT_BOUND) mbar_timeout(bar, parity);
   }
 }
 
@@ -182,6 +188,11 @@ __device__ __forceinline__ void tmem_st_wait() {
 // 4-byte asynchronous global -> shared copy; src_bytes = 0 writes zeros without reading (out-of-image padding)
 __device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {  // all but the N most recent groups of this thread have landed
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 // the barrier receives one arrival from this thread once all of its earlier cp.async copies have landed
 // (.noinc: the arrival is part of the barrier's initial count)

@@ -43,6 +43,8 @@ class EspcnNet:
         self._i1 = plan.add(a.offsets["f1/kernel:0"], 5, self.C, 64, ops.PACK_FIRST)
         self._i2 = plan.add(a.offsets["f2/kernel:0"], 3, 64, 32, ops.PACK_FWD, 32, 64)
         self._i3 = plan.add(a.offsets["f3/kernel:0"], 3, 32, self.cout3, ops.PACK_FWD, self.np3, 32)
+        self.np3f = (self.cout3 + 15) // 16 * 16  # the fused kernel pads f3's outputs to 16, not to a power of two (4x RGB: 48)
+        self._i3f = self._i3 if self.np3f == self.np3 else plan.add(a.offsets["f3/kernel:0"], 3, 32, self.cout3, ops.PACK_FWD, self.np3f, 32)
         plan.finalize()
         self.plan = plan
         self.bias3 = torch.zeros(self.np3, dtype=torch.float32, device=device)
@@ -146,10 +148,24 @@ class EspcnNet:
             self._bufs[key] = (ops.fpa_empty(n, H, W, 64, self.device), ops.fpa_empty(n, H, W, 32, self.device))
         return self._bufs[key]
 
-    def forward(self, lr: torch.Tensor, shuffle=True, out: torch.Tensor | None = None, rank=0, world=1, tile_rows=None) -> torch.Tensor:
-        """lr fp32 [N,h,w,C] -> shuffled [N,h*r,w*r,C] (shuffle=True) or packed [N,h,w,C*r^2]."""
+    def forward_fused(self, lr: torch.Tensor, shuffle=True, out: torch.Tensor | None = None, rank=0, world=1, uint8=False) -> torch.Tensor:
+        """The test graph (reference model_espcn.py:117-134 + the un-pack of experiment_test.py:173-177) as ONE kernel
+        (srk_espcn_forward): activations stay in tensor memory.  Rank `rank` of `world` produces its LR row band of every
+        frame (reads 4 halo rows from `lr`, writes only its band of `out`)."""
         n, H, W, C = lr.shape
         assert C == self.C
+        a, V = self.arena, self.plan.views
+        y0, y1 = (H * rank) // world, (H * (rank + 1)) // world
+        return ops.espcn_forward(lr, V[self._i1], a.view("f1/bias:0"), V[self._i2], a.view("f2/bias:0"), V[self._i3f], a.view("f3/bias:0"),
+                                 self.r, shuffle, out, (y0, y1), uint8)
+
+    def forward(self, lr: torch.Tensor, shuffle=True, out: torch.Tensor | None = None, rank=0, world=1, tile_rows=None, fused=True) -> torch.Tensor:
+        """lr fp32 [N,h,w,C] -> shuffled [N,h*r,w*r,C] (shuffle=True) or packed [N,h,w,C*r^2].  fused=False runs the three
+        layers as separate kernels through FPA buffers in HBM (the form training uses; kept for A/B measurements)."""
+        n, H, W, C = lr.shape
+        assert C == self.C
+        if fused and tile_rows is None:
+            return self.forward_fused(lr, shuffle, out, rank, world)
         a, r = self.arena, (self.r if shuffle else 1)
         if out is None:
             out = torch.empty((n, H * r, W * r, self.cout3 // (r * r)), dtype=torch.float32, device=lr.device)

@@ -230,6 +230,30 @@ def conv_tc_last(x: Fpa, w_packed: torch.Tensor, bias: torch.Tensor | None, k: i
     return out
 
 
+OUT_F32, OUT_U8 = 0, 1
+
+
+def espcn_forward(lr: torch.Tensor, w1p: torch.Tensor, b1: torch.Tensor, w2p: torch.Tensor, b2: torch.Tensor, w3p: torch.Tensor,
+                  b3: torch.Tensor, scaling_factor: int, shuffle: bool = True, out: torch.Tensor | None = None,
+                  rows: tuple[int, int] | None = None, uint8: bool = False) -> torch.Tensor:
+    """The whole ESPCN test graph in one persistent kernel (srk_espcn_forward): lr fp32 [n,H,W,C] -> fp32 | uint8
+    [n,H*r,W*r,C] (shuffle) or [n,H,W,C*r^2] (packed).  `rows` = (y_begin, y_end): only that LR row band of every frame is
+    produced (a rank's share of a tiled frame); the rest of `out` is left untouched."""
+    n, H, W, C_ = lr.shape
+    r = scaling_factor
+    cout = C_ * r * r
+    assert w1p.shape[1:] == (64, 64) and w2p.shape == (9, 32, 64) and w3p.shape == (9, _round_up(cout, 16), 32), "packed ESPCN kernels"
+    if out is None:
+        shape = (n, H * r, W * r, C_) if shuffle else (n, H, W, cout)
+        out = torch.empty(shape, dtype=torch.uint8 if uint8 else torch.float32, device=lr.device)
+    assert out.dtype == (torch.uint8 if uint8 else torch.float32) and out.numel() == n * H * W * cout
+    y0, y1 = rows if rows is not None else (0, H)
+    net = _ffi.SrkEspcnNet(w1p.data_ptr(), w2p.data_ptr(), w3p.data_ptr(), _f32(b1).data_ptr(), _f32(b2).data_ptr(), _f32(b3).data_ptr(), C_, r)
+    check(_ffi.lib().srk_espcn_forward(handle(), C.byref(net), _ptr(_f32(lr)), n, H, W, y0, y1, int(shuffle), OUT_U8 if uint8 else OUT_F32,
+                                       _ptr(out), _stream()), "srk_espcn_forward")
+    return out
+
+
 _wgrad_ws: dict = {}
 
 
