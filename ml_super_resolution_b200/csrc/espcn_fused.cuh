@@ -89,7 +89,7 @@ struct alignas(64) EspcnFusedParams {
 template <int C, int R, bool SHUF>
 struct EspcnCfg {
   static constexpr int kCout = C * R * R;
-  static constexpr int kSets = (kCout > 32) ? 2 : SRK_EF_SETS;  // epilogue sets (4 quadrant warps each) taking virtual rows round-robin
+  static constexpr int kSets = (kCout > 32) ? 2 : (C == 3 ? 3 : SRK_EF_SETS);  // epilogue sets (4 quadrant warps each) taking virtual rows round-robin
   static constexpr int NP3 = (kCout + 15) / 16 * 16;
   static constexpr int kRows = SHUF ? R : 1;          // output rows per LR row
   static constexpr int kRC = kCout / kRows;           // output elements per LR pixel per output row
@@ -459,10 +459,10 @@ __global__ void __launch_bounds__(EspcnCfg<C, R, SHUF>::kThreads, 1) espcn_fused
         ef_seg_seek(w, s_tab, v);
         const int r0 = v + 4 * w.i;  // input rows [r0, r0 + 5) of the input sequence
         cp_async_wait<5>();
-        ef_bar_sync(8, 128);  // every thread's part of those rows has landed; everyone is done reading the previous step's rows
         const int st = v % AS;
         if (gt == 0) EF_EV(0, v);
-        if (v >= AS) mbar_wait(C1((v - AS) & 3), ((v - AS) >> 2) & 1);  // MMA1(v - AS) has consumed this A stage
+        if (gt < 32 && v >= AS) mbar_wait(C1((v - AS) & 3), ((v - AS) >> 2) & 1);  // MMA1(v - AS) has consumed this A stage (one warp polls)
+        ef_bar_sync(8, 128);  // every thread's part of those rows has landed; everyone is done reading the previous step's rows
         if (gt == 0) EF_EV(1, v);
         const uint32_t arow = s_a + st * L::kABytes + gt * 128;
 #pragma unroll
