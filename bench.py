@@ -143,12 +143,32 @@ def launches_of(fn) -> int:
 
 
 # ------------------------------------------------------------------------------------------------ ESPCN (headline)
+ESPCN_FLOP_PER_OUT_PIXEL = 5027.6  # SURVEY 8(d) cfg2, C = 1: 2 * (25*64 + 576*32 + 288*9) / 9
+
+
+def ncu_traffic(kernel_substr: str, shape_key: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the tracked ncu capture
+    (profiles/r2_ncu_traffic.json, written by tools/ncu_traffic.py from an `ncu --set full` report); None unless the kernel
+    name and the workload shape recorded there match what is being benchmarked."""
+    p = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        for e in json.load(f):
+            if kernel_substr in e["kernel"] and e.get("shape") == shape_key:
+                return e["dram_bytes"]
+    return None
+
+
 def espcn_workload(args, rank, world):
     from ml_super_resolution_b200 import ops
-    from ml_super_resolution_b200.espcn.model_espcn import EspcnNet
+    from ml_super_resolution_b200.espcn.model_espcn import EspcnNet, build_model
+    from ml_super_resolution_b200.session import Session, pinned_empty, placeholder
     from ml_super_resolution_b200.tiling import plan_tiles
     C = 1
-    net = EspcnNet(None, SCALE, C, seed=42)
+    lr_ph = placeholder([None, None, None, C], "lr_source")
+    model = build_model(lr_ph, SCALE, channels=C, seed=42)
+    net = model["sr_result"].graph.net
     # trained-like magnitudes so tanh is exercised (reference init is sigma=0.02)
     net.arena.w.mul_(5.0)
     net.repack()
@@ -157,14 +177,29 @@ def espcn_workload(args, rank, world):
     out = torch.empty((FRAMES_PER_STEP, LR_H * SCALE, LR_W * SCALE, C), device="cuda")
     out_pix = FRAMES_PER_STEP * LR_H * SCALE * LR_W * SCALE
 
-    def step():
+    def step():  # ONE launch: srk_espcn_forward (f1 -> f2 -> f3 -> depth_to_space, activations in tensor memory)
         net.forward(lr, shuffle=True, out=out)
 
     ms, clocks = timed_steps(step, args.steps, args.warmup, world, ClockSampler(torch.cuda.current_device()) if rank == 0 else None)
     value = out_pix * world * args.steps / ms / 1e3  # Mpix/s, whole job
     n_launch = launches_of(step) * args.steps
 
-    # ---- per-kernel device times for the roofline (same buffers, outside the timed region)
+    # ---- roofline of the dominant (only) kernel: average launch duration over the timed region, live CUDA events above
+    pk = peaks()
+    k_ms = ms / args.steps
+    flops = ESPCN_FLOP_PER_OUT_PIXEL * out_pix
+    tf = flops / k_ms / 1e9
+    burst = ms < 2000.0  # a kernel timed alone for less than ~2 s runs at boost clocks: quote it against the burst figure
+    peak_tf = pk["tf_burst"] if burst else pk["tf_sust"]
+    alg_bytes = FRAMES_PER_STEP * LR_H * LR_W * (4 * C + 4 * C * SCALE * SCALE)
+    roofline = {"bound": "tensor", "kernel": "espcn_fused_kernel<1,3,true> (f1+f2+f3+pixel shuffle, one launch per step)", "achieved": round(tf, 1),
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": round(tf / peak_tf, 4), "peak_kind": "burst" if burst else "sustained",
+                "traffic": ncu_traffic("espcn_fused_kernel", f"{FRAMES_PER_STEP}x{LR_H}x{LR_W}x{C} r{SCALE} f32"), "peak_source": pk["src"],
+                "algorithmic_flops": flops, "algorithmic_bytes": alg_bytes, "hbm_GBps": round(alg_bytes / k_ms / 1e6, 1),
+                "hbm_frac": round(alg_bytes / k_ms / 1e6 / pk["hbm"], 4),
+                "note": "co-limited by the tensor pipe (N <= 96 MMAs run at the 49-cycle instruction floor), MUFU.TANH (96 per pixel) and issue slots; DESIGN.md 3.6"}
+
+    # ---- the layer-by-layer path (three kernels through HBM, what round 1 shipped and what training uses), for comparison
     Ht, Wt, tiles = plan_tiles(FRAMES_PER_STEP, LR_H, LR_W, 4)
     panels = ops.make_panels([t.as_tuple() for t in tiles])
     t1, t2 = net._get_bufs(len(tiles), Ht, Wt)
@@ -174,85 +209,57 @@ def espcn_workload(args, rank, world):
     k_f3 = event_time(lambda: ops.conv_tc_last(t2, net.plan.views[net._i3], net.bias3, 3, net.cout3, None, shuffle_r=SCALE, panels=panels,
                                                frame_shape=(FRAMES_PER_STEP, LR_H, LR_W), out=out))
     lr_px = FRAMES_PER_STEP * LR_H * LR_W
-    # algorithmic bytes per LR pixel: f1 reads fp32 C, writes 64 bf16; f2 reads 64 bf16, writes 32 bf16;
-    # f3 reads 32 bf16, writes C*r^2 fp32
-    kernels = {
-        "espcn_f1_conv_first_tc(5x5,C->64,tanh)": (k_f1, lr_px * (4 * C + 128)),
-        "espcn_f2_conv_tc(3x3,64->32,tanh)": (k_f2, lr_px * (128 + 64)),
-        "espcn_f3_conv_tc_last(3x3,32->9,shuffle)": (k_f3, lr_px * (64 + 4 * C * SCALE * SCALE)),
-    }
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of these three
-    # kernels at this exact shape (profiles/r1_ncu_espcn_kernels_v3.txt): no wasted re-reads (traffic ~ algorithmic bytes)
-    ncu_traffic = {"espcn_f1_conv_first_tc(5x5,C->64,tanh)": 1.081e9, "espcn_f2_conv_tc(3x3,64->32,tanh)": 1.630e9,
-                   "espcn_f3_conv_tc_last(3x3,32->9,shuffle)": 0.834e9}
-    dom = max(kernels, key=lambda k: kernels[k][0])
-    pk = peaks()
-    ach = kernels[dom][1] / kernels[dom][0] / 1e6  # GB/s
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s", "frac": round(ach / pk["hbm"], 4),
-                "traffic": ncu_traffic[dom] if FRAMES_PER_STEP == 4 else None, "algorithmic_bytes": kernels[dom][1], "peak_source": pk["src"],
-                "kernel_ms": {k: round(v[0], 4) for k, v in kernels.items()},
-                "kernel_GBps": {k: round(v[1] / v[0] / 1e6, 1) for k, v in kernels.items()},
-                "step_algorithmic_GB": round(sum(v[1] for v in kernels.values()) / 1e9, 3)}
+    layered = {"f1_ms": round(k_f1, 4), "f2_ms": round(k_f2, 4), "f3_ms": round(k_f3, 4),
+               "output_Mpix_per_s": round(out_pix / (k_f1 + k_f2 + k_f3) / 1e3, 1),
+               "GBps": {"f1": round(lr_px * (4 * C + 128) / k_f1 / 1e6, 1), "f2": round(lr_px * 192 / k_f2 / 1e6, 1),
+                        "f3": round(lr_px * (64 + 4 * C * SCALE * SCALE) / k_f3 / 1e6, 1)},
+               "step_algorithmic_GB": round(lr_px * (4 * C + 128 + 192 + 64 + 4 * C * SCALE * SCALE) / 1e9, 3)}
+    roofline["layered_path"] = layered
 
-    # ---- end to end through the public call with HOST buffers: every step copies its pinned input host->device and its
-    # full fp32 result device->host inside the timed region; copies run on their own streams and are double buffered so
-    # PCIe transfers of neighbouring steps overlap the kernels (throughput metric; every byte still moves every step)
-    lr_host = lr.cpu().pin_memory()
-    out_host = [torch.empty(out.shape, dtype=torch.float32).pin_memory() for _ in range(2)]
-    lr_dev = [torch.empty_like(lr) for _ in range(2)]
-    out_dev = [out, torch.empty_like(out)]
-    s_in, s_out, s_c = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.current_stream()
-    ev_in = [torch.cuda.Event() for _ in range(2)]
-    ev_c = [torch.cuda.Event() for _ in range(2)]
-    ev_out = [torch.cuda.Event() for _ in range(2)]
-    counter = [0]
+    # ---- end to end THROUGH THE DROP-IN SEAM: session.run(model[...], feed_dict={lr_source: host frames}) with page-locked
+    # host arrays.  Every step moves its input host->device and its result device->host inside the timed region.  The
+    # headline form returns what the reference's test driver writes to disk -- uint8 = saturate_cast(sr*127.5+127.5)
+    # (espcn/espcn/experiment_test.py:179-184) -- and the fp32 form (the raw session.run fetch) is reported next to it.
+    lr_host = pinned_empty(lr.shape)
+    lr_host[...] = lr.cpu().numpy()
+    out_u8, out_f32 = pinned_empty(out.shape, "uint8"), pinned_empty(out.shape, "float32")
+    sess = Session()
 
-    def e2e_step():
-        b = counter[0] & 1
-        counter[0] += 1
-        with torch.cuda.stream(s_in):
-            s_in.wait_event(ev_c[b])  # the forward that last read lr_dev[b] is done
-            lr_dev[b].copy_(lr_host, non_blocking=True)
-            ev_in[b].record(s_in)
-        s_c.wait_event(ev_in[b])
-        s_c.wait_event(ev_out[b])     # the D2H that last read out_dev[b] is done
-        net.forward(lr_dev[b], shuffle=True, out=out_dev[b])
-        ev_c[b].record(s_c)
-        with torch.cuda.stream(s_out):
-            s_out.wait_event(ev_c[b])
-            out_host[b].copy_(out_dev[b], non_blocking=True)
-            ev_out[b].record(s_out)
+    def e2e_u8():
+        sess.run(model["hr_images_u8"], feed_dict={lr_ph: lr_host}, out={model["hr_images_u8"]: out_u8})
 
-    def e2e_finalize():
-        s_c.wait_event(ev_out[0])
-        s_c.wait_event(ev_out[1])
+    def e2e_f32():
+        sess.run(model["hr_images"], feed_dict={lr_ph: lr_host}, out={model["hr_images"]: out_f32})
 
     n_e2e = max(4, args.steps // 2)
-    ms_e2e, _ = timed_steps(e2e_step, n_e2e, 2, world, None, finalize=e2e_finalize)
-    e2e_value = out_pix * world * n_e2e / ms_e2e / 1e3
-    e2e = {"value": round(e2e_value, 1), "unit": "output Mpix/s", "h2d_bytes_per_step": lr_host.numel() * 4, "d2h_bytes_per_step": out_host[0].numel() * 4,
-           "note": "pinned host buffers, fp32 in/out as the reference's session.run returns; H2D/compute/D2H double-buffered on three streams"}
-    cfg = {"workload": f"ESPCN 3x (5x5-64 tanh, 3x3-32 tanh, 3x3-9 + fused pixel shuffle) inference, {FRAMES_PER_STEP} synthetic 1920x1080 Y frames/step/GPU",
-           "frames_per_step_per_gpu": FRAMES_PER_STEP, "lr_shape": [LR_H, LR_W, C], "scale": SCALE, "panels": len(tiles) // FRAMES_PER_STEP,
-           "l2_policy": "working set per step (activations ~1.7 GB + 0.3 GB output) >> 126 MB L2", "parallelism": f"frames x{world}"}
+    ms_u8, _ = timed_steps(e2e_u8, n_e2e, 2, world, None)
+    ms_f32, _ = timed_steps(e2e_f32, max(2, n_e2e // 4), 1, world, None)
+    e2e = {"value": round(out_pix * world * n_e2e / ms_u8 / 1e3, 1), "unit": "output Mpix/s", "h2d_bytes_per_step": lr_host.size * 4,
+           "d2h_bytes_per_step": out_u8.size, "form": "uint8 (saturate_cast, as the reference's PNG hand-off)",
+           "fp32_form": {"value": round(out_pix * world * max(2, n_e2e // 4) / ms_f32 / 1e3, 1), "d2h_bytes_per_step": out_f32.size * 4},
+           "note": "Session.run on pinned host arrays: per call, row bands of each frame pipeline H2D / fused kernel / D2H on three streams; the call returns when the last band is on the host"}
+    cfg = {"workload": f"ESPCN 3x (5x5-64 tanh, 3x3-32 tanh, 3x3-9 + pixel shuffle) inference, {FRAMES_PER_STEP} synthetic 1920x1080 Y frames/step/GPU, ONE fused kernel per step",
+           "frames_per_step_per_gpu": FRAMES_PER_STEP, "lr_shape": [LR_H, LR_W, C], "scale": SCALE,
+           "l2_policy": "input + output per step (33 MB + 299 MB) > 126 MB L2; the activations never leave the SM", "parallelism": f"frames x{world}"}
     return dict(metric="ESPCN 3x output Mpix/s (fwd)", value=round(value, 1), unit="output Mpix/s", ms=ms, clocks=clocks, roofline=roofline,
                 e2e=e2e, gpu_launches=n_launch, config=cfg, scaling="weak")
 
 
-def espcn_cpu(frames: int, threads: int):
-    """CPU restatement (oracle, torch-CPU fp32 oneDNN) of the same ESPCN forward + pixel shuffle, `frames` frames."""
+def espcn_cpu(steps: int, threads: int):
+    """CPU restatement (oracle, torch-CPU fp32 oneDNN) of the same ESPCN forward + pixel shuffle: `steps` steps of
+    FRAMES_PER_STEP 1920x1080 Y frames each, the GPU arm's step."""
     from oracle import models as OM
     from oracle import ops as O
     torch.set_num_threads(threads)
     p = OM.espcn_init(seed=42, scaling_factor=SCALE, channels=1)
-    lr = OM.synthetic_images(1235, 1, LR_H, LR_W, 1)
-    OM.espcn_forward(p, lr[:, :64, :64], dtype=np.float32)  # warm
+    lr = OM.synthetic_images(1235, FRAMES_PER_STEP, LR_H, LR_W, 1)
+    OM.espcn_forward(p, lr[:1, :64, :64], dtype=np.float32)  # warm
     t0 = time.perf_counter()
-    for _ in range(frames):
+    for _ in range(steps):
         y = OM.espcn_forward(p, lr, dtype=np.float32)
         O.pixel_shuffle(y, SCALE)
     dt = time.perf_counter() - t0
-    return frames * LR_H * SCALE * LR_W * SCALE / dt / 1e6, dt
+    return steps * FRAMES_PER_STEP * LR_H * SCALE * LR_W * SCALE / dt / 1e6, dt
 
 
 # ------------------------------------------------------------------------------------------------ VDSR training
@@ -582,6 +589,89 @@ def enet_train_cpu(steps: int, threads: int, batch: int = 4):
 WORKLOADS = {"enet_train": enet_train_workload, "espcn": espcn_workload, "vdsr_train": vdsr_train_workload, "vdsr_infer": vdsr_infer_workload, "srcnn_train": srcnn_train_workload}
 
 
+def cpu_baseline_for(workload: str, threads: int):
+    """The oracle port of `workload` timed on the host cores, on a bounded sample of the same workload (a few seconds each)."""
+    with torch.no_grad():
+        if workload == "espcn":
+            v, dt = espcn_cpu(2, threads)
+            return {"value": round(v, 2), "unit": "output Mpix/s", "cores": threads, "kind": "port", "sample": f"2 steps of {FRAMES_PER_STEP} 1920x1080 Y frames, {dt:.1f} s"}
+        if workload == "vdsr_infer":
+            v, dt = vdsr_infer_cpu(threads)
+            return {"value": round(v, 3), "unit": "output Mpix/s", "cores": threads, "kind": "port", "sample": f"one 270x3840 band of the 4K frame through all 20 layers, {dt:.1f} s"}
+    if workload == "enet_train":
+        v, dt = enet_train_cpu(2, threads)
+        return {"value": round(v, 2), "unit": "patches/s", "cores": threads, "kind": "port", "sample": f"2 fwd+bwd steps of 4 patches, {dt:.1f} s"}
+    if workload == "srcnn_train":
+        v, dt = srcnn_train_cpu(5, threads)
+        return {"value": round(v, 2), "unit": "patches/s", "cores": threads, "kind": "port", "sample": f"5 degrade+fwd+bwd steps of 128 patches, {dt:.1f} s"}
+    if workload == "vdsr_train":
+        v, dt = vdsr_train_cpu(3, threads)
+        cpu = {"value": round(v, 2), "unit": "patches/s", "cores": threads, "kind": "port", "sample": f"3 fwd+bwd steps of 64 41x41x3 patches (20 layers, no optimiser step), {dt:.1f} s"}
+        from oracle import ops as O  # the reference's python input generator (numpy restatement), single-threaded as in the reference
+        rs = np.random.RandomState(7)
+        imgs = [rs.randint(0, 256, (256, 256, 3)).astype(np.uint8) for _ in range(8)]
+        g_cpu = O.vdsr_image_batches(imgs, [2.0, 3.0, 4.0], TRAIN_PATCH, TRAIN_BATCH, rs)
+        t0 = time.perf_counter()
+        next(g_cpu)
+        cpu["input_generator_patches_per_s"] = round(TRAIN_BATCH / (time.perf_counter() - t0), 1)
+        return cpu
+    return None
+
+
+def dp_check(rank: int, world: int) -> dict:
+    """Multi-GPU correctness, run ONCE before the timed region of every N > 1 run so that the scaling records carry it:
+      grad_rel_err    data-parallel VDSR gradients after the NCCL all-reduce vs the single-GPU gradients of the concatenated batch
+      replica_spread  max |w_rank - w_rank'| after 3 DP Adam steps (must be exactly 0)
+      tiled_equal     VDSR tile-sharded frame (ranks own disjoint tiles) == the single-GPU frame, bit for bit
+      espcn_bands_equal  fused ESPCN row bands computed by different ranks == the single-GPU frame, bit for bit"""
+    import torch.distributed as dist
+    from ml_super_resolution_b200.espcn.model_espcn import EspcnNet
+    from ml_super_resolution_b200.initializers import vdsr_params
+    from ml_super_resolution_b200.vdsr.model_vdsr import VdsrNet
+    L, per = 6, 8
+    rng = np.random.default_rng(7)
+    params = vdsr_params(3, L, 3)
+    for k in params:
+        if k.endswith("bias:0"):
+            params[k] = (0.05 * rng.standard_normal(params[k].shape)).astype(np.float32)
+    sd_all = torch.from_numpy(rng.uniform(-1, 1, (per * world, 41, 41, 3)).astype(np.float32)).cuda()
+    hd_all = torch.from_numpy(rng.uniform(-1, 1, (per * world, 41, 41, 3)).astype(np.float32)).cuda()
+    sd, hd = sd_all[rank * per:(rank + 1) * per].contiguous(), hd_all[rank * per:(rank + 1) * per].contiguous()
+    net = VdsrNet(params, L)
+    net.forward_backward(sd, hd, numel_total=float(sd_all.numel()))
+    dist.all_reduce(net.arena.g)
+    ref = VdsrNet(params, L)
+    ref.forward_backward(sd_all, hd_all)
+    err = float((net.arena.g - ref.arena.g).norm() / ref.arena.g.norm())
+    loss_dp = net._train_bufs["loss"][0:1].clone()
+    dist.all_reduce(loss_dp)
+    lerr = abs(float(loss_dp) - float(ref._train_bufs["loss"][0])) / float(ref._train_bufs["loss"][0])
+    net2 = VdsrNet(params, L)
+    for _ in range(3):
+        net2.train_step(sd, hd, lr=1e-3)
+    w = net2.arena.w.clone()
+    wmax, wmin = w.clone(), w.clone()
+    dist.all_reduce(wmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(wmin, op=dist.ReduceOp.MIN)
+    spread = float((wmax - wmin).abs().max())
+    frame = torch.from_numpy(rng.uniform(-1, 1, (1, 200, 600, 3)).astype(np.float32)).cuda()
+    out = torch.zeros_like(frame)
+    net.forward(frame, out=out, tile_rows=80, rank=rank, world=world)
+    dist.all_reduce(out)  # disjoint ownership: the sum assembles the frame (check-only collective)
+    same = bool(torch.equal(out, ref.forward(frame, tile_rows=80)))
+    en = EspcnNet(None, 3, 1, seed=5)
+    en.arena.w.mul_(5.0)
+    en.repack()
+    lrf = torch.from_numpy(rng.uniform(-1, 1, (2, 90, 300, 1)).astype(np.float32)).cuda()
+    eo = torch.zeros((2, 270, 900, 1), device="cuda")
+    en.forward_fused(lrf, out=eo, rank=rank, world=world)
+    dist.all_reduce(eo)
+    esame = bool(torch.equal(eo, en.forward_fused(lrf)))
+    res = {"world": world, "grad_rel_err": err, "loss_rel_err": lerr, "replica_spread": spread, "tiled_equal": same, "espcn_bands_equal": esame}
+    assert err < 2e-3 and lerr < 1e-4 and spread == 0.0 and same and esame, res
+    return res
+
+
 def run_reference(args, rank, world):
     """The reference's CPU path: oracle restatement of the TF-1.8 graph on torch-CPU fp32 with all host threads."""
     if rank != 0:
@@ -589,13 +679,14 @@ def run_reference(args, rank, world):
     threads = os.cpu_count() or 1
     t_all = time.perf_counter()
     if args.workload == "espcn":
-        frames = max(1, min(args.steps, 8))
+        steps = max(1, min(args.steps, 4))
         with torch.no_grad():
             for _ in range(min(args.warmup, 1)):
                 espcn_cpu(1, threads)
-            v, dt = espcn_cpu(frames, threads)
-        unit, metric, steps, sample = "output Mpix/s", "ESPCN 3x output Mpix/s (fwd)", frames, f"{frames} step(s) of ONE 1920x1080 Y frame each (GPU arm: {FRAMES_PER_STEP}/step)"
-        cfg = {"workload": "ESPCN 3x inference on synthetic 1920x1080 Y frames (CPU restatement, torch-CPU fp32)"}
+            v, dt = espcn_cpu(steps, threads)
+        unit, metric, sample = "output Mpix/s", "ESPCN 3x output Mpix/s (fwd)", f"{steps} step(s) of {FRAMES_PER_STEP} 1920x1080 Y frames each (the GPU arm's step)"
+        cfg = {"workload": f"ESPCN 3x (5x5-64 tanh, 3x3-32 tanh, 3x3-9 + pixel shuffle) inference, {FRAMES_PER_STEP} synthetic 1920x1080 Y frames/step (CPU restatement, torch-CPU fp32)",
+               "frames_per_step_per_gpu": FRAMES_PER_STEP, "lr_shape": [LR_H, LR_W, 1], "scale": SCALE}
     elif args.workload == "enet_train":
         steps = max(1, min(args.steps, 3))
         v, dt = enet_train_cpu(steps, threads)
@@ -646,6 +737,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dpc = dp_check(rank, world) if world > 1 else None
     res = WORKLOADS[args.workload](args, rank, world)
     also = {}
     if args.workload == "espcn" and not args.no_also:
@@ -654,38 +746,20 @@ def main():
         for name in ("vdsr_train", "vdsr_infer", "srcnn_train", "enet_train"):
             r = WORKLOADS[name](sub, rank, world)
             also[name] = {"metric": r["metric"], "value": r["value"], "unit": r["unit"], "ms_per_step": round(r["ms"] / sub.steps, 4),
-                          "roofline": r["roofline"], "e2e": r["e2e"], "scaling": r["scaling"], "steps": sub.steps}
+                          "roofline": r["roofline"], "e2e": r["e2e"], "scaling": r["scaling"], "steps": sub.steps, "config": r["config"]}
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            with torch.no_grad():
-                if args.workload == "espcn":
-                    v, dt = espcn_cpu(4, threads)
-                    cpu = {"value": round(v, 2), "unit": "output Mpix/s", "cores": threads, "kind": "port", "sample": f"4 frames of 1920x1080 Y, {dt:.1f} s"}
-                elif args.workload == "vdsr_infer":
-                    v, dt = vdsr_infer_cpu(threads)
-                    cpu = {"value": round(v, 3), "unit": "output Mpix/s", "cores": threads, "kind": "port", "sample": f"one 270x3840 band, {dt:.1f} s"}
-            if args.workload == "enet_train":
-                v, dt = enet_train_cpu(2, threads)
-                cpu = {"value": round(v, 2), "unit": "patches/s", "cores": threads, "kind": "port", "sample": f"2 fwd+bwd steps of 4 patches, {dt:.1f} s"}
-            if args.workload == "srcnn_train":
-                v, dt = srcnn_train_cpu(5, threads)
-                cpu = {"value": round(v, 2), "unit": "patches/s", "cores": threads, "kind": "port", "sample": f"5 degrade+fwd+bwd steps of 128 patches, {dt:.1f} s"}
-            if args.workload == "vdsr_train":
-                v, dt = vdsr_train_cpu(3, threads)
-                cpu = {"value": round(v, 2), "unit": "patches/s", "cores": threads, "kind": "port", "sample": f"3 fwd+bwd steps of 64 patches, {dt:.1f} s"}
-                from oracle import ops as O  # the reference's python input generator (numpy restatement), single-threaded as in the reference
-                rs = np.random.RandomState(7)
-                imgs = [rs.randint(0, 256, (256, 256, 3)).astype(np.uint8) for _ in range(8)]
-                g_cpu = O.vdsr_image_batches(imgs, [2.0, 3.0, 4.0], TRAIN_PATCH, TRAIN_BATCH, rs)
-                t0 = time.perf_counter()
-                next(g_cpu)
-                cpu["input_generator_patches_per_s"] = round(TRAIN_BATCH / (time.perf_counter() - t0), 1)
+            cpu = cpu_baseline_for(args.workload, threads)
+            for name in also:  # every part of BASELINE.json's metric carries its own CPU baseline in the same run
+                also[name]["cpu_baseline"] = cpu_baseline_for(name, threads)
         line = {"metric": res["metric"], "value": res["value"], "unit": res["unit"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": round(res["ms"] / args.steps, 4), "higher_is_better": True, "scaling": res["scaling"], "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic", "config": res["config"], "clocks": res["clocks"], "e2e": res["e2e"],
                 "gpu_launches": res["gpu_launches"], "roofline": res["roofline"], "cpu_baseline": cpu}
+        if dpc is not None:
+            line["dp_check"] = dpc
         if also:
             line["also"] = also
         print(json.dumps(line), flush=True)

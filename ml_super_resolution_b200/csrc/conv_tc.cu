@@ -1169,6 +1169,7 @@ extern "C" int srk_conv_tc_last(srk_handle_t h, const void* x_fpa, int cin_p, co
   SRK_CASE(64, 16, 5)
   SRK_CASE(32, 64, 3)
   SRK_CASE(64, 32, 3)
+  SRK_CASE(64, 64, 3)  // ESPCN 4x RGB training: 48 outputs from the 64-wide (zero-padded) f2 activations
 #undef SRK_CASE
   set_error("srk_conv_tc_last: unsupported (cin_p=%d, cout_p=%d, k=%d)", cin_p, cout_p, k);
   return -1;

@@ -159,6 +159,77 @@ class EspcnNet:
         return ops.espcn_forward(lr, V[self._i1], a.view("f1/bias:0"), V[self._i2], a.view("f2/bias:0"), V[self._i3f], a.view("f3/bias:0"),
                                  self.r, shuffle, out, (y0, y1), uint8)
 
+    # ------------------------------------------------------------------ host-to-host inference (the session.run seam)
+    def _host_state(self, n, H, W, shuffle, uint8):
+        key = (n, H, W, shuffle, uint8)
+        st = getattr(self, "_hs", None)
+        if st is None or st["key"] != key:
+            r, C = self.r, self.C
+            oshape = (n, H * r, W * r, C) if shuffle else (n, H, W, self.cout3)
+            odt = torch.uint8 if uint8 else torch.float32
+            st = {"key": key, "lr_dev": torch.empty((n, H, W, C), dtype=torch.float32, device=self.device),
+                  "out_dev": torch.empty(oshape, dtype=odt, device=self.device),
+                  "lr_pin": torch.empty((n, H, W, C), dtype=torch.float32).pin_memory(),
+                  "out_pin": torch.empty(oshape, dtype=odt).pin_memory(),
+                  "s_in": torch.cuda.Stream(), "s_out": torch.cuda.Stream()}
+            self._hs = st
+        return st
+
+    def forward_host(self, lr_host, out_host=None, shuffle=True, uint8=False, band_rows=540):
+        """Host array in, host array out -- what `session.run(sr, feed_dict={lr: frames})` does in the reference
+        (espcn/espcn/experiment_test.py:164-184) -- with the copies hidden: every frame is cut into row bands, and the
+        host->device copy of band k+1, the fused kernel on band k and the device->host copy of band k-1 run on three streams.
+        `lr_host` / `out_host`: numpy arrays or CPU tensors; page-locked ones (`torch.Tensor.pin_memory()`, or the arrays
+        `pinned_like()` returns) are used in place, pageable ones go through a pinned staging copy.  uint8=True returns
+        saturate_cast(x * 127.5 + 127.5) as the reference's PNG writer does (:179-184).  Returns `out_host` (or a staging
+        buffer that the next call overwrites when none was given)."""
+        lr_t = lr_host if isinstance(lr_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(lr_host, dtype=np.float32))
+        n, H, W, C = lr_t.shape
+        assert C == self.C and lr_t.dtype == torch.float32 and lr_t.is_contiguous()
+        st = self._host_state(n, H, W, shuffle, uint8)
+        if not lr_t.is_pinned():
+            st["lr_pin"].copy_(lr_t)
+            lr_t = st["lr_pin"]
+        out_t = st["out_pin"]
+        user_out = None
+        if out_host is not None:
+            cand = out_host if isinstance(out_host, torch.Tensor) else torch.from_numpy(out_host)
+            assert cand.shape == st["out_dev"].shape and cand.dtype == st["out_dev"].dtype and cand.is_contiguous()
+            if cand.is_pinned():
+                out_t = cand
+            else:
+                user_out = cand
+        lr_dev, out_dev, s_in, s_out = st["lr_dev"], st["out_dev"], st["s_in"], st["s_out"]
+        s_c = torch.cuda.current_stream()
+        s_in.wait_stream(s_c)
+        s_out.wait_stream(s_c)
+        a, V, r = self.arena, self.plan.views, (self.r if shuffle else 1)
+        bands = [(f, y0, min(H, y0 + band_rows)) for f in range(n) for y0 in range(0, H, band_rows)]
+        copied = {}  # frame -> input rows already on the device
+        ev_prev_out = None
+        for f, y0, y1 in bands:
+            need = min(H, y1 + HALO)
+            have = copied.get(f, 0)
+            with torch.cuda.stream(s_in):
+                if need > have:
+                    lr_dev[f, have:need].copy_(lr_t[f, have:need], non_blocking=True)
+                    copied[f] = need
+                ev_in = torch.cuda.Event()
+                ev_in.record(s_in)
+            s_c.wait_event(ev_in)
+            ops.espcn_forward(lr_dev[f:f + 1], V[self._i1], a.view("f1/bias:0"), V[self._i2], a.view("f2/bias:0"), V[self._i3f], a.view("f3/bias:0"),
+                              self.r, shuffle, out_dev[f:f + 1], (y0, y1), uint8)
+            ev_c = torch.cuda.Event()
+            ev_c.record(s_c)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_c)
+                out_t[f, y0 * r:y1 * r].copy_(out_dev[f, y0 * r:y1 * r], non_blocking=True)
+        s_out.synchronize()
+        if user_out is not None:
+            user_out.copy_(out_t)
+            out_t = user_out
+        return out_t if isinstance(out_host, torch.Tensor) or out_host is None else out_host
+
     def forward(self, lr: torch.Tensor, shuffle=True, out: torch.Tensor | None = None, rank=0, world=1, tile_rows=None, fused=True) -> torch.Tensor:
         """lr fp32 [N,h,w,C] -> shuffled [N,h*r,w*r,C] (shuffle=True) or packed [N,h,w,C*r^2].  fused=False runs the three
         layers as separate kernels through FPA buffers in HBM (the form training uses; kept for A/B measurements)."""
@@ -201,14 +272,35 @@ class _EspcnGraph:
     def __init__(self, net, lr_ph, hr_ph=None):
         self.net, self.lr_ph, self.hr_ph = net, lr_ph, hr_ph
 
-    def execute(self, keys, feeds):
+    @staticmethod
+    def _to_device(x, device):
+        """One path for every feed: numpy array, CPU tensor or device tensor -> contiguous fp32 device tensor."""
+        t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        return t.to(device, torch.float32, non_blocking=True).contiguous()
+
+    def execute(self, keys, feeds, outs=None):
         net = self.net
         out = {}
+        outs = outs or {}
         x = feeds[self.lr_ph]
-        lr = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
-        lr = lr.to(net.device, torch.float32).contiguous()
+        if not (keys & {"optimizer", "loss"}) and not (isinstance(x, torch.Tensor) and x.is_cuda):
+            # inference on host arrays: band-pipelined copies around the fused kernel (EspcnNet.forward_host)
+            from ..session import as_host_tensor
+            lr_h = as_host_tensor(x, np.float32)
+            for key, shuffle, u8 in (("sr_result", False, False), ("sr_results", False, False), ("hr_images", True, False), ("hr_images_u8", True, True)):
+                if key in keys and key not in out:
+                    dst = outs.get(key)
+                    res = net.forward_host(lr_h, None if dst is None else as_host_tensor(dst), shuffle, u8)
+                    val = dst if dst is not None else res.numpy().copy()  # a fresh array, as session.run returns; pass out= to avoid the copy
+                    out[key] = val
+                    if key in ("sr_result", "sr_results"):
+                        out["sr_result"] = out["sr_results"] = val
+            out["step"] = getattr(net, "step", 0)
+            out["scaling_factor"] = net.r
+            return out
+        lr = self._to_device(x, net.device)
         if "optimizer" in keys:
-            hr = torch.from_numpy(np.ascontiguousarray(feeds[self.hr_ph], dtype=np.float32)).to(net.device)
+            hr = self._to_device(feeds[self.hr_ph], net.device)
             rate = [v for k, v in feeds.items() if isinstance(k, Placeholder) and k.name == "learning_rate"]
             step_before = getattr(net, "step", 0)
             loss = net.train_step(lr, hr, float(rate[0]) if rate else 0.01)
@@ -220,12 +312,14 @@ class _EspcnGraph:
             packed = net.forward(lr, shuffle=False)
             out["sr_result"] = out["sr_results"] = packed.cpu().numpy()
             if "loss" in keys:
-                hr = torch.from_numpy(np.ascontiguousarray(feeds[self.hr_ph], dtype=np.float32)).to(net.device)
+                hr = self._to_device(feeds[self.hr_ph], net.device)
                 acc = torch.zeros(1, device=net.device)
                 ops.mse_fwd_bwd(packed, hr, acc, None)
                 out["loss"] = float(acc)
         if "hr_images" in keys:
             out["hr_images"] = net.forward(lr, shuffle=True).cpu().numpy()
+        if "hr_images_u8" in keys:
+            out["hr_images_u8"] = net.forward_fused(lr, shuffle=True, uint8=True).cpu().numpy()
         out["step"] = getattr(net, "step", 0)
         out["scaling_factor"] = net.r
         return out
@@ -235,7 +329,7 @@ def build_model(lr_source, scaling_factor=3, hr_target=None, params=None, channe
     """espcn/espcn/model_espcn.py:6 `build_model(lr_source, scaling_factor=3, hr_target=None)`."""
     net = EspcnNet(params, scaling_factor, channels, device, seed)
     g = _EspcnGraph(net, lr_source, hr_target)
-    model = {"lr_source": lr_source, "sr_result": Handle(g, "sr_result"), "hr_images": Handle(g, "hr_images")}
+    model = {"lr_source": lr_source, "sr_result": Handle(g, "sr_result"), "hr_images": Handle(g, "hr_images"), "hr_images_u8": Handle(g, "hr_images_u8")}
     if hr_target is None:
         return model
     model["hr_target"] = hr_target
@@ -262,4 +356,4 @@ def build_test_model(meta_path, ckpt_path, device="cuda"):
     net = EspcnNet(variables, scaling_factor, 3, device)
     g = _EspcnGraph(net, lr_sources)
     return {"lr_sources": lr_sources, "sr_results": Handle(g, "sr_results"), "scaling_factor": scaling_factor,
-            "hr_images": Handle(g, "hr_images")}
+            "hr_images": Handle(g, "hr_images"), "hr_images_u8": Handle(g, "hr_images_u8")}

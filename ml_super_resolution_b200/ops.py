@@ -414,6 +414,29 @@ def adam_step_dev(w, g, m, v, lr_t_dev: torch.Tensor, beta1=0.9, beta2=0.999, ep
                                        beta2, eps, weight_decay, _ptr(decay_mask), _stream()), "srk_adam_step_dev")
 
 
+class PinnedScalarFeed:
+    """Feeds one host-computed fp32 scalar per step (the bias-corrected Adam rate) into device memory without a host sync.
+    The copy reads pinned memory when the GPU EXECUTES it, not when it is queued, and with graph replay the host runs several
+    steps ahead: a single reused pinned word would be overwritten before earlier steps' copies had run.  So the values live in a
+    ring of pinned slots with one event each; a slot is rewritten only after the copy that read it has executed."""
+
+    def __init__(self, slots: int = 16):
+        self.buf = torch.zeros(slots, dtype=torch.float32).pin_memory()
+        self.events = [None] * slots
+        self.i = 0
+
+    def push(self, value: float, dst: torch.Tensor) -> None:
+        k = self.i % len(self.events)
+        self.i += 1
+        if self.events[k] is not None:
+            self.events[k].synchronize()  # (long since executed unless the host is > `slots` steps ahead)
+        self.buf[k] = value
+        dst.copy_(self.buf[k:k + 1], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[k] = ev
+
+
 def sumsq_masked(w: torch.Tensor, mask: torch.Tensor | None, scale: float, out_accum: torch.Tensor) -> None:
     check(_ffi.lib().srk_sumsq_masked(handle(), _ptr(_f32(w)), _ptr(mask), w.numel(), scale, _ptr(out_accum), _stream()), "srk_sumsq_masked")
 

@@ -32,6 +32,35 @@ class Handle:
         return f"Handle({self.key!r})"
 
 
+def pinned_empty(shape, dtype="float32"):
+    """A page-locked numpy array (backed by a pinned torch tensor that stays alive with it): feeds / fetch buffers of this kind
+    are DMA'd directly, without a staging copy."""
+    import numpy as np
+    import torch
+    t = torch.empty(tuple(shape), dtype=getattr(torch, str(np.dtype(dtype)))).pin_memory()
+    a = t.numpy()
+    _PINNED[a.__array_interface__["data"][0]] = t
+    return a
+
+
+_PINNED: dict = {}
+
+
+def as_host_tensor(x, dtype=None):
+    """numpy array / CPU tensor -> CPU tensor sharing its memory; arrays from `pinned_empty` come back as their pinned tensor."""
+    import numpy as np
+    import torch
+    if isinstance(x, torch.Tensor):
+        return x
+    x = np.asarray(x)
+    if x.flags["C_CONTIGUOUS"]:
+        t = _PINNED.get(x.__array_interface__["data"][0])
+        if t is not None and t.numel() == x.size and t.numpy().dtype == x.dtype:
+            return t.view(x.shape) if t.shape != x.shape else t
+    x = np.ascontiguousarray(x, dtype=dtype) if dtype is not None else np.ascontiguousarray(x)
+    return torch.from_numpy(x)
+
+
 class Session:
     """`with Session() as session: session.run(fetches, feed_dict=...)`."""
 
@@ -41,8 +70,11 @@ class Session:
     def __exit__(self, *exc):
         return False
 
-    def run(self, fetches, feed_dict=None):
+    def run(self, fetches, feed_dict=None, out=None):
+        """`out` (extension, optional): {Handle: preallocated host array} -- the fetch is written into that array (page-locked
+        arrays avoid a staging copy; see `pinned_empty`) and the same array is returned, like a TF callable with a fetch buffer."""
         feed_dict = feed_dict or {}
+        out = out or {}
         flat = []
 
         def collect(f):
@@ -67,7 +99,8 @@ class Session:
                 graphs.append(h.graph)
         for g in graphs:
             keys = {h.key for h in flat if h.graph is g}
-            vals = g.execute(keys, feed_dict)
+            outs = {h.key: a for h, a in out.items() if h.graph is g}
+            vals = g.execute(keys, feed_dict, outs) if outs else g.execute(keys, feed_dict)
             for k in keys:
                 results[(id(g), k)] = vals.get(k)
 

@@ -263,13 +263,12 @@ class SrcnnNet:
             ops.adam_step_dev(a.w, a.g, a.m, a.v, lr_t, beta1=0.5, beta2=0.9)
             self._repack_train()
             self.repack()
-        lr_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        lr_feed = ops.PinnedScalarFeed()
 
         def step(lr: float = 1e-3):
             g_fb.replay()
             self.step += 1
-            lr_host[0] = lr * math.sqrt(1.0 - 0.9 ** self.step) / (1.0 - 0.5 ** self.step)
-            lr_t.copy_(lr_host, non_blocking=True)
+            lr_feed.push(lr * math.sqrt(1.0 - 0.9 ** self.step) / (1.0 - 0.5 ** self.step), lr_t)
             g_opt.replay()
             return b["loss"]
 

@@ -274,15 +274,14 @@ class VdsrNet:
         with torch.cuda.graph(g_opt):
             ops.adam_step_dev(a.w, a.g, a.m, a.v, b["lr_t"], weight_decay=WEIGHT_DECAY, decay_mask=a.decay_mask)
             self.repack()
-        lr_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        lr_feed = ops.PinnedScalarFeed()
 
         def step(lr: float):
             g_fb.replay()
             if world > 1:
                 torch.distributed.all_reduce(a.g, group=group)
             self.step += 1
-            lr_host[0] = self.adam_lr_t(lr, self.step)
-            b["lr_t"].copy_(lr_host, non_blocking=True)
+            lr_feed.push(self.adam_lr_t(lr, self.step), b["lr_t"])
             g_opt.replay()
             return b["loss"]
 
