@@ -209,8 +209,11 @@ def test_graphed_steps_without_host_sync_equal_eager(srk_ops):
     for _ in range(12):
         step(1e-3)  # no float(loss), no synchronize
     torch.cuda.synchronize()
-    we, wg = eager.arena.w, graphed.arena.w
-    assert float((we - wg).abs().max()) <= 1e-6 * float(we.abs().max()) + 1e-7
+    d = (eager.arena.w - graphed.arena.w).abs()
+    # fp32 atomics in the first/last-layer wgrad and the MSE sum make last bits order-dependent, and Adam's first steps act like
+    # sign(g): single elements may differ by up to 2*lr per step.  A stale Adam rate (a later step's, ~25 % off during the first
+    # steps) would instead shift EVERY weight: mean |d| ~ 1e-4.
+    assert float(d.mean()) <= 2e-5 and float(d.max()) <= 12 * 2e-3, (float(d.mean()), float(d.max()))
 
 
 # ------------------------------------------------------------------------------------------------ EnhanceNet cfg5
