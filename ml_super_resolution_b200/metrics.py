@@ -43,7 +43,7 @@ def rgb_to_y(x: torch.Tensor, scale=1.0, bias=0.0, clip=(-3.0e38, 3.0e38)) -> to
     return y
 
 
-def espcn_scores(sr_packed: torch.Tensor, hr_packed: torch.Tensor, scaling_factor: int, score_space: str = "rgb"):
+def espcn_scores(sr_packed: torch.Tensor, hr_packed: torch.Tensor, scaling_factor: int, score_space: str = "y"):
     """espcn/espcn/experiment_test.py:30-53 -> (psnrs, ssims), max_val 1.0, in RGB or Y space of the PACKED tensors."""
     n, h, w, c = hr_packed.shape
     if score_space == "y":

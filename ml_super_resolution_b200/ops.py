@@ -475,7 +475,6 @@ class PackPlan:
             elem += count
         self.total = elem
         self.out = torch.zeros(_round_up(dst, 1024), dtype=torch.uint8, device=self.device)
-        assert self.out.data_ptr() % 1024 == 0 or True
         host = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
         self.jobs_dev = torch.from_numpy(host).to(self.device)
         self.views = [self.out[o:o + nb].view(dt).view(shape) for (o, nb, shape, dt) in layout]

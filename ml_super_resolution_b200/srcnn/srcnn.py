@@ -290,9 +290,13 @@ class _SrcnnGraph:
     def __init__(self, net, hi_ph):
         self.net, self.hi_ph = net, hi_ph
 
+    reader = None
+
     def execute(self, keys, feeds):
         net = self.net
-        x = feeds[self.hi_ph]
+        if keys == {"step"}:
+            return {"step": net.step}
+        x = feeds[self.hi_ph] if self.hi_ph is not None and self.hi_ph in feeds else next(self.reader)
         hi = (x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))).to(net.device).contiguous()
         if "trainer" in keys:
             b = net.forward_backward(hi)
@@ -309,14 +313,128 @@ class _SrcnnGraph:
         sr = net.forward(lo)
         side = (hi.shape[1] - sr.shape[1]) // 2
         crop = lambda t: t[:, side:side + sr.shape[1], side:side + sr.shape[1], :]
-        out = {"step": 0, "sr_images": sr.cpu().numpy(), "hd_images": crop(hi).cpu().numpy(), "sd_images": crop(lo).cpu().numpy()}
+        out = {"step": net.step, "sr_images": sr.cpu().numpy(), "hd_images": crop(hi).cpu().numpy(), "sd_images": crop(lo).cpu().numpy()}
         if "loss" in keys:
             out["loss"] = float(net.loss(sr, hi)[0])
         return out
 
 
+def build_dataset_reader(flags=FLAGS, seed=None):
+    """srcnn/srcnn.py:46-78: an endless generator of [batch, crop, crop, 3] batches in [-1, 1] -- whole JPEG files read, randomly
+    cropped and randomly mirrored -- from `training_images_path/*.jpg` (training) or the one `sr_source_path` image."""
+    import glob
+    import os
+    from ..io.images import imread_u8
+    paths = glob.glob(os.path.join(flags.training_images_path, "*.jpg")) if flags.train else [flags.sr_source_path]
+    rng = np.random.RandomState(seed)
+    size = flags.crop_image_size
+    images = {}
+
+    def crops():
+        while True:
+            for p_ in rng.permutation(paths):  # tf.train.string_input_producer: shuffled epochs
+                if p_ not in images:
+                    images[p_] = imread_u8(p_)
+                im = images[p_]
+                y, x = rng.randint(0, im.shape[0] - size + 1), rng.randint(0, im.shape[1] - size + 1)
+                c = im[y:y + size, x:x + size]
+                if rng.randint(2):
+                    c = c[:, ::-1]
+                yield c.astype(np.float32) / 127.5 - 1.0
+
+    g = crops()
+    while True:
+        yield np.stack([next(g) for _ in range(flags.batch_size)])
+
+
 def build_srcnn(hi_images=None, params=None, channels=3, device="cuda", seed=0, flags=FLAGS):
-    """srcnn/srcnn.py:81 `build_srcnn()`; `hi_images` replaces the in-graph dataset reader (:86)."""
+    """srcnn/srcnn.py:81 `build_srcnn()`: called without arguments it reads the global FLAGS and owns its dataset reader, as the
+    reference does (fetches need no feeds); `hi_images` (a placeholder) replaces the in-graph reader (:86) with a feed."""
     net = SrcnnNet(params, channels, device, seed, flags)
     g = _SrcnnGraph(net, hi_images)
+    if hi_images is None and (flags.training_images_path or flags.sr_source_path):
+        g.reader = build_dataset_reader(flags)
     return {k: Handle(g, k) for k in ("step", "loss", "trainer", "hd_images", "sd_images", "sr_images")}
+
+
+def build_sr_result(fetched):
+    """srcnn/srcnn.py:168-183: [hd | sd | sr] side by side, the batch stacked vertically (numpy, from fetched arrays)."""
+    hd, sd, sr = fetched["hd_images"], fetched["sd_images"], fetched["sr_images"]
+    b, w = hd.shape[0], hd.shape[1]
+    return np.concatenate([hd.reshape(1, b * w, w, -1), sd.reshape(1, b * w, w, -1), sr.reshape(1, b * w, w, -1)], axis=2)
+
+
+def train(flags=FLAGS):
+    """srcnn/srcnn.py:203-258."""
+    import glob
+    import json
+    import os
+    from ..params import load_params
+    from ..session import Session
+    os.makedirs(flags.ckpt_dir_path, exist_ok=True)
+    os.makedirs(flags.logs_dir_path, exist_ok=True)
+    found = glob.glob(os.path.join(flags.ckpt_dir_path, "model.ckpt-*.npz"))
+    source = max(found, key=lambda p_: int(p_.rsplit("-", 1)[1][:-4])) if found else None
+    srcnn = build_srcnn(params=load_params(source) if source else None, flags=flags)
+    net = srcnn["step"].graph.net
+    if source:
+        net.step = int(source.rsplit("-", 1)[1][:-4])
+    log = open(os.path.join(flags.logs_dir_path, "events.jsonl"), "a")
+    stop = getattr(flags, "stop_training_at_k_step", None)  # (extension: the reference loops until interrupted)
+    with Session() as session:
+        while True:
+            fetched = session.run({"loss": srcnn["loss"], "step": srcnn["step"], "trainer": srcnn["trainer"]})
+            step = fetched["step"]
+            log.write(json.dumps({"step": int(step), "loss": float(fetched["loss"])}) + "\n")
+            if step % 100 == 0:
+                print("loss[{}]: {}".format(step, fetched["loss"]))
+            if step % 5000 == 0 or step == stop:
+                net.arena.save(os.path.join(flags.ckpt_dir_path, f"model.ckpt-{step}.npz"), global_step=step)
+            if step == stop:
+                break
+    log.close()
+
+
+def super_resolution(flags=FLAGS):
+    """srcnn/srcnn.py:261-288: [hd | sd | sr] of one crop of `sr_source_path`, saturate_cast((x + 1) * 127.5), written as an image."""
+    import glob
+    import os
+    from ..io.images import write_png
+    from ..params import load_params
+    from ..session import Session
+    found = glob.glob(os.path.join(flags.ckpt_dir_path, "model.ckpt-*.npz"))
+    source = max(found, key=lambda p_: int(p_.rsplit("-", 1)[1][:-4]))
+    srcnn = build_srcnn(params=load_params(source), flags=flags)
+    with Session() as session:
+        fetched = session.run({k: srcnn[k] for k in ("hd_images", "sd_images", "sr_images")})
+    image = build_sr_result(fetched)[0]
+    write_png(flags.sr_target_path, np.clip((image + 1.0) * 127.5, 0, 255).astype(np.uint8))
+
+
+def main(_):
+    """srcnn/srcnn.py:291-299."""
+    sanity_check()
+    if FLAGS.train:
+        train()
+    else:
+        super_resolution()
+
+
+if __name__ == "__main__":
+    from .. import flags as _flags
+    for _name, _default in vars(FLAGS).items():
+        _kind = {bool: _flags.DEFINE_boolean, int: _flags.DEFINE_integer}.get(type(_default), _flags.DEFINE_string)
+        _kind(_name, _default, "")
+    _flags.DEFINE_integer("stop_training_at_k_step", 0, "stop after k steps (0: run until interrupted, as the reference does)")
+    _argv = []
+    for _a in __import__("sys").argv[1:]:  # the reference spells its flags with hyphens (--ckpt-dir-path): same names here
+        if _a.startswith("--"):
+            _k, _eq, _v = _a[2:].partition("=")
+            _a = "--" + _k.replace("-", "_") + _eq + _v
+        _argv.append(_a)
+    _flags.parse(_argv)
+    for _name in list(vars(FLAGS)) + ["stop_training_at_k_step"]:
+        setattr(FLAGS, _name, getattr(_flags.FLAGS, _name))
+    if not FLAGS.stop_training_at_k_step:
+        FLAGS.stop_training_at_k_step = None
+    main(None)

@@ -132,3 +132,13 @@ def image_batches(images, scaling_factors, image_size, batch_size, seed=None, rn
         yield bufs[slot]["sd"], bufs[slot]["hd"]
         consumed[slot].record(torch.cuda.current_stream())  # recorded when the consumer asks for the next batch
         slot ^= 1
+
+
+def hd_image_to_sd_image(hd_image, scaling_factor):
+    """vdsr/vdsr/dataset.py:13-38, same call: `hd_image` float [H,W,C] in [0,1] -> the blurred, bilinearly down- and up-scaled
+    `sd_image` [H,W,C] (numpy in, numpy out); the arithmetic runs in srk_degrade_gauss_bilinear on the current device."""
+    hd = np.ascontiguousarray(hd_image, dtype=np.float32)
+    assert hd.ndim == 3
+    x = torch.from_numpy(hd[None]).cuda()
+    scales = torch.full((1,), float(scaling_factor), dtype=torch.float32, device=x.device)
+    return ops.degrade_gauss_bilinear(x, scales)[0].cpu().numpy()

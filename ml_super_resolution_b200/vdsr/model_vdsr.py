@@ -340,16 +340,17 @@ class _VdsrGraph:
         out = {}
         if keys == {"step"}:
             return {"step": net.step}
+        learning_rate = net.learning_rate  # a fed value overrides the variable for THIS run only, as a TF feed does
         for ph, val in feeds.items():
-            if isinstance(ph, Placeholder) and ph.variable_of is self:
-                self.set_variable(ph.name, val)
+            if isinstance(ph, Placeholder) and ph.variable_of is self and ph.name == "learning_rate":
+                learning_rate = float(val)
         sd = _to_device(feeds[self.sd_ph], net.device)
         train = "trainer" in keys
         if train or "loss" in keys or "psnr" in keys:
             hd = _to_device(feeds[self.hd_ph], net.device)
         if train:
             out["step"] = net.step
-            loss = net.train_step(sd, hd, net.learning_rate, self.use_adam)
+            loss = net.train_step(sd, hd, learning_rate, self.use_adam)
             out["trainer"] = None
             out["loss"] = float(loss)
             sr = net._train_bufs["sr"]
