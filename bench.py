@@ -672,7 +672,7 @@ def dp_check(rank: int, world: int) -> dict:
     return res
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out):
     """The reference's CPU path: oracle restatement of the TF-1.8 graph on torch-CPU fp32 with all host threads."""
     if rank != 0:
         return
@@ -713,10 +713,36 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": round(v, 3), "unit": unit, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": round(v, 3), "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": round(time.perf_counter() - t_all, 1)}
-    print(json.dumps(line), flush=True)
+    out.emit(json.dumps(line))
+
+
+class _JsonOnlyStdout:
+    """Keeps stdout for the ONE JSON line: while the benchmark runs, file descriptor 1 points at stderr, so anything a library
+    prints to stdout (NCCL's version banner, for one) cannot end up next to the record."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line: str):
+        sys.stdout.flush()
+        os.write(self.saved, (line + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
 
 
 def main():
+    with _JsonOnlyStdout() as out:
+        _main(out)
+
+
+def _main(out):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -729,7 +755,7 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     rank, world, local = dist_info()
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, out)
         return
     assert torch.cuda.is_available(), "bench.py (native arm) needs a B200; there is no CPU fallback"
     if world != args.gpus and world == 1 and args.gpus > 1:
@@ -762,7 +788,7 @@ def main():
             line["dp_check"] = dpc
         if also:
             line["also"] = also
-        print(json.dumps(line), flush=True)
+        out.emit(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
 

@@ -160,6 +160,17 @@ typedef struct {
 int srk_espcn_forward(srk_handle_t h, const srk_espcn_net* net, const float* lr, int n, int H, int W, int y_begin,
                       int y_end, int shuffle, int out_kind, void* out, srk_stream_t stream);
 
+/* ---- data-parallel exchange step: NCCL sum all-reduce of the flat fp32 gradient arena over NVLink ----------
+ * The reference trains on one GPU (vdsr/README.md:14); these calls extend the `minimize` of vdsr/vdsr/model_vdsr.py:146-148
+ * (gradients are summed across ranks before the optimiser applies them; every rank then runs the identical update).
+ * NCCL is loaded at run time (libnccl.so.2 of the host process).  srk_comm_unique_id: rank 0 creates the 128-byte
+ * ncclUniqueId, the host distributes it (any side channel), every rank calls srk_comm_init (collective, blocking).
+ * srk_allreduce_grads is asynchronous on `stream` and may be captured into a CUDA graph. */
+int srk_comm_unique_id(void* id128);
+int srk_comm_init(srk_handle_t h, const void* id128, int rank, int world);
+int srk_allreduce_grads(srk_handle_t h, float* flat, size_t n, srk_stream_t stream);
+int srk_comm_destroy(srk_handle_t h);
+
 /* Weight gradient of a 3x3 64->64 layer on tensor cores: dW[u,v,ci,co] = sum_p x[p+(u-1)*Wp+(v-1)][ci]
  * * dy[p][co], dbias[co] = sum_p dy[p][co].  Split over CTAs along the pixel axis; every CTA stores its
  * partial [9*64*64+64] block into `workspace` and a second kernel sums the partials in a fixed order

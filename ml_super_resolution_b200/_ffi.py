@@ -79,6 +79,10 @@ SIGNATURES = {
     "srk_u8_to_pm1": (_I, [_P, _P, _SZ, _P, _P]),
     "srk_crop_flip_u8": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "srk_affine_f32": (_I, [_P, _P, _SZ, _F, _F, _P, _P]),
+    "srk_comm_unique_id": (_I, [_P]),
+    "srk_comm_init": (_I, [_P, _P, _I, _I]),
+    "srk_allreduce_grads": (_I, [_P, _P, _SZ, _P]),
+    "srk_comm_destroy": (_I, [_P]),
     "srk_espcn_forward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "srk_fpa_halo_exchange": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _P]),
     "srk_fpa_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
@@ -104,7 +108,7 @@ def lib() -> C.CDLL:
 # kernels launched per C-ABI call (everything else: 0) -- feeds bench.py's `gpu_launches`
 KERNELS_PER_CALL = {name: 1 for name in SIGNATURES if name not in
                     ("srk_version", "srk_last_error", "srk_create", "srk_destroy", "srk_num_sms", "srk_fpa_rows",
-                     "srk_conv_wgrad_tc_workspace_bytes")}
+                     "srk_conv_wgrad_tc_workspace_bytes", "srk_comm_unique_id", "srk_comm_init", "srk_allreduce_grads", "srk_comm_destroy")}
 KERNELS_PER_CALL["srk_conv_wgrad_tc"] = 1  # +1 when it also runs the reduce (counted as srk_wgrad_reduce_many otherwise)
 launch_count = 0
 

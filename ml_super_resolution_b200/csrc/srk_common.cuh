@@ -41,7 +41,7 @@ struct srk_ctx {
   std::unordered_set<const void*> once;  // kernels whose attributes are set / tables that are uploaded on this device
   std::unordered_map<srk_tmap_key, CUtensorMap, srk_tmap_key_hash> tmaps;
   void* comm = nullptr;      // ncclComm_t once srk_comm_init has run (collective.cu)
-  void* comm_lib = nullptr;  // dlopen handle of libnccl
+  int comm_world = 1;
 };
 
 namespace srk {

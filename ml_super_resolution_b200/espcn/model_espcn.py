@@ -133,7 +133,8 @@ class EspcnNet:
         b = self.forward_backward(lr, hr_packed, float(hr_packed.numel()) * world)
         a = self.arena
         if world > 1:
-            torch.distributed.all_reduce(a.g, group=group)
+            ops.comm_init(group)
+            ops.allreduce_grads(a.g)
         self.step += 1
         ops.adam_step(a.w, a.g, a.m, a.v, learning_rate, self.step)
         self._repack_train()

@@ -414,6 +414,30 @@ def adam_step_dev(w, g, m, v, lr_t_dev: torch.Tensor, beta1=0.9, beta2=0.999, ep
                                        beta2, eps, weight_decay, _ptr(decay_mask), _stream()), "srk_adam_step_dev")
 
 
+_comm_ready: set = set()
+
+
+def comm_init(group=None) -> None:
+    """srk_comm_init on this rank's handle: rank 0 creates the ncclUniqueId, torch.distributed (any backend) hands it round."""
+    import torch.distributed as dist
+    dev = torch.cuda.current_device()
+    if dev in _comm_ready:
+        return
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    buf = (C.c_char * 128)()
+    if rank == 0:
+        check(_ffi.lib().srk_comm_unique_id(buf), "srk_comm_unique_id")
+    ids = [bytes(buf)]
+    dist.broadcast_object_list(ids, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    check(_ffi.lib().srk_comm_init(handle(), C.c_char_p(ids[0]), rank, world), "srk_comm_init")
+    _comm_ready.add(dev)
+
+
+def allreduce_grads(flat: torch.Tensor) -> None:
+    """Sum all-reduce of the flat gradient arena over the ranks of `comm_init` (srk_allreduce_grads; graph-capturable)."""
+    check(_ffi.lib().srk_allreduce_grads(handle(), _ptr(_f32(flat)), flat.numel(), _stream()), "srk_allreduce_grads")
+
+
 class PinnedScalarFeed:
     """Feeds one host-computed fp32 scalar per step (the bias-corrected Adam rate) into device memory without a host sync.
     The copy reads pinned memory when the GPU EXECUTES it, not when it is queued, and with graph replay the host runs several

@@ -242,20 +242,23 @@ class VdsrNet:
             world = torch.distributed.get_world_size(group)
         b = self.forward_backward(sd, hd, numel_total=float(sd.numel()) * world)
         if world > 1:
-            torch.distributed.all_reduce(self.arena.g, group=group)  # NCCL sum over NVLink: the one exchange step
+            ops.comm_init(group)
+            ops.allreduce_grads(self.arena.g)  # srk_allreduce_grads: NCCL sum over NVLink, the path's one exchange step
         self.apply_gradients(lr, use_adam)
         return b["loss"].sum()
 
     def make_graphed_step(self, sd_static: torch.Tensor, hd_static: torch.Tensor, group=None):
         """Capture the Adam training step into CUDA graphs (the ~85 launches of a step are latency-bound at
         64 patches of 41x41).  Returns `step(lr) -> loss buffer [mse, reg]`; new batches are copied INTO
-        `sd_static` / `hd_static` before each call.  Graph A = forward + loss + backward, then (world > 1) the
-        NCCL gradient all-reduce runs eagerly, graph B = Adam (learning rate read from device memory, so the
-        same graph serves every step) + weight re-pack."""
+        `sd_static` / `hd_static` before each call.  ONE graph holds forward + loss + backward, the NCCL gradient
+        all-reduce (srk_allreduce_grads, captured like any other kernel: no host round trip between backward and
+        optimiser) and Adam (learning rate read from device memory, so the same graph serves every step) + re-pack."""
         world = 1
         if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             world = torch.distributed.get_world_size(group)
         numel_total = float(sd_static.numel()) * world
+        if world > 1:
+            ops.comm_init(group)
         a = self.arena
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -268,24 +271,25 @@ class VdsrNet:
         a.m.zero_()
         a.v.zero_()
         torch.cuda.synchronize()
-        g_fb, g_opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g_fb):
+        if world > 1:
+            ops.allreduce_grads(a.g)  # first collective outside capture: NCCL sets up its channels here
+            torch.cuda.synchronize()
+        g_step = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_step):
             self.forward_backward(sd_static, hd_static, numel_total)
-        with torch.cuda.graph(g_opt):
+            if world > 1:
+                ops.allreduce_grads(a.g)
             ops.adam_step_dev(a.w, a.g, a.m, a.v, b["lr_t"], weight_decay=WEIGHT_DECAY, decay_mask=a.decay_mask)
             self.repack()
         lr_feed = ops.PinnedScalarFeed()
 
         def step(lr: float):
-            g_fb.replay()
-            if world > 1:
-                torch.distributed.all_reduce(a.g, group=group)
             self.step += 1
             lr_feed.push(self.adam_lr_t(lr, self.step), b["lr_t"])
-            g_opt.replay()
+            g_step.replay()
             return b["loss"]
 
-        step.graphs = (g_fb, g_opt)
+        step.graphs = (g_step,)
         return step
 
     @staticmethod
