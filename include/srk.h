@@ -34,7 +34,8 @@ extern "C" {
 typedef struct srk_ctx* srk_handle_t;
 typedef void* srk_stream_t; /* cudaStream_t */
 
-enum { SRK_ACT_NONE = 0, SRK_ACT_RELU = 1, SRK_ACT_TANH = 2 };
+enum { SRK_ACT_NONE = 0, SRK_ACT_RELU = 1, SRK_ACT_TANH = 2, SRK_ACT_LEAKY_RELU = 3, SRK_ACT_SIGMOID = 4 };
+enum { SRK_DT_BF16 = 0, SRK_DT_TF32 = 1, SRK_DT_F32 = 1 }; /* storage: bf16, or fp32 (read by the tensor core as tf32) */
 enum { SRK_PAD_SAME = 0, SRK_PAD_VALID = 1 };
 enum { SRK_PACK_FWD = 0, SRK_PACK_DGRAD = 1, SRK_PACK_ROT180T_F32 = 2, SRK_PACK_FIRST = 3, SRK_PACK_FIRST_ROT180T = 4 };
 
@@ -159,6 +160,61 @@ typedef struct {
 } srk_espcn_net;
 int srk_espcn_forward(srk_handle_t h, const srk_espcn_net* net, const float* lr, int n, int H, int W, int y_begin,
                       int y_end, int shuffle, int out_kind, void* out, srk_stream_t stream);
+
+/* ---- generic tensor-core GEMM and the layers built on it (csrc/gemm_tc.cu, csrc/f2_ops.cu) ------------------------------
+ * D[b][M][N] = act(A[b][M][K] x B[b][N][K]^T + bias[N]): both operands row-major with K contiguous (leading dimensions lda / ldb
+ * and batch strides in ELEMENTS; rows must start on 16-byte boundaries), in_dtype SRK_DT_BF16 or SRK_DT_TF32 (fp32 storage,
+ * tcgen05 kind::tf32), fp32 accumulation, D bf16 or fp32.  act: SRK_ACT_* (leaky = slope of SRK_ACT_LEAKY_RELU; tanh is tanhf).
+ * With srk_im2col / srk_col2im / srk_transpose this is
+ *   tf.layers.conv2d(.., 3, strides 1|2, 'same', leaky_relu), tf.layers.dense       enet/enet/model_enet.py:129-159 (discriminator)
+ *   tf.nn.conv2d + bias_add + relu                                                  enet/enet/model_vgg.py:11-24 (VGG-19)
+ *   tf.matmul(x, x, transpose_a=True) per 16x16 patch                               enet/enet/model_enet.py:248-249 (Gram matrices)
+ * and their gradients (what `minimize` adds, :325-335), and -- with SRK_DT_TF32 -- the fp32-storage form of every convolution of
+ * the four models (north_star's tf32 variant). */
+int srk_gemm_tc(srk_handle_t h, const void* A, const void* B, void* D, int M, int N, int K, int batch, long long lda,
+                long long ldb, long long ldd, long long stride_a, long long stride_b, long long stride_d, const float* bias,
+                int act, float leaky, int in_dtype, int out_dtype, srk_stream_t stream);
+/* TF output size of a k x k / stride window: 'SAME' ceil(in / stride), 'VALID' (in - k) / stride + 1. */
+int srk_conv_out_size(int in, int k, int stride, int pad_mode);
+/* col[m][(u*k+v)*C + c] = x[n, oy*s+u-pt, ox*s+v-pl, c] (zero outside; TF 'SAME' pads pad_total/2 before and the remainder AFTER:
+ * asymmetric for stride 2), rows Kp >= k*k*C long (zero beyond); transposed != 0 writes colT[kk][m] with row length Mp instead
+ * (the K-major operand of the weight gradient).  x, col: bf16 or fp32 NHWC. */
+int srk_im2col(srk_handle_t h, const void* x, int dtype, int n, int H, int W, int C, int k, int stride, int pad_mode, void* col,
+               int Kp, long long Mp, int transposed, srk_stream_t stream);
+/* dx[n,y,x,c] = sum of the dcol entries that srk_im2col filled from it (gather form, deterministic): the data gradient. */
+int srk_col2im(srk_handle_t h, const void* dcol, int dtype, int n, int H, int W, int C, int k, int stride, int pad_mode, int Kp,
+               void* dx, srk_stream_t stream);
+/* y[b][c][r] = x[b][r][c]. */
+int srk_transpose(srk_handle_t h, const void* x, int dtype, int batch, int R, int Ccols, long long ldx, long long stride_x, void* y,
+                  long long ldy, long long stride_y, srk_stream_t stream);
+/* tf.nn.max_pool(ksize 2, strides 2, 'SAME') and its gradient (first maximum of a window receives it).  model_vgg.py:27-36 */
+int srk_maxpool2x2(srk_handle_t h, const void* x, int dtype, int n, int H, int W, int C, void* y, srk_stream_t stream);
+int srk_maxpool2x2_bwd(srk_handle_t h, const void* x, const void* dy, int dtype, int n, int H, int W, int C, void* dx, srk_stream_t stream);
+/* dx = dy * act'(y), y = the saved activation OUTPUT (relu, leaky-relu, sigmoid, tanh). */
+int srk_act_bwd(srk_handle_t h, const void* dy, const void* y, int dtype, long long n, int act, float leaky, void* dx, srk_stream_t stream);
+/* VGG input: y[p][c] = x[p][2-c] * scale + shift - (103.939, 116.779, 123.68)[c]   (tf.reverse + mean pixel, model_vgg.py:77-81; the
+ * caller's scale / shift = 127.5 / 127.5 map [-1,1] images to [0,255], model_enet.py:291-292); gradient w.r.t. x (optionally added). */
+int srk_vgg_preprocess(srk_handle_t h, const float* x, long long pixels, float scale, float shift, int out_dtype, void* y, srk_stream_t stream);
+int srk_vgg_preprocess_bwd(srk_handle_t h, const void* dy, int dtype, long long pixels, float scale, float* dx, int accumulate, srk_stream_t stream);
+/* normalize(): y = x / (reduce_mean(x, axis=-1, keepdims) + 1e-6), fp32 out, and its gradient.  model_enet.py:34-41 */
+int srk_normalize_channels(srk_handle_t h, const void* x, int dtype, long long pixels, int C, float* y, srk_stream_t stream);
+int srk_normalize_channels_bwd(srk_handle_t h, const void* x, const float* dy, int dtype, long long pixels, int C, void* dx, srk_stream_t stream);
+/* tf.extract_image_patches(16x16, stride 16, VALID) + reshape [-1, 256, C] (model_enet.py:226-243) as bf16: xp [q][256][C] and its
+ * transpose xt [q][C][256] (the K-major operand of the Gram GEMM); gradient from d(xt) back to the NHWC tensor. */
+int srk_extract_patches16(srk_handle_t h, const float* x, int n, int H, int W, int C, void* xp_bf16, void* xt_bf16, srk_stream_t stream);
+int srk_extract_patches16_bwd(srk_handle_t h, const float* dxt, int n, int H, int W, int C, float* dx, srk_stream_t stream);
+/* tf.losses.log_loss(labels = label * ones, predictions = p, MEAN): *loss_accum += scale * loss; dp = scale * d loss / d p.  :164-181 */
+int srk_log_loss(srk_handle_t h, const float* p, long long n, float label, float scale, float* loss_accum, float* dp, srk_stream_t stream);
+/* y = alpha * x + beta * y ;  y = convert(x * scale) ;  out[c] (=|+=) sum_m x[m][c] (bias gradients). */
+int srk_axpby(srk_handle_t h, const float* x, long long n, float alpha, float beta, float* y, srk_stream_t stream);
+int srk_convert(srk_handle_t h, const void* x, int src_dtype, long long n, float scale, void* y, int dst_dtype, srk_stream_t stream);
+int srk_colsum(srk_handle_t h, const void* x, int dtype, long long M, int C, float* out, int accumulate, srk_stream_t stream);
+
+/* 3xTF32 operand split for fp32-level accuracy on the tf32 tensor cores: row r of y = [hi | lo | hi] (side 0: the A operand) or
+ * [hi | hi | lo] (side 1: the B operand), hi = round-to-nearest tf32(x), lo = tf32(x - hi), segments Kp (multiple of 4) long.
+ * srk_gemm_tc over the 3*Kp-long rows then yields hi.hi + lo.hi + hi.lo. */
+int srk_tf32_split(srk_handle_t h, const float* x, int batch, long long R, int K, long long ldx, long long stride_x, float* y, int Kp,
+                   int side, srk_stream_t stream);
 
 /* ---- data-parallel exchange step: NCCL sum all-reduce of the flat fp32 gradient arena over NVLink ----------
  * The reference trains on one GPU (vdsr/README.md:14); these calls extend the `minimize` of vdsr/vdsr/model_vdsr.py:146-148

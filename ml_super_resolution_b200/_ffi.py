@@ -79,6 +79,25 @@ SIGNATURES = {
     "srk_u8_to_pm1": (_I, [_P, _P, _SZ, _P, _P]),
     "srk_crop_flip_u8": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "srk_affine_f32": (_I, [_P, _P, _SZ, _F, _F, _P, _P]),
+    "srk_gemm_tc": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I64, _I64, _I64, _I64, _I64, _I64, _P, _I, _F, _I, _I, _P]),
+    "srk_conv_out_size": (_I, [_I, _I, _I, _I]),
+    "srk_im2col": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I64, _I, _P]),
+    "srk_col2im": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "srk_transpose": (_I, [_P, _P, _I, _I, _I, _I, _I64, _I64, _P, _I64, _I64, _P]),
+    "srk_maxpool2x2": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "srk_maxpool2x2_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "srk_act_bwd": (_I, [_P, _P, _P, _I, _I64, _I, _F, _P, _P]),
+    "srk_vgg_preprocess": (_I, [_P, _P, _I64, _F, _F, _I, _P, _P]),
+    "srk_vgg_preprocess_bwd": (_I, [_P, _P, _I, _I64, _F, _P, _I, _P]),
+    "srk_normalize_channels": (_I, [_P, _P, _I, _I64, _I, _P, _P]),
+    "srk_normalize_channels_bwd": (_I, [_P, _P, _P, _I, _I64, _I, _P, _P]),
+    "srk_extract_patches16": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "srk_extract_patches16_bwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
+    "srk_log_loss": (_I, [_P, _P, _I64, _F, _F, _P, _P, _P]),
+    "srk_axpby": (_I, [_P, _P, _I64, _F, _F, _P, _P]),
+    "srk_convert": (_I, [_P, _P, _I, _I64, _F, _P, _I, _P]),
+    "srk_colsum": (_I, [_P, _P, _I, _I64, _I, _P, _I, _P]),
+    "srk_tf32_split": (_I, [_P, _P, _I, _I64, _I, _I64, _I64, _P, _I, _I, _P]),
     "srk_comm_unique_id": (_I, [_P]),
     "srk_comm_init": (_I, [_P, _P, _I, _I]),
     "srk_allreduce_grads": (_I, [_P, _P, _SZ, _P]),
@@ -108,7 +127,7 @@ def lib() -> C.CDLL:
 # kernels launched per C-ABI call (everything else: 0) -- feeds bench.py's `gpu_launches`
 KERNELS_PER_CALL = {name: 1 for name in SIGNATURES if name not in
                     ("srk_version", "srk_last_error", "srk_create", "srk_destroy", "srk_num_sms", "srk_fpa_rows",
-                     "srk_conv_wgrad_tc_workspace_bytes", "srk_comm_unique_id", "srk_comm_init", "srk_allreduce_grads", "srk_comm_destroy")}
+                     "srk_conv_wgrad_tc_workspace_bytes", "srk_conv_out_size", "srk_comm_unique_id", "srk_comm_init", "srk_allreduce_grads", "srk_comm_destroy")}
 KERNELS_PER_CALL["srk_conv_wgrad_tc"] = 1  # +1 when it also runs the reduce (counted as srk_wgrad_reduce_many otherwise)
 launch_count = 0
 

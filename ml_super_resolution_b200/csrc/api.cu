@@ -70,6 +70,39 @@ int make_tensor_map_2d(srk_ctx* h, CUtensorMap* out, const void* gptr, uint64_t 
   return 0;
 }
 
+int make_tensor_map_3d(srk_ctx* h, CUtensorMap* out, const void* gptr, uint32_t elem_bytes, uint64_t rows, uint64_t cols, uint64_t batch,
+                       uint64_t row_stride_bytes, uint64_t batch_stride_bytes, uint32_t box_rows) {
+  SRK_REQUIRE(elem_bytes == 2 || elem_bytes == 4, "tensor map: element size %u", elem_bytes);
+  SRK_REQUIRE(row_stride_bytes % 16 == 0 && (batch <= 1 || batch_stride_bytes % 16 == 0) && reinterpret_cast<uintptr_t>(gptr) % 16 == 0,
+              "tensor map: base and strides must be multiples of 16 bytes (row stride %llu, batch stride %llu)", (unsigned long long)row_stride_bytes,
+              (unsigned long long)batch_stride_bytes);
+  const uint32_t box_cols = 128 / elem_bytes;
+  srk_tmap_key key{gptr, rows, uint32_t(cols), box_rows, box_cols, elem_bytes};
+  key.row_stride = row_stride_bytes;
+  key.batch = batch;
+  key.batch_stride = batch_stride_bytes;
+  auto it = h->tmaps.find(key);
+  if (it != h->tmaps.end()) {
+    *out = it->second;
+    return 0;
+  }
+  if (h->tmaps.size() > 4096) h->tmaps.clear();
+  EncodeTiledFn enc = encode_fn();
+  SRK_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  if (batch < 1) batch = 1;
+  cuuint64_t dims[3] = {cols, rows, batch};
+  cuuint64_t strides[2] = {row_stride_bytes, batch > 1 ? batch_stride_bytes : row_stride_bytes * rows};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(gptr), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SRK_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d (ptr %p rows %llu cols %llu batch %llu)", int(r), gptr,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)batch);
+  h->tmaps.emplace(key, *out);
+  return 0;
+}
+
 }  // namespace srk
 
 extern "C" {

@@ -18,8 +18,10 @@ struct srk_tmap_key {
   const void* ptr;
   uint64_t rows;
   uint32_t cols, box_rows, box_cols, elem_bytes;
+  uint64_t row_stride = 0, batch = 0, batch_stride = 0;  // (3-D maps of the generic GEMM; 0 for the packed 2-D maps)
   bool operator==(const srk_tmap_key& o) const {
-    return ptr == o.ptr && rows == o.rows && cols == o.cols && box_rows == o.box_rows && box_cols == o.box_cols && elem_bytes == o.elem_bytes;
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && box_rows == o.box_rows && box_cols == o.box_cols && elem_bytes == o.elem_bytes &&
+           row_stride == o.row_stride && batch == o.batch && batch_stride == o.batch_stride;
   }
 };
 struct srk_tmap_key_hash {
@@ -27,6 +29,7 @@ struct srk_tmap_key_hash {
     uint64_t h = reinterpret_cast<uint64_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
     h ^= (k.rows + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
     h ^= ((uint64_t(k.cols) << 40) ^ (uint64_t(k.box_rows) << 20) ^ (uint64_t(k.box_cols) << 4) ^ k.elem_bytes) * 0xC2B2AE3D27D4EB4Full;
+    h ^= (k.row_stride * 0x9E3779B97F4A7C15ull) ^ (k.batch << 17) ^ (k.batch_stride * 0xD6E8FEB86659FD93ull);
     return size_t(h);
   }
 };
@@ -96,6 +99,11 @@ inline FpaGeom fpa_geom(int n_img, int H, int W) {
 // (128 B -> SW128, 64 B -> SW64, 32 B -> SW32).  Returns 0 on success.  The encoded map is cached in the handle (a model
 // replays the same few buffers every step, and cuTensorMapEncodeTiled costs microseconds of host time per call).
 int make_tensor_map_2d(srk_ctx* h, CUtensorMap* out, const void* gptr, uint64_t rows, uint32_t cols, uint32_t box_rows);
+
+// 3-D row-major tensor map [batch][rows][cols] of 2- or 4-byte elements with explicit strides (bytes, multiples of 16), box
+// {128 bytes of columns, box_rows, 1}, SWIZZLE_128B, zero fill out of bounds: the operand tiles of the generic GEMM.
+int make_tensor_map_3d(srk_ctx* h, CUtensorMap* out, const void* gptr, uint32_t elem_bytes, uint64_t rows, uint64_t cols, uint64_t batch,
+                       uint64_t row_stride_bytes, uint64_t batch_stride_bytes, uint32_t box_rows);
 
 // true exactly once per (handle, key): guards per-device one-time work such as cudaFuncSetAttribute or a __constant__ upload
 inline bool first_use(srk_ctx* h, const void* key) { return h->once.insert(key).second; }

@@ -1,6 +1,5 @@
-"""EnhanceNet generator on the B200 conv hot path -- drop-in for `build_generator` / `residual_block` of
-enet/enet/model_enet.py (the discriminator / VGG / texture losses of `build_enet` are outside the hot path,
-SURVEY section 2.1 #10-11).
+"""EnhanceNet on the B200 conv hot path -- drop-in for enet/enet/model_enet.py: `build_generator` / `residual_block` (below) and
+`build_enet` with the discriminator / VGG-19 perceptual / texture-matching losses (`losses.py`).
 
   conv2d            3x3 3->64 ReLU                      srk_conv_first_tc                    reference :63-70
   10 x residual     3x3 64->64 ReLU ; 1x1 64->64 ;      srk_conv_tc ; srk_conv_tc(k=1) with  reference :8-31
@@ -241,3 +240,113 @@ def build_generator(sd_images, bq_images, hd_images=None, scope_name="g_", param
     """enet/enet/model_enet.py:44 `build_generator(sd_images, bq_images, hd_images, scope_name)` -> sr_images handle."""
     net = EnetGenerator(params, scope_name, device, seed)
     return Handle(_EnetGraph(net, sd_images, bq_images), "sr_images")
+
+
+# ---------------------------------------------------------------------------------------------
+# build_enet: generator + the training losses (enet/enet/model_enet.py:264-348)
+# ---------------------------------------------------------------------------------------------
+
+
+class EnetPat:
+    """ENet-P / -PA / -PAT training state: generator, discriminator, constant VGG-19, and one training step
+    (`g_trainer` = Adam(1e-4) on g_losses w.r.t. the generator, `d_trainer` = Adam(1e-4) on a_loss w.r.t. the discriminator)."""
+
+    def __init__(self, pat_model="pat", vgg_weights=None, params=None, d_params=None, hd_size=128, device="cuda", seed=0):
+        from . import losses as L
+        self.pat = pat_model
+        self.gen = EnetGenerator(params, "g_", device, seed)
+        self.vgg = L.Vgg19(vgg_weights if vgg_weights is not None else L.vgg19_random_weights(seed), device)
+        self.disc = L.Discriminator(hd_size, d_params, "d_", device, seed + 1) if "a" in pat_model else None
+        self.device = device
+        self.step = 0
+        self.last = {}
+
+    def losses_and_dsr(self, sr: torch.Tensor, hd: torch.Tensor) -> torch.Tensor:
+        """The loss section of build_enet (:288-322) on the device: fills `self.last` with device scalars p_loss / g_loss /
+        t_loss / g_loss_all and returns d(g_losses)/d(sr)."""
+        from . import losses as L
+        from .. import nn
+        z = lambda: torch.zeros(1, dtype=torch.float32, device=sr.device)  # noqa: E731
+        p_loss, g_loss, t_loss = z(), z(), z()
+        hd_acts, sr_acts = self.vgg.forward(hd), self.vgg.forward(sr)
+        taps = L.perceptual_loss(self.vgg, sr_acts, hd_acts, p_loss)
+        if "t" in self.pat:
+            taps.update(L.texture_matching_loss(sr_acts, hd_acts, t_loss))
+        dsr = torch.zeros_like(sr)
+        self.vgg.backward(sr_acts, taps, dsr, accumulate=False)
+        if "a" in self.pat:
+            scale = 2.0 if "t" in self.pat else 1.0
+            g_scaled = z()
+            nn.axpby(self.disc.generator_loss(sr, g_scaled, scale), dsr, 1.0, 1.0)
+            nn.axpby(g_scaled, g_loss, 1.0 / scale, 0.0)
+        total = z()
+        nn.axpby(p_loss, total, 1.0, 0.0)
+        if "a" in self.pat:
+            nn.axpby(g_loss, total, 2.0 if "t" in self.pat else 1.0, 1.0)
+        if "t" in self.pat:
+            nn.axpby(t_loss, total, 1.0, 1.0)
+        self.last = {"p_loss": p_loss, "g_loss": g_loss, "t_loss": t_loss, "g_loss_all": total}
+        return dsr
+
+    def train_step(self, sd, bq, hd, g_train=True, d_train=True, learning_rate=1e-4):
+        """One `session.run({g_trainer, d_trainer, losses})` (enet/enet/experiment_train.py): both trainers use the generator output
+        computed with the weights from before the step, as TF evaluates them in one graph run."""
+        gen = self.gen
+        sr = gen.forward_backward(sd, bq, lambda s: self.losses_and_dsr(s, hd))
+        if self.disc is not None:
+            a_loss = torch.zeros(1, dtype=torch.float32, device=sr.device)
+            self.disc.discriminator_loss_and_grads(sr, hd, a_loss)
+            self.last["a_loss"] = a_loss
+            if d_train:
+                self.disc.adam_step(learning_rate)
+        if g_train:
+            a = gen.arena
+            self.step += 1
+            ops.adam_step(a.w, a.g, a.m, a.v, learning_rate, self.step)
+            gen._tb["plan"].run(a.w)
+            gen.repack()
+        return sr
+
+
+class _EnetPatGraph:
+    def __init__(self, trainer: EnetPat, sd_ph, bq_ph, hd_ph):
+        self.t, self.sd_ph, self.bq_ph, self.hd_ph = trainer, sd_ph, bq_ph, hd_ph
+
+    def execute(self, keys, feeds):
+        t = self.t
+        if keys == {"step"}:
+            return {"step": t.step}
+        dev = t.device
+        to = lambda x: (x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))).to(dev).contiguous()  # noqa: E731
+        sd, bq = to(feeds[self.sd_ph]), to(feeds[self.bq_ph])
+        out = {"step": t.step}
+        if keys <= {"sr_images", "step"}:
+            out["sr_images"] = t.gen.forward(sd, bq).cpu().numpy()
+            return out
+        hd = to(feeds[self.hd_ph])
+        sr = t.train_step(sd, bq, hd, g_train="g_trainer" in keys, d_train="d_trainer" in keys)
+        out.update(g_trainer=None, d_trainer=None, sr_images=sr.cpu().numpy() if "sr_images" in keys else None)
+        for k, v in t.last.items():
+            out[k] = float(v)
+        return out
+
+
+def build_enet(sd_images, bq_images, hd_images, pat_model, vgg19_path, params=None, d_params=None, hd_size=128, device="cuda", seed=0):
+    """enet/enet/model_enet.py:264 `build_enet(sd_images, bq_images, hd_images, pat_model, vgg19_path)` -> the same dict keys
+    (`sd_images, bq_images, sr_images [, hd_images, step, p_loss, g_loss_all, g_trainer, a_loss, g_loss, d_trainer, t_loss]`).
+    `vgg19_path`: the keras VGG-19 weights as `.npz` (`<layer>_W_1:0`, `<layer>_b_1:0`); None = random stand-in weights."""
+    from . import losses as L
+    trainer = EnetPat(pat_model, L.load_vgg_weights(vgg19_path) if vgg19_path else None, params, d_params, hd_size, device, seed)
+    g = _EnetPatGraph(trainer, sd_images, bq_images, hd_images)
+    model = {"sd_images": sd_images, "bq_images": bq_images, "sr_images": Handle(g, "sr_images")}
+    if hd_images is None:
+        return model
+    model["hd_images"] = hd_images
+    for k in ("step", "p_loss", "g_loss_all", "g_trainer"):
+        model[k] = Handle(g, k)
+    if "a" in pat_model:
+        for k in ("a_loss", "g_loss", "d_trainer"):
+            model[k] = Handle(g, k)
+    if "t" in pat_model:
+        model["t_loss"] = Handle(g, "t_loss")
+    return model

@@ -45,6 +45,14 @@ def _ptr(t: torch.Tensor | None) -> C.c_void_p:
     return C.c_void_p(t.data_ptr())
 
 
+def _ptr_any(t: torch.Tensor | None) -> C.c_void_p:
+    """Device pointer of a tensor or a strided VIEW of one (the callee is given the strides explicitly)."""
+    if t is None:
+        return C.c_void_p(0)
+    assert t.is_cuda
+    return C.c_void_p(t.data_ptr())
+
+
 def _f32(t: torch.Tensor) -> torch.Tensor:
     assert t.dtype == torch.float32, t.dtype
     return t
