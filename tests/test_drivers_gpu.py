@@ -63,3 +63,22 @@ def test_srcnn_main_trains_from_jpegs(tmp_path):
     _run("ml_super_resolution_b200.srcnn.srcnn", "--train", f"--training-images-path={data}", f"--ckpt-dir-path={ckpt}", f"--logs-dir-path={logs}",
          "--batch-size=4", "--crop-image-size=66", "--stop_training_at_k_step=2")
     assert os.path.exists(os.path.join(ckpt, "model.ckpt-2.npz"))
+
+
+def test_enet_train_and_resolve(tmp_path):
+    data, ckpt, logs = str(tmp_path / "data"), str(tmp_path / "ckpt"), str(tmp_path / "logs")
+    _images(data, n=2, size=256)
+    _run("ml_super_resolution_b200.enet.experiment_train", f"--train_dir_path={data}", f"--ckpt_path={ckpt}", f"--log_path={logs}", "--model=pat",
+         "--batch_size=2", "--stop_training_at_k_step=2")
+    ck = os.path.join(ckpt, "model.ckpt-2.npz")
+    assert os.path.exists(ck)
+    keys = np.load(ck).files
+    assert any(k.startswith("g_/") for k in keys) and any(k.startswith("d_/") for k in keys)
+    small = str(tmp_path / "small")
+    _images(small, n=1, size=40)
+    gen = str(tmp_path / "gen.npz")
+    _run("ml_super_resolution_b200.enet.experiment_resolve", "--extract_model", f"--source_ckpt_path={ck}", f"--target_ckpt_path={gen}")
+    out = str(tmp_path / "out")
+    _run("ml_super_resolution_b200.enet.experiment_resolve", f"--graph_define_path={gen}", f"--source_dir_path={small}", f"--target_dir_path={out}")
+    from PIL import Image
+    assert Image.open(os.path.join(out, "im0_sr.png")).size == (160, 160) and os.path.exists(os.path.join(out, "im0_bq.png"))
