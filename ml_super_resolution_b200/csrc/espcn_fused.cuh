@@ -89,16 +89,28 @@ struct alignas(64) EspcnFusedParams {
 template <int C, int R, bool SHUF>
 struct EspcnCfg {
   static constexpr int kCout = C * R * R;
-  static constexpr int kSets = (kCout > 32) ? 2 : (C == 3 ? 3 : SRK_EF_SETS);  // epilogue sets (4 quadrant warps each) taking virtual rows round-robin
+  static constexpr int kSets = (C == 1) ? 4 : ((kCout > 32) ? 2 : 3);  // epilogue sets (4 quadrant warps each) taking virtual rows round-robin
   static constexpr int NP3 = (kCout + 15) / 16 * 16;
   static constexpr int kRows = SHUF ? R : 1;          // output rows per LR row
   static constexpr int kRC = kCout / kRows;           // output elements per LR pixel per output row
   static constexpr int kK1 = 25 * C;                  // im2col depth; K slot kK1 carries the bias
   static constexpr int kK1Steps = (kK1 + 1 + 15) / 16;
   static constexpr int kB1 = (kK1 + 1 + 63) / 64;
+  // Y-channel form (C == 1, the BASELINE configuration): f2 and f3 read their A operands (a1, a2) from SHARED memory (SS mode)
+  // so that the horizontal taps are row-shifted operand descriptors instead of a lane-shift in the epilogue, and stack the
+  // three VERTICAL taps along N into a rotating window of three accumulators (see MMA2 below); the biases are one more MMA
+  // each.  The epilogues shrink to load / tanh / pack / store and get DEDICATED warps per stage (two EPI1 sets alternating
+  // rows, four EPI2 warps, four EPI3 warps), because a rotating window is single-buffered: the next row's MMAs start when the
+  // finished row has been read out, so the read-out must not queue behind other work.  RGB keeps the TS-mode form (its im2col
+  // tile and transpose buffers leave no room for the a1 / a2 rings).
+  static constexpr bool kSS = (C == 1);
+  static constexpr int kND1 = kSS ? 2 : 1;           // D1 accumulators
+  static constexpr int kNA1S = 3, kNA2S = 3;         // a1 / a2 ring slots in shared memory (kSS)
+  static constexpr int kA1Bytes = 128 * 128, kA2Bytes = 128 * 64;
   static constexpr int kW1Bytes = kB1 * 64 * 128;
-  static constexpr int kW2Bytes = 9 * 32 * 128;
-  static constexpr int kW3Bytes = 9 * NP3 * 64;
+  static constexpr int kW2Blocks = kSS ? 15 : 9;     // kSS: per dx the blocks [dy2 dy1 dy0 dy2 dy1] (every rotation is a window of 3)
+  static constexpr int kW2Bytes = kW2Blocks * 32 * 128;
+  static constexpr int kW3Bytes = kW2Blocks * NP3 * 64;
   static constexpr int kAS = 2;                       // im2col stages
   static constexpr int kABytes = kB1 * 128 * 128;
   static constexpr int kInElems = 132 * C;            // one input row of the strip: x = 120*s - 6 .. 120*s + 125
@@ -106,13 +118,14 @@ struct EspcnCfg {
   static constexpr int kInSlots = (C == 1) ? 32 : 20, kPrefetch = (C == 1) ? 12 : 10;  // input ring: 5 rows in use + 12 in flight + 5 (segment jump) < 32
   // tensor memory columns
   static constexpr int kN2 = 96, kN3 = 3 * NP3;
-  static constexpr int kND2 = (NP3 <= 32) ? 2 : 1;
-  static constexpr int kNA1 = (NP3 == 32) ? 3 : 4;
+  static constexpr int kND2 = kSS ? 1 : ((NP3 <= 32) ? 2 : 1);
+  static constexpr int kNA1 = kSS ? 0 : ((NP3 == 32) ? 3 : 4);
   static constexpr int kColD1 = 0;
-  static constexpr int kColA1 = 64;
+  static constexpr int kColA1 = 64 * kND1;
   static constexpr int kColD2 = kColA1 + kNA1 * 32;
   static constexpr int kColA2 = kColD2 + kND2 * kN2;
-  static constexpr int kColD3 = kColA2 + 4 * 16;
+  static_assert(!kSS || (kK1 + 1 <= 32 && NP3 == 16), "kSS: the bias K-steps of the first-layer tiles must be free; 1 KB weight blocks");
+  static constexpr int kColD3 = kColA2 + (kSS ? 0 : 4 * 16);
   static_assert(kColD3 + kN3 <= 512, "tensor memory plan does not fit");
   // shared memory
   static constexpr int kTBufBytes = 32 * kCout * 4;   // per EPI3 warp: its 32 pixels' outputs in OUTPUT order [row][pixel*kRC + e]
@@ -121,13 +134,15 @@ struct EspcnCfg {
   static constexpr int kOffW2 = kOffW1 + kW1Bytes;
   static constexpr int kOffW3 = kOffW2 + kW2Bytes;
   static constexpr int kOffA = (kOffW3 + kW3Bytes + 1023) / 1024 * 1024;
-  static constexpr int kOffIn = kOffA + kAS * kABytes;
+  static constexpr int kOffA1 = kOffA + kAS * kABytes;  // 1024-aligned (kABytes is a multiple of 16 KB); rows -1 / 128 of a slot are its neighbours' memory
+  static constexpr int kOffA2 = kOffA1 + (kSS ? kNA1S * kA1Bytes : 0);
+  static constexpr int kOffIn = kOffA2 + (kSS ? kNA2S * kA2Bytes : 0);
   static constexpr int kOffTBuf = kOffIn + kInSlots * kInRowBytes;
-  static constexpr int kOffXch = kOffTBuf + 4 * kSets * kTBufBytes;    // one lane-exchange area per epilogue set
+  static constexpr int kOffXch = kOffTBuf + 4 * (kSS ? 1 : kSets) * kTBufBytes;    // one lane-exchange area per epilogue set
   static constexpr int kOffBias = kOffXch + kSets * kXchBytes;     // b2[32] b3[NP3]
   static constexpr int kOffTab = kOffBias + (32 + NP3) * 4;   // segment table
   static constexpr int kOffBars = (kOffTab + kEfTabInts * 4 + 7) / 8 * 8;
-  static constexpr int kNumBars = 1 + kAS + 4 + 2 + 4 + 2 + 4;
+  static constexpr int kNumBars = 1 + kAS + 4 + 4 + 4 + 4 + 4;
   static constexpr int kOffTmemSlot = kOffBars + kNumBars * 8;
   static constexpr int kUsed = kOffTmemSlot + 16 + 1024;
   static constexpr int kTotal = kUsed < 120 * 1024 ? 120 * 1024 : kUsed;  // > half an SM's shared memory: one CTA (one 512-column TMEM owner) per SM
@@ -270,7 +285,7 @@ __global__ void __launch_bounds__(EspcnCfg<C, R, SHUF>::kThreads, 1) espcn_fused
   const uint32_t s_base = smem_u32(smem);
   int* const s_tab = reinterpret_cast<int*>(smem + L::kOffTab);
   const uint32_t s_w1 = s_base + L::kOffW1, s_w2 = s_base + L::kOffW2, s_w3 = s_base + L::kOffW3;
-  const uint32_t s_a = s_base + L::kOffA, s_in = s_base + L::kOffIn;
+  const uint32_t s_a = s_base + L::kOffA, s_a1 = s_base + L::kOffA1, s_a2 = s_base + L::kOffA2, s_in = s_base + L::kOffIn;
   float* s_bias = reinterpret_cast<float*>(smem + L::kOffBias);
   const uint32_t s_bars = s_base + L::kOffBars;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmemSlot);
@@ -279,10 +294,10 @@ __global__ void __launch_bounds__(EspcnCfg<C, R, SHUF>::kThreads, 1) espcn_fused
   // Commit barriers are rings of FOUR indexed by v & 3: a waiter for row v must know that the ring slot's previous phase (row
   // v - 4) is complete, or its parity test passes early; every waiter's preceding wait was for a row >= v - S, S <= 4.
   auto C1 = [&](int i) { return s_bars + 8u * (1 + AS + i); };
-  auto G2 = [&](int i) { return s_bars + 8u * (1 + AS + 4 + i); };
-  auto C2 = [&](int i) { return s_bars + 8u * (1 + AS + 6 + i); };
-  auto G3 = [&](int i) { return s_bars + 8u * (1 + AS + 10 + i); };
-  auto C3 = [&](int i) { return s_bars + 8u * (1 + AS + 12 + i); };
+  auto G2 = [&](int i) { return s_bars + 8u * (1 + AS + 4 + i); };  // two in use (TS form) or four (kSS: EPI1 runs up to three rows ahead of MMA2)
+  auto C2 = [&](int i) { return s_bars + 8u * (1 + AS + 8 + i); };
+  auto G3 = [&](int i) { return s_bars + 8u * (1 + AS + 12 + i); };  // likewise two or four
+  auto C3 = [&](int i) { return s_bars + 8u * (1 + AS + 16 + i); };
   static_assert(L::kSets <= 4, "commit-barrier rings hold four phases");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -293,10 +308,8 @@ __global__ void __launch_bounds__(EspcnCfg<C, R, SHUF>::kThreads, 1) espcn_fused
     for (int i = 0; i < AS; ++i) {
       mbar_init(G1(i), 4 + 4);  // one arrival per warp (every arrival wakes every sleeping waiter of the CTA): gather + one epilogue set
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(G2(i), 4 + 4);  // EPI1 of one set + EPI2 (drain) of a set
-      mbar_init(G3(i), 4 + 4);  // EPI2 + EPI3 (drain)
-    }
+    for (int i = 0; i < 4; ++i) mbar_init(G2(i), 4 + 4);  // EPI1 of one set + EPI2 (drain) of a set
+    for (int i = 0; i < 4; ++i) mbar_init(G3(i), 4 + 4);  // EPI2 + EPI3 (drain)
     for (int i = 0; i < 4; ++i) {
       mbar_init(C1(i), 1);
       mbar_init(C2(i), 1);
@@ -328,8 +341,18 @@ __global__ void __launch_bounds__(EspcnCfg<C, R, SHUF>::kThreads, 1) espcn_fused
       if (lane == 0) {
         mbar_arrive_expect_tx(bar_w, L::kW1Bytes + L::kW2Bytes + L::kW3Bytes);
         for (int b = 0; b < L::kB1; ++b) tma_load_2d(s_w1 + b * 8192, &p.map_w1, 0, b * 64, bar_w);
-        for (int t = 0; t < 9; ++t) tma_load_2d(s_w2 + t * 4096, &p.map_w2, 0, t * 32, bar_w);
-        for (int t = 0; t < 9; ++t) tma_load_2d(s_w3 + t * NP3 * 64, &p.map_w3, 0, t * NP3, bar_w);
+        if constexpr (L::kSS) {
+          for (int dx = 0; dx < 3; ++dx)
+            for (int j = 0; j < 5; ++j) tma_load_2d(s_w2 + (dx * 5 + j) * 4096, &p.map_w2, 0, (((j < 3) ? 2 - j : 5 - j) * 3 + dx) * 32, bar_w);
+        } else {
+          for (int t = 0; t < 9; ++t) tma_load_2d(s_w2 + t * 4096, &p.map_w2, 0, t * 32, bar_w);
+        }
+        if constexpr (L::kSS) {
+          for (int dx = 0; dx < 3; ++dx)
+            for (int j = 0; j < 5; ++j) tma_load_2d(s_w3 + (dx * 5 + j) * NP3 * 64, &p.map_w3, 0, (((j < 3) ? 2 - j : 5 - j) * 3 + dx) * NP3, bar_w);
+        } else {
+          for (int t = 0; t < 9; ++t) tma_load_2d(s_w3 + t * NP3 * 64, &p.map_w3, 0, t * NP3, bar_w);
+        }
       }
 #ifdef SRK_TRACE
       // timeline only: lanes 0..2 watch the commit barriers of the three MMA stages and record when each row's MMAs completed
@@ -353,6 +376,22 @@ __global__ void __launch_bounds__(EspcnCfg<C, R, SHUF>::kThreads, 1) espcn_fused
           const __nv_bfloat16 bv = __float2bfloat16_rn(p.b1[co]);
           *reinterpret_cast<__nv_bfloat16*>(smem + L::kOffW1 + kb * 8192 + co * 128 + (((kk / 8) ^ (co & 7)) << 4) + (kk % 8) * 2) = bv;
         }
+        if constexpr (L::kSS) {
+          // f2's bias is one more MMA (K-step 2 of these tiles: A = the im2col tile's constant columns 32, 33 = 1, B = rows
+          // n < 32 of this tile with b2[n] split into bf16 high and low parts at columns 32, 33: exact to 2^-17)
+          const float b = p.b2[lane];
+          const __nv_bfloat16 bh = __float2bfloat16_rn(b), bl = __float2bfloat16_rn(b - __bfloat162float(bh));
+          __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(smem + L::kOffW1 + lane * 128 + ((4 ^ (lane & 7)) << 4));
+          d[0] = bh;
+          d[1] = bl;
+          if (lane < NP3) {  // f3's bias likewise: K-step 3, columns 48, 49, rows n < NP3
+            const float b3v = lane < COUT ? p.b3[lane] : 0.f;
+            const __nv_bfloat16 ch = __float2bfloat16_rn(b3v), cl = __float2bfloat16_rn(b3v - __bfloat162float(ch));
+            __nv_bfloat16* d3 = reinterpret_cast<__nv_bfloat16*>(smem + L::kOffW1 + lane * 128 + ((6 ^ (lane & 7)) << 4));
+            d3[0] = ch;
+            d3[1] = cl;
+          }
+        }
         fence_proxy_async_smem();
         __syncwarp();
       }
@@ -367,7 +406,7 @@ __global__ void __launch_bounds__(EspcnCfg<C, R, SHUF>::kThreads, 1) espcn_fused
           for (int k = 0; k < L::kK1Steps; ++k) {
             const uint32_t a_addr = s_a + st * L::kABytes + (k / 4) * (128 * 128) + (k % 4) * 32;
             const uint32_t b_addr = s_w1 + (k / 4) * (64 * 128) + (k % 4) * 32;
-            umma_bf16(tmem + L::kColD1, umma_desc(hi, a_addr), umma_desc(hi, b_addr), idesc, k != 0);
+            umma_bf16(tmem + L::kColD1 + (v % L::kND1) * 64, umma_desc(hi, a_addr), umma_desc(hi, b_addr), idesc, k != 0);
           }
           umma_commit(C1(v & 3));
         }
@@ -379,45 +418,110 @@ __global__ void __launch_bounds__(EspcnCfg<C, R, SHUF>::kThreads, 1) espcn_fused
       constexpr uint32_t idesc = umma_idesc_bf16(128, L::kN2, 0, 0);
       constexpr uint64_t hi = umma_desc_hi(0, 1024, UMMA_LAYOUT_SW128);
       mbar_wait(bar_w, 0);
+      if constexpr (L::kSS) {
+        // Row u of a1 (shared memory, SW128 K-major, one 128-byte row per lane) feeds the three output rows v = u, u+1, u+2
+        // (vertical tap dy = u + 2 - v).  Their accumulators are the three 32-column slots of ONE 96-column window, row v in
+        // slot v % 3, so a single N = 96 instruction per (dx, K-step) serves all three; which tap each slot needs rotates
+        // with u % 3, and the weight blocks are stored [dy2 dy1 dy0 dy2 dy1] so that every rotation is a contiguous window.
+        // The horizontal tap dx is a ROW-SHIFTED A descriptor (start address -/+ 128 bytes: lane j reads pixel j + dx - 1;
+        // the two rows beyond the slot are neighbouring memory and only reach the discarded apron lanes 0 and 127).
+        // Row u+2 is opened by the bias instruction (accumulate off), closed by row u+2's own instructions.
+        constexpr uint32_t idesc32 = umma_idesc_bf16(128, 32, 0, 0);
+        int m3 = 0, sl = 0;  // v % 3, v % kNA1S
 #pragma unroll 1
-      for (int v = 0; v < V; ++v) {
-        mbar_wait(G2(v & 1), (v >> 1) & 1);
-        tc_fence_after();
-        if (lane == 0) EF_EV(9, v);
-        const uint32_t d = tmem + L::kColD2 + (v % ND2) * L::kN2;
-        if (elect_one()) {
+        for (int v = 0; v < V; ++v) {
+          mbar_wait(G2(v & 3), (v >> 2) & 1);
+          tc_fence_after();
+          if (lane == 0) EF_EV(9, v);
+          const uint32_t a0 = s_a1 + sl * L::kA1Bytes - 128;
+          const uint32_t b0 = s_w2 + ((2 * m3) % 3) * 4096;
+          const uint32_t dinit = tmem + L::kColD2 + ((m3 + 2) % 3) * 32;
+          if (elect_one()) {
+            umma_bf16(dinit, umma_desc(hi, s_a + 64), umma_desc(hi, s_w1 + 64), idesc32, 0);
 #pragma unroll
-          for (int dy = 0; dy < 3; ++dy) {
-            const uint32_t a = tmem + L::kColA1 + ((v + dy + 2 * NA1 - 2) % NA1) * 32;
+            for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16_ts(d, a + k * 8, umma_desc(hi, s_w2 + dy * 3 * 4096 + k * 32), idesc, (dy | k) != 0);
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem + L::kColD2, umma_desc(hi, a0 + dx * 128 + k * 32), umma_desc(hi, b0 + dx * 5 * 4096 + k * 32), idesc, 1);
+            }
+            umma_commit(C2(v & 3));
           }
-          umma_commit(C2(v & 3));
+          __syncwarp();
+          if (lane == 0) EF_EV(10, v);
+          m3 = (m3 == 2) ? 0 : m3 + 1;
+          sl = (sl == L::kNA1S - 1) ? 0 : sl + 1;
         }
-        __syncwarp();
-        if (lane == 0) EF_EV(10, v);
+      } else {
+#pragma unroll 1
+        for (int v = 0; v < V; ++v) {
+          mbar_wait(G2(v & 1), (v >> 1) & 1);
+          tc_fence_after();
+          if (lane == 0) EF_EV(9, v);
+          const uint32_t d = tmem + L::kColD2 + (v % ND2) * L::kN2;
+          if (elect_one()) {
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+              const uint32_t a = tmem + L::kColA1 + ((v + dy + 2 * NA1 - 2) % NA1) * 32;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16_ts(d, a + k * 8, umma_desc(hi, s_w2 + dy * 3 * 4096 + k * 32), idesc, (dy | k) != 0);
+            }
+            umma_commit(C2(v & 3));
+          }
+          __syncwarp();
+          if (lane == 0) EF_EV(10, v);
+        }
       }
     } else if (warp == W0 + 6) {
       // ---------------------------------------------------------------- MMA3: out accumulator = sum_dy a2[v-2+dy] (TMEM) x W3 row dy
       constexpr uint32_t idesc = umma_idesc_bf16(128, L::kN3, 0, 0);
       constexpr uint64_t hi = umma_desc_hi(0, 512, UMMA_LAYOUT_SW64);
       mbar_wait(bar_w, 0);
+      if constexpr (L::kSS) {
+        // as MMA2: a2 rows in shared memory (SW64 K-major, 64-byte rows), window of three NP3-column accumulators, bias instruction
+        constexpr uint32_t idesc16 = umma_idesc_bf16(128, NP3, 0, 0);
+        constexpr uint64_t hi128 = umma_desc_hi(0, 1024, UMMA_LAYOUT_SW128);
+        int m3 = 0, sl = 0;
 #pragma unroll 1
-      for (int v = 0; v < V; ++v) {
-        mbar_wait(G3(v & 1), (v >> 1) & 1);
-        tc_fence_after();
-        if (lane == 0) EF_EV(15, v);
-        if (elect_one()) {
+        for (int v = 0; v < V; ++v) {
+          mbar_wait(G3(v & 3), (v >> 2) & 1);
+          tc_fence_after();
+          if (lane == 0) EF_EV(15, v);
+          const uint32_t a0 = s_a2 + sl * L::kA2Bytes - 64;
+          const uint32_t b0 = s_w3 + ((2 * m3) % 3) * (NP3 * 64);
+          const uint32_t dinit = tmem + L::kColD3 + ((m3 + 2) % 3) * NP3;
+          if (elect_one()) {
+            umma_bf16(dinit, umma_desc(hi128, s_a + 96), umma_desc(hi128, s_w1 + 96), idesc16, 0);
 #pragma unroll
-          for (int dy = 0; dy < 3; ++dy) {
-            const uint32_t a = tmem + L::kColA2 + ((v + dy + 2) & 3) * 16;
+            for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
-            for (int k = 0; k < 2; ++k) umma_bf16_ts(tmem + L::kColD3, a + k * 8, umma_desc(hi, s_w3 + dy * 3 * NP3 * 64 + k * 32), idesc, (dy | k) != 0);
+              for (int k = 0; k < 2; ++k)
+                umma_bf16(tmem + L::kColD3, umma_desc(hi, a0 + dx * 64 + k * 32), umma_desc(hi, b0 + dx * 5 * NP3 * 64 + k * 32), idesc, 1);
+            }
+            umma_commit(C3(v & 3));
           }
-          umma_commit(C3(v & 3));
+          __syncwarp();
+          if (lane == 0) EF_EV(16, v);
+          m3 = (m3 == 2) ? 0 : m3 + 1;
+          sl = (sl == L::kNA2S - 1) ? 0 : sl + 1;
         }
-        __syncwarp();
-        if (lane == 0) EF_EV(16, v);
+      } else {
+#pragma unroll 1
+        for (int v = 0; v < V; ++v) {
+          mbar_wait(G3(v & 1), (v >> 1) & 1);
+          tc_fence_after();
+          if (lane == 0) EF_EV(15, v);
+          if (elect_one()) {
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+              const uint32_t a = tmem + L::kColA2 + ((v + dy + 2) & 3) * 16;
+#pragma unroll
+              for (int k = 0; k < 2; ++k) umma_bf16_ts(tmem + L::kColD3, a + k * 8, umma_desc(hi, s_w3 + dy * 3 * NP3 * 64 + k * 32), idesc, (dy | k) != 0);
+            }
+            umma_commit(C3(v & 3));
+          }
+          __syncwarp();
+          if (lane == 0) EF_EV(16, v);
+        }
       }
     } else if (warp >= W0 && warp < W0 + 4) {
       // ---------------------------------------------------------------- gather: cp.async input ring -> im2col rows of A (bf16, SW128)
@@ -451,6 +555,17 @@ __global__ void __launch_bounds__(EspcnCfg<C, R, SHUF>::kThreads, 1) espcn_fused
       // by at most 9 over five steps (one row per step, five at a segment start, segments last >= 5 steps), so the rows step v
       // reads were committed by step v-6 at the latest: wait_group<5> + the group barrier makes them visible.
       static_assert(L::kPrefetch >= 9 && L::kInSlots >= L::kPrefetch + 10, "input ring look-ahead");
+      if constexpr (L::kSS) {
+        // constant columns of the im2col tiles (K-steps 2, 3; the gather only ever writes K-steps 0, 1): A[.][32] = A[.][33] = 1
+        // is the A operand of the bias instructions (bf16 high + low part of the bias in the B rows)
+        for (int st = 0; st < AS; ++st) {
+          const uint32_t arow = s_a + st * L::kABytes + gt * 128;
+          ef_sts128u(arow + ((4 ^ (gt & 7)) << 4), 0x3F803F80u, 0u, 0u, 0u);
+          ef_sts128u(arow + ((5 ^ (gt & 7)) << 4), 0u, 0u, 0u, 0u);
+          ef_sts128u(arow + ((6 ^ (gt & 7)) << 4), 0x3F803F80u, 0u, 0u, 0u);
+          ef_sts128u(arow + ((7 ^ (gt & 7)) << 4), 0u, 0u, 0u, 0u);
+        }
+      }
       for (int i = 0; i < 5 + L::kPrefetch && issued < total_in; ++i) issue_row();
       cp_async_commit();
       for (int i = 0; i < 5; ++i) cp_async_commit();  // (empty groups: uniform accounting from step 0 on)
@@ -492,6 +607,165 @@ __global__ void __launch_bounds__(EspcnCfg<C, R, SHUF>::kThreads, 1) espcn_fused
       }
       cp_async_wait<0>();
     } else if (warp < W0) {
+      if constexpr (L::kSS) {
+        // ---------------------------------------------------------------- epilogues of the Y-channel form: dedicated warps per stage
+        constexpr int RC = L::kRC, ROWS = L::kRows;
+        constexpr int kVec = 8 * RC;                    // 16-byte groups per output row of this warp's 32 pixels
+        constexpr int kIter = (kVec + 31) / 32;
+        const int quad = warp & 3, grp = warp >> 2, gl = quad * 32 + lane;
+        const uint32_t lane_addr = uint32_t(quad * 32) << 16;
+        const bool tr = (quad == 0 && lane == 0);  // the thread that records the timeline
+        EfSeg w;
+        ef_seg_load(w, s_tab, 0);
+        if (grp < 2) {
+          // ============================================================== EPI1 (two sets, rows v = grp, grp + 2, ...):
+          // a1 = tanh(D1) -> bf16 -> shared-memory ring (SW128 K-major: lane = tile row, eight 16-byte chunks of eight channels)
+          if (lane == 0) mbar_arrive(G1(grp));  // stands in for EPI1(grp - 2): both D1 accumulators start out drained
+          int sl = grp % L::kNA1S;
+#pragma unroll 1
+          for (int v = grp; v < V; v += 2) {
+            ef_seg_seek(w, s_tab, v);
+            const int x = w.s * kEfStripW - kEfLane0 + gl, y = w.ya - 2 + (v - w.v0);
+            const bool valid = (x >= 0) && (x < p.W) && (y >= 0) && (y < p.H);
+            mbar_wait(C1(v & 3), (v >> 2) & 1);
+            tc_fence_after();
+            if (tr) EF_EV(5, v);
+            if (v >= L::kNA1S) {  // the slot's previous row was read by MMA2(v - kNA1S)
+              const int vv = v - L::kNA1S;
+              mbar_wait(C2(vv & 3), (vv >> 2) & 1);
+            }
+            if (tr) EF_EV(7, v);
+            const bool all_valid = __all_sync(0xffffffffu, valid);
+            const uint32_t dst = s_a1 + sl * L::kA1Bytes + gl * 128;
+            const uint32_t src = tmem + L::kColD1 + (v & 1) * 64 + lane_addr;
+#pragma unroll 1
+            for (int hf = 0; hf < 2; ++hf) {  // (rolled: instruction-cache footprint)
+              uint32_t u[32], pk[16];
+              tmem_ld_32x32b_x32(src + hf * 32, u);
+              tmem_ld_wait();
+              if (hf == 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(G1(v & 1));  // D1 accumulator drained: MMA1(v + 2) may overwrite it
+                if (tr) EF_EV(6, v);
+              }
+#pragma unroll
+              for (int c = 0; c < 16; ++c) pk[c] = ef_pack(ef_tanh(__uint_as_float(u[2 * c])), ef_tanh(__uint_as_float(u[2 * c + 1])));
+              if (!all_valid) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) pk[c] = valid ? pk[c] : 0u;
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q) ef_sts128u(dst + (((hf * 4 + q) ^ (gl & 7)) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(G2(v & 3));  // a1[v] is in shared memory
+            if (tr) EF_EV(8, v);
+            sl = (sl + 2) % L::kNA1S;
+          }
+        } else if (grp == 2) {
+          // ============================================================== EPI2 (every row): the accumulator slot holds the nine
+          // taps + bias; a2 = tanh(.) -> bf16 -> shared-memory ring (SW64 K-major: 64-byte rows, four 16-byte chunks)
+          if (lane == 0) mbar_arrive(G2(0));  // stands in for EPI2(-1)
+          int m3 = 0, sl = 0;
+#pragma unroll 1
+          for (int v2 = 0; v2 < V; ++v2) {
+            ef_seg_seek(w, s_tab, v2);
+            const int j2 = v2 - w.v0;
+            const int x = w.s * kEfStripW - kEfLane0 + gl, y = w.ya - 3 + j2;
+            const bool valid = (j2 >= 2) && (x >= 0) && (x < p.W) && (y >= 0) && (y < p.H);
+            const bool all_valid = __all_sync(0xffffffffu, valid);
+            mbar_wait(C2(v2 & 3), (v2 >> 2) & 1);
+            tc_fence_after();
+            if (tr) EF_EV(11, v2);
+            uint32_t u[32], pk[16];
+            tmem_ld_32x32b_x32(tmem + L::kColD2 + m3 * 32 + lane_addr, u);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(G2((v2 + 1) & 3));  // slot read out: MMA2(v2 + 1) may open row v2 + 3 in it
+            if (tr) EF_EV(12, v2);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) pk[c] = ef_pack(ef_tanh(__uint_as_float(u[2 * c])), ef_tanh(__uint_as_float(u[2 * c + 1])));
+            if (!all_valid) {
+#pragma unroll
+              for (int c = 0; c < 16; ++c) pk[c] = valid ? pk[c] : 0u;
+            }
+            if (v2 >= L::kNA2S) {  // the slot's previous row was read by MMA3(v2 - kNA2S)
+              const int vv = v2 - L::kNA2S;
+              mbar_wait(C3(vv & 3), (vv >> 2) & 1);
+            }
+            if (tr) EF_EV(13, v2);
+            const uint32_t dst = s_a2 + sl * L::kA2Bytes + gl * 64;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ef_sts128u(dst + ((q ^ ((gl >> 1) & 3)) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(G3(v2 & 3));  // a2[v2] is in shared memory
+            if (tr) EF_EV(14, v2);
+            m3 = (m3 == 2) ? 0 : m3 + 1;
+            sl = (sl == L::kNA2S - 1) ? 0 : sl + 1;
+          }
+        } else {
+          // ============================================================== EPI3 (every row): out = accumulator slot (taps + bias)
+          // -> depth_to_space through a per-warp transpose tile -> global, 16-byte stores
+          if (lane == 0) mbar_arrive(G3(0));  // stands in for EPI3(-1)
+          float* const tb = reinterpret_cast<float*>(smem + L::kOffTBuf + quad * L::kTBufBytes);
+          const int64_t orow = int64_t(p.W) * RC;  // elements per output row
+          const bool vec_ok = (orow & 3) == 0;       // every warp segment starts on a 16-byte boundary
+          const bool u8 = p.out_kind == SRK_OUT_U8;
+          int m3 = 0;
+#pragma unroll 1
+          for (int v3 = 0; v3 < V; ++v3) {
+            mbar_wait(C3(v3 & 3), (v3 >> 2) & 1);
+            tc_fence_after();
+            if (tr) EF_EV(17, v3);
+            uint32_t u[16];
+            tmem_ld_32x32b_x16(tmem + L::kColD3 + m3 * NP3 + lane_addr, u);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(G3((v3 + 1) & 3));  // slot read out: MMA3(v3 + 1) may open row v3 + 3 in it
+            if (tr) EF_EV(18, v3);
+            m3 = (m3 == 2) ? 0 : m3 + 1;
+            ef_seg_seek(w, s_tab, v3);
+            const int j3 = v3 - w.v0;
+            if (j3 >= 4) {
+              // transpose tile in OUTPUT order: channel c = (dy*R + dx)*C + ch goes to output row dy, element pixel*RC + (dx*C + ch)
+#pragma unroll
+              for (int c = 0; c < COUT; ++c) tb[((c / RC) * 32 + lane) * RC + (c % RC)] = __uint_as_float(u[c]);
+              __syncwarp();
+              if (tr) EF_EV(19, v3);
+              // The warp's 32 pixels own, in each of the ROWS output rows, one contiguous run of 32*RC elements that starts on a
+              // 16-byte boundary (x of lane 0 is a multiple of 4): 16-byte stores, consecutive lanes on consecutive groups.
+              const int wvalid = min(kEfStripW, p.W - w.s * kEfStripW);
+              const int e_lo = max(0, kEfLane0 - quad * 32) * RC;                           // this warp's valid element range
+              const int e_hi = max(0, min(32, kEfLane0 + wvalid - quad * 32)) * RC;         // of a 32*RC-element row segment
+              const int64_t base = (int64_t(w.n) * p.H + (w.ya + j3 - 4)) * ROWS * orow + int64_t(w.s * kEfStripW - kEfLane0 + quad * 32) * RC;
+#pragma unroll
+              for (int dy = 0; dy < ROWS; ++dy) {
+#pragma unroll
+                for (int it = 0; it < kIter; ++it) {
+                  const int e = 4 * (lane + 32 * it);
+                  if (kVec % 32 == 0 || e < 4 * kVec) {
+                    const float4 val = *reinterpret_cast<const float4*>(tb + dy * 32 * RC + e);
+                    const int64_t idx = base + dy * orow + e;
+                    if (vec_ok && e >= e_lo && e + 4 <= e_hi) {
+                      if (u8) *reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(p.out) + idx) = ef_u8(val.x) | (ef_u8(val.y) << 8) | (ef_u8(val.z) << 16) | (ef_u8(val.w) << 24);
+                      else *reinterpret_cast<float4*>(static_cast<float*>(p.out) + idx) = val;
+                    } else if (e + 4 > e_lo && e < e_hi) {  // strip edge of a frame whose width is not a multiple of 4
+                      ef_store_partial(p.out, u8, idx, val, e_lo - e, e_hi - e);
+                    }
+                  }
+                }
+              }
+              __syncwarp();
+            }
+            if (tr) EF_EV(20, v3);
+          }
+        }
+      } else {
       // ---------------------------------------------------------------- epilogue: set `set` takes the virtual rows v = set, set+S, ...;
       // per iteration it drains the oldest stage first: EPI3(v-2S), EPI2(v-S), EPI1(v)
       constexpr int RC = L::kRC, ROWS = L::kRows;
@@ -685,6 +959,7 @@ __global__ void __launch_bounds__(EspcnCfg<C, R, SHUF>::kThreads, 1) espcn_fused
           if (lane == 0) mbar_arrive(G2(v & 1));
           if (tr) EF_EV(8, v);
         }
+      }
       }
     }
   }
