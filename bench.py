@@ -197,7 +197,7 @@ def espcn_workload(args, rank, world):
                 "traffic": ncu_traffic("espcn_fused_kernel", f"{FRAMES_PER_STEP}x{LR_H}x{LR_W}x{C} r{SCALE} f32"), "peak_source": pk["src"],
                 "algorithmic_flops": flops, "algorithmic_bytes": alg_bytes, "hbm_GBps": round(alg_bytes / k_ms / 1e6, 1),
                 "hbm_frac": round(alg_bytes / k_ms / 1e6 / pk["hbm"], 4),
-                "note": "co-limited by the tensor pipe (N <= 96 MMAs run at the 49-cycle instruction floor), MUFU.TANH (96 per pixel) and issue slots; DESIGN.md 3.6"}
+                "note": "bound by the UMMA operand fetch from shared memory (SS-mode N <= 96 instructions run at a 60-cycle floor; ncu l1tex__data_pipe_tc_wavefronts_mem_shared 75 %) plus the hand-over of the single-buffered rotating accumulator window; DESIGN.md 3.6"}
 
     # ---- the layer-by-layer path (three kernels through HBM, what round 1 shipped and what training uses), for comparison
     Ht, Wt, tiles = plan_tiles(FRAMES_PER_STEP, LR_H, LR_W, 4)
