@@ -1125,6 +1125,10 @@ extern "C" int srk_conv_tc(srk_handle_t h, const void* x_fpa, int cin_p, const v
   p.addend_fpa = static_cast<const __nv_bfloat16*>(addend_fpa);
   p.relu_after_add = relu_after_add;
   cudaStream_t s = as_stream(stream);
+  // wide frames: the column-strip form of the plain 3x3 64->64 layer (no lane shift in the epilogue, conv_strip.cu)
+  if (cin_p == 64 && cout_p == 64 && k == 3 && !mask_src && !addend_fpa && (act == SRK_ACT_NONE || act == SRK_ACT_RELU) &&
+      conv_strip_applicable(h, n_img, H, W))
+    return launch_conv_strip(h, x_fpa, w_packed, bias, act, n_img, H, W, y_fpa, s);
 #define SRK_CASE(CIN, NP, KS) \
   if (cin_p == CIN && cout_p == NP && k == KS) return launch_conv_tc<CIN, NP, KS, EPI_FPA>(h, p, x_fpa, w_packed, y_fpa, s);
   SRK_CASE(64, 64, 3)

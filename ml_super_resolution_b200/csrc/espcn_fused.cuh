@@ -44,6 +44,7 @@
 
 #include "sm100_ptx.cuh"
 #include "srk_common.cuh"
+#include "strip_walk.cuh"
 
 namespace srk {
 
@@ -65,8 +66,6 @@ static __device__ unsigned long long g_ef_trace[24 * 256];  // one copy per tran
 #define SRK_EF_SETS 4
 #endif
 
-constexpr int kEfMaxSegs = 64;            // strip segments one CTA can follow; the host splits a call so that no CTA sees more
-constexpr int kEfTabInts = 72 + 3 * 64;   // segment table: v0[0..64] (v0[nseg] = V), nseg at [71], then n[64], s[64], ya[64]
 constexpr int kEfStripW = 120;  // stored pixels per strip
 constexpr int kEfLane0 = 4;     // lane of the strip's first stored pixel (a multiple of 4 keeps warp segments 16-byte aligned)
 
@@ -183,44 +182,6 @@ __device__ __forceinline__ uint32_t ef_u8(float v) {  // tf.saturate_cast(v * 12
   return uint32_t(fminf(fmaxf(q, 0.f), 255.f));
 }
 
-// This CTA's virtual rows: its unit range [u0, u1) cut at strip boundaries into segments (frame n, strip s, rows [ya, ya+R)),
-// each R + 4 virtual rows long (the vertical apron) and R + 8 input rows long.  One thread tabulates the segments in shared
-// memory at kernel start (the only divisions of the kernel); every role then follows the table with a cursor held in registers.
-struct EfSeg {
-  int i, v0, v1, n, s, ya;  // segment index, its virtual rows [v0, v1), frame, strip, first image row
-};
-__device__ __forceinline__ void ef_seg_load(EfSeg& c, const int* tab, int i) {
-  c.i = i;
-  c.v0 = tab[i];
-  c.v1 = tab[i + 1];
-  c.n = tab[72 + i];
-  c.s = tab[72 + 64 + i];
-  c.ya = tab[72 + 128 + i];
-}
-// position the cursor on virtual row v (< V; v never decreases)
-__device__ __forceinline__ void ef_seg_seek(EfSeg& c, const int* tab, int v) {
-  while (v >= c.v1) ef_seg_load(c, tab, c.i + 1);
-}
-static __device__ __noinline__ void ef_build_segments(int* tab, uint32_t u0, uint32_t u1, int hb, int y0, int strips) {
-  int v = 0, i = 0;
-  while (u0 < u1 && i < kEfMaxSegs) {
-    const uint32_t qq = u0 / uint32_t(hb);
-    const uint32_t off = u0 - qq * uint32_t(hb);
-    uint32_t len = uint32_t(hb) - off;
-    if (len > u1 - u0) len = u1 - u0;
-    const uint32_t n = qq / uint32_t(strips);
-    tab[i] = v;
-    tab[72 + i] = int(n);
-    tab[72 + 64 + i] = int(qq - n * uint32_t(strips));
-    tab[72 + 128 + i] = y0 + int(off);
-    v += int(len) + 4;
-    u0 += len;
-    ++i;
-  }
-  tab[i] = v;
-  tab[71] = i;
-}
-
 // t[j] = D[j-1][block 0] + D[j+1][block 2] over the 128 lanes of a tile for NC live columns: the edge lanes of each quadrant
 // warp swap in the neighbouring quadrant's row through shared memory (named barrier `bar`, 128 threads), then one rotating
 // shuffle per column serves every lane.  `xq` = the group's exchange area [quadrant][block][16], already offset by the parity
@@ -328,7 +289,7 @@ __global__ void __launch_bounds__(EspcnCfg<C, R, SHUF>::kThreads, 1) espcn_fused
   pdl_wait();
   pdl_launch_dependents();
   for (int i = threadIdx.x; i < 32 + NP3; i += blockDim.x) s_bias[i] = (i < 32) ? p.b2[i] : (i - 32 < COUT ? p.b3[i - 32] : 0.f);
-  if (threadIdx.x == 32) ef_build_segments(s_tab, u0, u1, p.hb, p.y0, p.strips);
+  if (threadIdx.x == 32) ef_build_segments(s_tab, u0, u1, p.hb, p.y0, p.strips, 4);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();

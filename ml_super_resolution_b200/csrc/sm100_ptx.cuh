@@ -110,6 +110,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, int c0, int c
       ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(src)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, int c0, int c1, int c2, uint32_t src) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+      ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(src)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
