@@ -55,6 +55,15 @@ int srk_create(int device, srk_handle_t* out);
 int srk_destroy(srk_handle_t h);
 int srk_num_sms(srk_handle_t h);
 
+/* Kernel form of the plain 3x3 64->64 srk_conv_tc layers on this handle (sticky until changed):
+ *   SRK_CONV_FORM_AUTO  (default) column strips when the FPA images are at least 112 pixels wide, else the flat stream
+ *   SRK_CONV_FORM_FLAT / SRK_CONV_FORM_STRIP  force one form.
+ * A model that cuts a frame into panels sets the form from the FRAME width before it runs its layers, so that tiled and
+ * un-tiled runs of one frame use the same arithmetic and stay bit-identical (the reference has no tiling: its
+ * experiment_resolve.py:60-69 feeds whole frames to tf.layers.conv2d). */
+enum { SRK_CONV_FORM_AUTO = 0, SRK_CONV_FORM_FLAT = 1, SRK_CONV_FORM_STRIP = 2 };
+int srk_set_conv_form(srk_handle_t h, int form);
+
 /* rows (multiple of 128) an FPA buffer for n_img images of H x W must hold */
 int64_t srk_fpa_rows(int n_img, int H, int W);
 
@@ -114,7 +123,10 @@ int srk_conv_first_tc(srk_handle_t h, const float* x, int n_frames, int FH, int 
  * k is 3 or 1.  mask_kind: SRK_ACT_RELU -> (mask_src>0), SRK_ACT_TANH -> (1-mask_src^2).
  * addend (optional FPA, cout_p channels): relu_after_add = 0 -> y + addend; 1 -> relu(y + addend) (residual block
  * output, enet/enet/model_enet.py:29-31); 2 -> (conv + addend) * act'(mask_src): the data gradient through that
- * junction, where the skip path's gradient joins before the producing layer's activation mask. */
+ * junction, where the skip path's gradient joins before the producing layer's activation mask.
+ * The plain 3x3 64->64 layer (no mask, no addend, act none | relu) has two kernel forms: the flat-stream one (any geometry)
+ * and the column-strip one (csrc/conv_strip.cu: no lane shift in the epilogue, ~25 % faster on wide frames); they add the
+ * nine taps in different fp32 orders, so their outputs differ in the last bf16 bit.  srk_set_conv_form chooses. */
 int srk_conv_tc(srk_handle_t h, const void* x_fpa, int cin_p, const void* w_packed, const float* bias,
                 int k, int cout_p, int act, int n_img, int H, int W, void* y_fpa,
                 const void* mask_src, int mask_kind, const void* addend_fpa, int relu_after_add,

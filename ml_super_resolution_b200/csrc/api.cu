@@ -137,6 +137,12 @@ int srk_destroy(srk_handle_t h) {
 
 int srk_num_sms(srk_handle_t h) { return h ? h->num_sms : -1; }
 
+int srk_set_conv_form(srk_handle_t h, int form) {
+  SRK_REQUIRE(h && form >= SRK_CONV_FORM_AUTO && form <= SRK_CONV_FORM_STRIP, "srk_set_conv_form: bad argument (form %d)", form);
+  h->conv_form = form;
+  return 0;
+}
+
 int64_t srk_fpa_rows(int n_img, int H, int W) { return srk::fpa_geom(n_img, H, W).rows_alloc; }
 
 }  // extern "C"

@@ -55,7 +55,7 @@ struct alignas(64) ConvStripParams {
   CUtensorMap map_out;  // same tensor shape        box {64, 126, 1}
   CUtensorMap map_w;    // [9*64][64]               box {64, 64}      SRK_PACK_FWD (tap-major, t = dy*3 + dx)
   const float* bias;    // [64] or null
-  int n_img, H, W, strips;
+  int n_base, n_img, H, W, strips;  // images [n_base, n_base + n_img) of the FPA are processed by this launch
   long long units;      // n_img * strips * H
   int act;
 };
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) conv_strip_kernel(const __grid_
         if (lane == 0) {
           mbar_arrive_expect_tx(FULL(st), kCsTileBytes);
           // virtual row j of a segment is the input row ya - 1 + j = FPA row index n*(H+1) + ya + j (index 0 = the zero row)
-          tma_load_3d(s_in + st * kCsTileBytes, &p.map_in, 0, w.s * kCsStripW - 1, w.n * rows_per_img + w.ya + (v - w.v0), FULL(st));
+          tma_load_3d(s_in + st * kCsTileBytes, &p.map_in, 0, w.s * kCsStripW - 1, (p.n_base + w.n) * rows_per_img + w.ya + (v - w.v0), FULL(st));
         }
         __syncwarp();
         if (++st == kCsStages) st = 0, ++lap;
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) conv_strip_kernel(const __grid_
             fence_proxy_async_smem();
             asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
             if (leader) {
-              tma_store_3d(&p.map_out, 0, w.s * kCsStripW, w.n * rows_per_img, stage);
+              tma_store_3d(&p.map_out, 0, w.s * kCsStripW, (p.n_base + w.n) * rows_per_img, stage);
               tma_store_commit();
             }
           }
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) conv_strip_kernel(const __grid_
           fence_proxy_async_smem();
           asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
           if (leader) {
-            tma_store_3d(&p.map_out, 0, w.s * kCsStripW, w.n * rows_per_img + w.ya + j - 1, stage);  // output row ya + j - 2 -> FPA index + 1
+            tma_store_3d(&p.map_out, 0, w.s * kCsStripW, (p.n_base + w.n) * rows_per_img + w.ya + j - 1, stage);  // output row ya + j - 2 -> FPA index + 1
             tma_store_commit();
           }
         }
@@ -266,15 +266,9 @@ __global__ void __launch_bounds__(kCsThreads, 1) conv_strip_kernel(const __grid_
   if (warp == 10) tmem_dealloc<512>(tmem);
 }
 
-// Whether the strip form serves this geometry: wide rows (a strip is 126 pixels: narrow patches would leave most lanes idle) and
-// few enough strip segments per CTA for the segment table.
-bool conv_strip_applicable(srk_ctx* h, int n_img, int H, int W) {
-  if (std::getenv("SRK_NO_STRIP") != nullptr || W < 112 || H < 8) return false;  // (the environment switch is for A/B measurements)
-  const int strips = (W + 1 + kCsStripW - 1) / kCsStripW;
-  const long long units = (long long)n_img * strips * H;
-  if (units >= (1ll << 31)) return false;
-  const int grid = int(std::min<long long>(h->num_sms, std::max<long long>(1, units / 8)));
-  return (units / grid) / H + 3 <= kEfMaxSegs;
+// AUTO form: wide rows only (a strip is 126 pixels: narrow patches would leave most lanes idle).
+bool conv_strip_applicable(srk_ctx*, int /*n_img*/, int /*H*/, int W) {
+  return std::getenv("SRK_NO_STRIP") == nullptr && W >= 112;  // (the environment switch is for A/B measurements)
 }
 
 int launch_conv_strip(srk_ctx* h, const void* x_fpa, const void* w_packed, const float* bias, int act, int n_img, int H, int W, void* y_fpa,
@@ -290,14 +284,22 @@ int launch_conv_strip(srk_ctx* h, const void* x_fpa, const void* w_packed, const
   if (int rc = make_tensor_map_3d(h, &p.map_out, y_fpa, 2, uint64_t(Wp), 64, img_rows, 128, uint64_t(Wp) * 128, kCsStripW)) return rc;
   if (int rc = make_tensor_map_2d(h, &p.map_w, w_packed, 9 * 64, 64, 64)) return rc;
   p.bias = bias;
-  p.n_img = n_img;
   p.H = H;
   p.W = W;
   p.strips = (Wp + kCsStripW - 1) / kCsStripW;
-  p.units = (long long)n_img * p.strips * H;
   p.act = act;
-  const int grid = int(std::min<long long>(h->num_sms, std::max<long long>(1, p.units / 8)));
-  SRK_CHECK_CUDA(launch_pdl(conv_strip_kernel, dim3(grid), dim3(kCsThreads), size_t(kCsSmem), stream, p));
+  // A CTA follows at most kEfMaxSegs strip segments (one per strip it touches): images are processed in chunks small enough for
+  // that (one launch for anything but thousands of tiny images).
+  SRK_REQUIRE(p.strips <= (kEfMaxSegs - 3) * h->num_sms, "conv_strip: image width %d too large", W);
+  const int chunk = std::max(1, (kEfMaxSegs - 3) * h->num_sms / p.strips);
+  for (int n0 = 0; n0 < n_img; n0 += chunk) {
+    p.n_base = n0;
+    p.n_img = std::min(chunk, n_img - n0);
+    p.units = (long long)p.n_img * p.strips * H;
+    SRK_REQUIRE(p.units < (1ll << 31), "conv_strip: too many strip rows for one launch");
+    const int grid = int(std::min<long long>(h->num_sms, std::max<long long>(1, p.units / 8)));
+    SRK_CHECK_CUDA(launch_pdl(conv_strip_kernel, dim3(grid), dim3(kCsThreads), size_t(kCsSmem), stream, p));
+  }
   return 0;
 }
 

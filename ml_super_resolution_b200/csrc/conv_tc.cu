@@ -1127,7 +1127,7 @@ extern "C" int srk_conv_tc(srk_handle_t h, const void* x_fpa, int cin_p, const v
   cudaStream_t s = as_stream(stream);
   // wide frames: the column-strip form of the plain 3x3 64->64 layer (no lane shift in the epilogue, conv_strip.cu)
   if (cin_p == 64 && cout_p == 64 && k == 3 && !mask_src && !addend_fpa && (act == SRK_ACT_NONE || act == SRK_ACT_RELU) &&
-      conv_strip_applicable(h, n_img, H, W))
+      (h->conv_form == SRK_CONV_FORM_STRIP || (h->conv_form == SRK_CONV_FORM_AUTO && conv_strip_applicable(h, n_img, H, W))))
     return launch_conv_strip(h, x_fpa, w_packed, bias, act, n_img, H, W, y_fpa, s);
 #define SRK_CASE(CIN, NP, KS) \
   if (cin_p == CIN && cout_p == NP && k == KS) return launch_conv_tc<CIN, NP, KS, EPI_FPA>(h, p, x_fpa, w_packed, y_fpa, s);

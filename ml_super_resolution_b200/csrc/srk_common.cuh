@@ -43,6 +43,7 @@ struct srk_ctx {
   int smem_optin;
   std::unordered_set<const void*> once;  // kernels whose attributes are set / tables that are uploaded on this device
   std::unordered_map<srk_tmap_key, CUtensorMap, srk_tmap_key_hash> tmaps;
+  int conv_form = 0;         // SRK_CONV_FORM_*: kernel form of the plain 3x3 64->64 layers (srk_set_conv_form)
   void* comm = nullptr;      // ncclComm_t once srk_comm_init has run (collective.cu)
   int comm_world = 1;
 };

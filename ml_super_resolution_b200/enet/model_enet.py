@@ -107,14 +107,19 @@ class EnetGenerator:
         t = seam(ops.conv_first_tc(sd, W[self._idx[0]], a.view(self._b(0)), 3, "SAME", "relu", panels=panels[0],
                                    panel_hw=(hh, ww) if need_tiles else None), 0)
         i = 1
+        # the FRAME's width at each resolution decides the kernel form of the 3x3 layers (ops.conv_form): panels compute what
+        # the un-tiled frame would
         for _ in range(10):
-            x = seam(ops.conv_tc(t, W[self._idx[i]], a.view(self._b(i)), 3, "relu"), 0)
+            with ops.conv_form(w):
+                x = seam(ops.conv_tc(t, W[self._idx[i]], a.view(self._b(i)), 3, "relu"), 0)
             t = ops.conv_tc(x, W[self._idx[i + 1]], a.view(self._b(i + 1)), 1, None, addend=t, relu_after_add=True)
             i += 2
         for level in (1, 2):
-            t = seam(ops.conv_tc(ops.fpa_upsample2(t), W[self._idx[i]], a.view(self._b(i)), 3, "relu"), level)
+            with ops.conv_form(w << level):
+                t = seam(ops.conv_tc(ops.fpa_upsample2(t), W[self._idx[i]], a.view(self._b(i)), 3, "relu"), level)
             i += 1
-        t = seam(ops.conv_tc(t, W[self._idx[i]], a.view(self._b(i)), 3, "relu"), 2)
+        with ops.conv_form(4 * w):
+            t = seam(ops.conv_tc(t, W[self._idx[i]], a.view(self._b(i)), 3, "relu"), 2)
         return ops.conv_tc_last(t, W[self._idx[i + 1]], self.bias_last, 3, 3, None, addend=bq, panels=panels[2],
                                 frame_shape=(n, 4 * h, 4 * w) if need_tiles else None, out=out)
 

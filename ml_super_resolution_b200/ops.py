@@ -207,6 +207,28 @@ def conv_first_tc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor | 
     return out
 
 
+CONV_FORMS = {"auto": 0, "flat": 1, "strip": 2}
+STRIP_MIN_W = 112  # frames at least this wide run their plain 3x3 64->64 layers in the column-strip form (csrc/conv_strip.cu)
+
+
+class conv_form:
+    """`with ops.conv_form(frame_width): ...` -- kernel form of the plain 3x3 64->64 layers inside the block (srk_set_conv_form),
+    chosen from the FRAME width so that a frame cut into panels runs the same arithmetic as the un-tiled frame (bit-identical
+    tiling); "auto" outside such blocks (training patches, single calls)."""
+
+    def __init__(self, frame_width_or_form):
+        f = frame_width_or_form
+        self.form = f if isinstance(f, str) else ("strip" if f >= STRIP_MIN_W else "flat")
+
+    def __enter__(self):
+        check(_ffi.lib().srk_set_conv_form(handle(), CONV_FORMS[self.form]), "srk_set_conv_form")
+        return self
+
+    def __exit__(self, *exc):
+        check(_ffi.lib().srk_set_conv_form(handle(), CONV_FORMS["auto"]), "srk_set_conv_form")
+        return False
+
+
 def conv_tc(x: Fpa, w_packed: torch.Tensor, bias: torch.Tensor | None, k: int, act=None, out: Fpa | None = None,
             mask_src: Fpa | None = None, mask_kind=None, addend: Fpa | None = None, relu_after_add=False) -> Fpa:
     """Tensor-core conv FPA -> FPA (srk_conv_tc).  w_packed: [k*k, cout_p, cin_p] bf16."""

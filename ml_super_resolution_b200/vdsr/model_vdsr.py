@@ -106,7 +106,8 @@ class VdsrNet:
             if taps is not None:
                 taps["conv.1"] = taps["relu.1"] = ops.fpa_to_nhwc(t)
             for i in range(1, self.L - 1):
-                t = ops.conv_tc(t, self.wf(i), a.view(self._bname(i)), 3, "relu", out=bufs[i % 2])
+                with ops.conv_form(W):
+                    t = ops.conv_tc(t, self.wf(i), a.view(self._bname(i)), 3, "relu", out=bufs[i % 2])
                 if taps is not None:
                     taps[f"conv.{i + 1}"] = taps[f"relu.{i + 1}"] = ops.fpa_to_nhwc(t)
             ops.conv_tc_last(t, self.wf(self.L - 1), self.bias_last, 3, self.C, None, addend=sd, out=out)
@@ -133,7 +134,8 @@ class VdsrNet:
             if exchange:  # the gather pads a panel's window edge with zeros: its seam columns come from the neighbour too
                 ops.fpa_halo_exchange(t, panels, max_cols)
             for i in range(1, self.L - 1):
-                t = ops.conv_tc(t, self.wf(i), a.view(self._bname(i)), 3, "relu", out=bufs[i % 2])
+                with ops.conv_form(W):  # the FRAME's width decides the kernel form: panels compute what the un-tiled frame would
+                    t = ops.conv_tc(t, self.wf(i), a.view(self._bname(i)), 3, "relu", out=bufs[i % 2])
                 if exchange:
                     ops.fpa_halo_exchange(t, panels, max_cols)
             ops.conv_tc_last(t, self.wf(self.L - 1), self.bias_last, 3, self.C, None, addend=sd, panels=panels, frame_shape=(n, H, W),

@@ -275,10 +275,42 @@ def test_edge_geometries_and_error_behaviour(srk_ops):
     assert float((got - ref).abs().max()) <= 3e-2
     # refusals
     wide = srk_ops.fpa_empty(1, 4, 300, 64)
-    with pytest.raises(SrkError, match="too large|column panels"):
-        srk_ops.conv_tc(wide, wp, b, 3, "relu")
+    with srk_ops.conv_form("flat"):  # the flat-stream form keeps 2*Wp + 128 rows in shared memory: 254 px is its limit
+        with pytest.raises(SrkError, match="too large|column panels"):
+            srk_ops.conv_tc(wide, wp, b, 3, "relu")
+    srk_ops.conv_tc(wide, wp, b, 3, "relu")  # (any width in the column-strip form, which is what wide frames get by default)
+    with pytest.raises(SrkError, match="too large|column panels"):  # forms without a strip variant (masked data gradient) still refuse
+        srk_ops.conv_tc(wide, wp, None, 3, None, mask_src=wide, mask_kind="relu")
     with pytest.raises(SrkError, match="unsupported"):
         srk_ops.conv_tc(srk_ops.fpa_empty(1, 4, 4, 64), torch.zeros((49, 64, 64), dtype=torch.bfloat16, device="cuda"), b, 7, "relu")
     with pytest.raises(SrkError, match="smaller than the 11x11"):
         from ml_super_resolution_b200 import metrics as M
         M.ssim(torch.zeros((1, 8, 8, 3), device="cuda"), torch.zeros((1, 8, 8, 3), device="cuda"), 2.0)
+
+
+@pytest.mark.parametrize("shape,act", [((1, 9, 126), "relu"), ((2, 20, 130), None), ((3, 17, 253), "relu"), ((2, 40, 400), "relu"), ((5, 3, 24), "relu"),
+                                       ((1, 1, 1), None)])
+def test_conv_strip_form(srk_ops, shape, act):
+    """The column-strip form of the plain 3x3 64->64 layer (csrc/conv_strip.cu; vdsr/vdsr/model_vdsr.py:64-83) against the oracle and
+    against the flat-stream form: same bf16 gate, a complete FPA (zero pad row / column written), ragged strips (widths that are
+    not multiples of 126), images narrower than a strip and smaller than the receptive field, several images per launch."""
+    n, h, w = shape
+    r = _rng(h * 1000 + w)
+    x = _bf(r.uniform(-1, 1, (n, h, w, 64)))
+    wt = _bf(r.standard_normal((3, 3, 64, 64)) / 24)
+    b = (r.standard_normal(64) * 0.1).astype(np.float32)
+    xf, wp, bd = srk_ops.fpa_from_nhwc(_dev(x)), srk_ops.pack_conv_weights(_dev(wt)), _dev(b)
+    ref = O.conv2d_nhwc(x, wt, b, "SAME", act)
+    outs = {}
+    for form in ("strip", "flat") if w <= 254 else ("strip",):  # (254 px is the flat-stream form's limit)
+        y = srk_ops.fpa_empty(n, h, w, 64)
+        y.data.fill_(float("nan"))
+        with srk_ops.conv_form(form):
+            srk_ops.conv_tc(xf, wp, bd, 3, act, out=y)
+        outs[form] = srk_ops.fpa_to_nhwc(y).cpu().numpy()
+        _close_bf16(outs[form], ref)
+        raw = y.data.float().cpu().numpy()[: n * (h + 1) * (w + 1)].reshape(n, h + 1, w + 1, 64)
+        assert np.all(raw[:, 0] == 0) and np.all(raw[:, :, w] == 0), form
+    # the two forms add the nine taps in different fp32 orders: equal to one bf16 rounding step
+    if "flat" in outs:
+        assert np.abs(outs["strip"] - outs["flat"]).max() <= 2.0 ** -7 * max(1.0, np.abs(ref).max())
