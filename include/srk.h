@@ -56,7 +56,8 @@ int srk_destroy(srk_handle_t h);
 int srk_num_sms(srk_handle_t h);
 
 /* Kernel form of the plain 3x3 64->64 srk_conv_tc layers on this handle (sticky until changed):
- *   SRK_CONV_FORM_AUTO  (default) column strips when the FPA images are at least 112 pixels wide, else the flat stream
+ *   SRK_CONV_FORM_AUTO  (default) column strips when at least 80 % of a 126-lane tile carries pixels (rows of 100+ pixels cut
+ *                       into strips, or several narrow images side by side: 3 x 42 lanes for 41-pixel patches), else the flat stream
  *   SRK_CONV_FORM_FLAT / SRK_CONV_FORM_STRIP  force one form.
  * A model that cuts a frame into panels sets the form from the FRAME width before it runs its layers, so that tiled and
  * un-tiled runs of one frame use the same arithmetic and stay bit-identical (the reference has no tiling: its
@@ -131,6 +132,19 @@ int srk_conv_tc(srk_handle_t h, const void* x_fpa, int cin_p, const void* w_pack
                 int k, int cout_p, int act, int n_img, int H, int W, void* y_fpa,
                 const void* mask_src, int mask_kind, const void* addend_fpa, int relu_after_add,
                 srk_stream_t stream);
+
+/* A CHAIN of plain 3x3 64->64 layers of one geometry in ONE persistent launch (column-strip form, csrc/conv_strip.cu): layer l
+ * reads x_fpa[l] and writes y_fpa[l] (normally x_fpa[l+1] == y_fpa[l]); between layers the CTAs meet at a grid barrier instead
+ * of paying a launch each -- at 64 patches of 41x41 a launch lives 12.7 us of which ~5 us is work.
+ *   replaces the 18 middle tf.layers.conv2d(.., 64, 3, 'same', relu) of vdsr/vdsr/model_vdsr.py:64-83 (forward chain) and
+ *   their data gradients (tf.gradients of the same lines: SRK_PACK_DGRAD weights, mask_src[l] = the saved activation whose
+ *   ReLU' masks layer l's output, bias null, act none).
+ * Arrays of n_layers (<= 20) HOST pointers to device buffers; bias / mask_src may be null (or hold null entries); act[l] is
+ * SRK_ACT_NONE | SRK_ACT_RELU.  sync_word: 16 bytes of device memory for the grid barriers (the call zeroes them on the stream);
+ * may be null when n_layers == 1. */
+int srk_conv_tc_chain(srk_handle_t h, int n_layers, const void* const* x_fpa, const void* const* w_packed, const float* const* bias,
+                      const int* act, void* const* y_fpa, const void* const* mask_src, int n_img, int H, int W, void* sync_word,
+                      srk_stream_t stream);
 
 /* Last layer: tensor-core conv from an FPA into an fp32 NHWC frame, fused with the global
  * residual add and (ESPCN) the depth_to_space pixel shuffle:

@@ -44,6 +44,7 @@ SIGNATURES = {
     "srk_destroy": (_I, [_P]),
     "srk_num_sms": (_I, [_P]),
     "srk_set_conv_form": (_I, [_P, _I]),
+    "srk_conv_tc_chain": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "srk_fpa_rows": (_I64, [_I, _I, _I]),
     "srk_pack_conv_weights": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "srk_pack_conv_weights_batched": (_I, [_P, _P, _P, _I, _I64, _P, _P]),

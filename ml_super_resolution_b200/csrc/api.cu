@@ -103,6 +103,30 @@ int make_tensor_map_3d(srk_ctx* h, CUtensorMap* out, const void* gptr, uint32_t 
   return 0;
 }
 
+int make_tensor_map_fpa4(srk_ctx* h, CUtensorMap* out, const void* gptr, int n_img, int H, int W, uint32_t box_x, uint32_t box_n) {
+  const std::array<uint64_t, 6> key{reinterpret_cast<uint64_t>(gptr), uint64_t(n_img), uint64_t(H), uint64_t(W), box_x, box_n};
+  auto it = h->tmaps_fpa.find(key);
+  if (it != h->tmaps_fpa.end()) {
+    *out = it->second;
+    return 0;
+  }
+  if (h->tmaps_fpa.size() > 4096) h->tmaps_fpa.clear();
+  EncodeTiledFn enc = encode_fn();
+  SRK_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  SRK_REQUIRE(box_x >= 1 && box_x <= 256 && box_n >= 1 && box_n <= 256 && box_x * box_n <= 128, "tensor map: FPA box %u x %u", box_x, box_n);
+  const uint64_t Wp = uint64_t(W) + 1, rows = uint64_t(H) + 1;
+  cuuint64_t dims[4] = {64, Wp, rows, uint64_t(n_img)};
+  cuuint64_t strides[3] = {128, Wp * 128, rows * Wp * 128};
+  cuuint32_t box[4] = {64, box_x, 1, box_n};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(gptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SRK_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (FPA 4-D) failed with CUresult %d (ptr %p n %d H %d W %d box %u x %u)", int(r), gptr, n_img, H, W,
+              box_x, box_n);
+  h->tmaps_fpa.emplace(key, *out);
+  return 0;
+}
+
 }  // namespace srk
 
 extern "C" {

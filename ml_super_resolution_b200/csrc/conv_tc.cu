@@ -1126,9 +1126,9 @@ extern "C" int srk_conv_tc(srk_handle_t h, const void* x_fpa, int cin_p, const v
   p.relu_after_add = relu_after_add;
   cudaStream_t s = as_stream(stream);
   // wide frames: the column-strip form of the plain 3x3 64->64 layer (no lane shift in the epilogue, conv_strip.cu)
-  if (cin_p == 64 && cout_p == 64 && k == 3 && !mask_src && !addend_fpa && (act == SRK_ACT_NONE || act == SRK_ACT_RELU) &&
+  if (cin_p == 64 && cout_p == 64 && k == 3 && (!mask_src || mask_kind == SRK_ACT_RELU) && !addend_fpa && (act == SRK_ACT_NONE || act == SRK_ACT_RELU) &&
       (h->conv_form == SRK_CONV_FORM_STRIP || (h->conv_form == SRK_CONV_FORM_AUTO && conv_strip_applicable(h, n_img, H, W))))
-    return launch_conv_strip(h, x_fpa, w_packed, bias, act, n_img, H, W, y_fpa, s);
+    return launch_conv_strip(h, x_fpa, w_packed, bias, act, n_img, H, W, y_fpa, mask_src, s);
 #define SRK_CASE(CIN, NP, KS) \
   if (cin_p == CIN && cout_p == NP && k == KS) return launch_conv_tc<CIN, NP, KS, EPI_FPA>(h, p, x_fpa, w_packed, y_fpa, s);
   SRK_CASE(64, 64, 3)

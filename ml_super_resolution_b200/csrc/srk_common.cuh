@@ -3,7 +3,9 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <array>
 #include <cstring>
+#include <map>
 #include <unordered_map>
 #include <unordered_set>
 #include <utility>
@@ -43,6 +45,7 @@ struct srk_ctx {
   int smem_optin;
   std::unordered_set<const void*> once;  // kernels whose attributes are set / tables that are uploaded on this device
   std::unordered_map<srk_tmap_key, CUtensorMap, srk_tmap_key_hash> tmaps;
+  std::map<std::array<uint64_t, 6>, CUtensorMap> tmaps_fpa;  // 4-D FPA maps (make_tensor_map_fpa4)
   int conv_form = 0;         // SRK_CONV_FORM_*: kernel form of the plain 3x3 64->64 layers (srk_set_conv_form)
   void* comm = nullptr;      // ncclComm_t once srk_comm_init has run (collective.cu)
   int comm_world = 1;
@@ -106,6 +109,11 @@ int make_tensor_map_2d(srk_ctx* h, CUtensorMap* out, const void* gptr, uint64_t 
 int make_tensor_map_3d(srk_ctx* h, CUtensorMap* out, const void* gptr, uint32_t elem_bytes, uint64_t rows, uint64_t cols, uint64_t batch,
                        uint64_t row_stride_bytes, uint64_t batch_stride_bytes, uint32_t box_rows);
 
+// 4-D bf16 view of an FPA of 64 channels: dims {64 channels, Wp pixels, H+1 image rows (row 0 = the zero row), n_img}, box
+// {64, box_x, 1, box_n}, SWIZZLE_128B, zero fill out of bounds.  A box is box_n * box_x consecutive 128-byte rows in shared
+// memory: one image row of box_n images side by side (conv_strip.cu).
+int make_tensor_map_fpa4(srk_ctx* h, CUtensorMap* out, const void* gptr, int n_img, int H, int W, uint32_t box_x, uint32_t box_n);
+
 // true exactly once per (handle, key): guards per-device one-time work such as cudaFuncSetAttribute or a __constant__ upload
 inline bool first_use(srk_ctx* h, const void* key) { return h->once.insert(key).second; }
 
@@ -137,7 +145,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 // Column-strip form of the 3x3 64->64 FPA convolution (conv_strip.cu): srk_conv_tc routes wide frames there.
 bool conv_strip_applicable(srk_ctx* h, int n_img, int H, int W);
 int launch_conv_strip(srk_ctx* h, const void* x_fpa, const void* w_packed, const float* bias, int act, int n_img, int H, int W, void* y_fpa,
-                      cudaStream_t stream);
+                      const void* mask_src, cudaStream_t stream);
 
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

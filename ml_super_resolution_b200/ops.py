@@ -208,7 +208,16 @@ def conv_first_tc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor | 
 
 
 CONV_FORMS = {"auto": 0, "flat": 1, "strip": 2}
-STRIP_MIN_W = 112  # frames at least this wide run their plain 3x3 64->64 layers in the column-strip form (csrc/conv_strip.cu)
+STRIP_W = 126  # pixels per column strip (csrc/conv_strip.cu)
+
+
+def strip_lanes(width: int) -> float:
+    """Share of a 126-lane tile of the column-strip form that carries pixels for images `width` wide (cs_geom in conv_strip.cu):
+    narrow images sit side by side, each with its zero column; wide ones are cut into strips."""
+    wp = width + 1
+    if 2 * wp <= STRIP_W:
+        return (STRIP_W // wp) * wp / STRIP_W
+    return wp / (-(-wp // STRIP_W) * STRIP_W)
 
 
 class conv_form:
@@ -218,7 +227,7 @@ class conv_form:
 
     def __init__(self, frame_width_or_form):
         f = frame_width_or_form
-        self.form = f if isinstance(f, str) else ("strip" if f >= STRIP_MIN_W else "flat")
+        self.form = f if isinstance(f, str) else ("strip" if (f >= 100 and (strip_lanes(f) >= 0.8 or f > 254)) else "flat")
 
     def __enter__(self):
         check(_ffi.lib().srk_set_conv_form(handle(), CONV_FORMS[self.form]), "srk_set_conv_form")
@@ -240,6 +249,35 @@ def conv_tc(x: Fpa, w_packed: torch.Tensor, bias: torch.Tensor | None, k: int, a
                                  _ptr(out.data), _ptr(mask_src.data if mask_src is not None else None), ACT[mask_kind],
                                  _ptr(addend.data if addend is not None else None), int(relu_after_add), _stream()), "srk_conv_tc")
     return out
+
+
+class ConvChain:
+    """A prepared srk_conv_tc_chain call: n plain 3x3 64->64 layers of one geometry in one persistent launch.  The pointer arrays
+    live in this object (host memory the C call reads at launch time)."""
+
+    def __init__(self, xs: list[Fpa], w_packed: list[torch.Tensor], biases: list[torch.Tensor | None], acts: list, ys: list[Fpa],
+                 masks: list[Fpa | None] | None = None):
+        n = len(xs)
+        assert n == len(w_packed) == len(biases) == len(acts) == len(ys) and 1 <= n <= 20
+        g = xs[0]
+        assert all((a.n_img, a.H, a.W, a.C) == (g.n_img, g.H, g.W, 64) for a in list(xs) + list(ys))
+        assert all(w.shape == (9, 64, 64) for w in w_packed)
+        masks = masks or [None] * n
+        vp = C.c_void_p * n
+        self._keep = (xs, w_packed, biases, ys, masks)  # the buffers must outlive the launches
+        self.x = vp(*[a.data.data_ptr() for a in xs])
+        self.w = vp(*[w.data_ptr() for w in w_packed])
+        self.b = vp(*[(b.data_ptr() if b is not None else None) for b in biases])
+        self.a = (C.c_int * n)(*[ACT[a] for a in acts])
+        self.y = vp(*[a.data.data_ptr() for a in ys])
+        self.m = vp(*[(m.data.data_ptr() if m is not None else None) for m in masks])
+        self.n, self.geom = n, (g.n_img, g.H, g.W)
+        self.sync = torch.zeros(4, dtype=torch.int32, device=g.data.device)
+
+    def run(self) -> Fpa:
+        check(_ffi.lib().srk_conv_tc_chain(handle(), self.n, self.x, self.w, self.b, self.a, self.y, self.m, *self.geom, _ptr(self.sync), _stream()),
+              "srk_conv_tc_chain")
+        return self._keep[3][-1]
 
 
 def conv_tc_last(x: Fpa, w_packed: torch.Tensor, bias: torch.Tensor | None, k: int, cout: int, act=None,

@@ -279,8 +279,9 @@ def test_edge_geometries_and_error_behaviour(srk_ops):
         with pytest.raises(SrkError, match="too large|column panels"):
             srk_ops.conv_tc(wide, wp, b, 3, "relu")
     srk_ops.conv_tc(wide, wp, b, 3, "relu")  # (any width in the column-strip form, which is what wide frames get by default)
-    with pytest.raises(SrkError, match="too large|column panels"):  # forms without a strip variant (masked data gradient) still refuse
-        srk_ops.conv_tc(wide, wp, None, 3, None, mask_src=wide, mask_kind="relu")
+    srk_ops.conv_tc(wide, wp, None, 3, None, mask_src=wide, mask_kind="relu")  # (so does the masked data-gradient form)
+    with pytest.raises(SrkError, match="too large|column panels"):  # forms without a strip variant (residual junction) still refuse
+        srk_ops.conv_tc(wide, wp, None, 3, None, addend=wide, relu_after_add=True)
     with pytest.raises(SrkError, match="unsupported"):
         srk_ops.conv_tc(srk_ops.fpa_empty(1, 4, 4, 64), torch.zeros((49, 64, 64), dtype=torch.bfloat16, device="cuda"), b, 7, "relu")
     with pytest.raises(SrkError, match="smaller than the 11x11"):
@@ -314,3 +315,55 @@ def test_conv_strip_form(srk_ops, shape, act):
     # the two forms add the nine taps in different fp32 orders: equal to one bf16 rounding step
     if "flat" in outs:
         assert np.abs(outs["strip"] - outs["flat"]).max() <= 2.0 ** -7 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("shape", [(8, 41, 41), (7, 20, 24), (5, 3, 62), (2, 20, 130)])
+def test_conv_strip_side_by_side_and_mask(srk_ops, shape):
+    """Column-strip form with several narrow images side by side in one tile (3 x 42 lanes for VDSR's 41-pixel training patches,
+    vdsr/vdsr/experiment_train.py:17-26; a last group that is only partly filled) and its data-gradient form: SRK_PACK_DGRAD-style
+    call with the ReLU' mask of the saved activation (tf.gradients through vdsr/vdsr/model_vdsr.py:64-83)."""
+    n, h, w = shape
+    r = _rng(n * 100 + w)
+    x = _bf(r.uniform(-1, 1, (n, h, w, 64)))
+    wt = _bf(r.standard_normal((3, 3, 64, 64)) / 24)
+    saved = _bf(r.standard_normal((n, h, w, 64)))
+    xf, wp, mf = srk_ops.fpa_from_nhwc(_dev(x)), srk_ops.pack_conv_weights(_dev(wt)), srk_ops.fpa_from_nhwc(_dev(saved))
+    ref = O.conv2d_nhwc(x, wt, None, "SAME", None) * (saved > 0)
+    outs = {}
+    for form in ("strip", "flat"):
+        y = srk_ops.fpa_empty(n, h, w, 64)
+        y.data.fill_(float("nan"))
+        with srk_ops.conv_form(form):
+            srk_ops.conv_tc(xf, wp, None, 3, None, out=y, mask_src=mf, mask_kind="relu")
+        outs[form] = srk_ops.fpa_to_nhwc(y).cpu().numpy()
+        _close_bf16(outs[form], ref)
+        raw = y.data.float().cpu().numpy()[: n * (h + 1) * (w + 1)].reshape(n, h + 1, w + 1, 64)
+        assert np.all(raw[:, 0] == 0) and np.all(raw[:, :, w] == 0), form
+    assert np.abs(outs["strip"] - outs["flat"]).max() <= 2.0 ** -7 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("shape,layers", [((16, 41, 41), 6), ((2, 50, 300), 4)])
+def test_conv_chain_equals_layer_by_layer(srk_ops, shape, layers):
+    """srk_conv_tc_chain: n layers in one persistent launch (grid barrier between layers, two alternating parts for small layers)
+    == the same layers launched one by one, bit for bit -- forward (bias + ReLU) and masked data-gradient form; repeated calls
+    re-arm the barrier words."""
+    n, h, w = shape
+    g = torch.Generator(device="cuda").manual_seed(3)
+    ws = [srk_ops.pack_conv_weights(torch.randn((3, 3, 64, 64), device="cuda", generator=g) / 24) for _ in range(layers)]
+    bs = [torch.randn(64, device="cuda", generator=g) * 0.1 for _ in range(layers)]
+    x0 = srk_ops.fpa_from_nhwc(torch.randn((n, h, w, 64), device="cuda", generator=g))
+    masks = [srk_ops.fpa_from_nhwc(torch.randn((n, h, w, 64), device="cuda", generator=g)) for _ in range(layers)]
+    nv = n * (h + 1) * (w + 1)
+    for use_mask in (False, True):
+        seq = [x0]
+        with srk_ops.conv_form("strip"):
+            for l in range(layers):
+                seq.append(srk_ops.conv_tc(seq[-1], ws[l], None if use_mask else bs[l], 3, None if use_mask else "relu",
+                                           mask_src=masks[l] if use_mask else None, mask_kind="relu" if use_mask else None))
+        bufs = [srk_ops.fpa_empty(n, h, w, 64) for _ in range(layers)]
+        chain = srk_ops.ConvChain([x0] + bufs[:-1], ws, [None] * layers if use_mask else bs, [None] * layers if use_mask else ["relu"] * layers, bufs,
+                                  masks if use_mask else None)
+        for _ in range(2):
+            chain.run()
+        for l in range(layers):
+            assert torch.equal(bufs[l].data[:nv], seq[l + 1].data[:nv]), (use_mask, l)
