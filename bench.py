@@ -533,24 +533,30 @@ def enet_train_workload(args, rank, world):
         ops.mse_fwd_bwd(sr, hd, loss, dsr)
         return dsr
 
-    def step():
+    def eager_step():
         net.forward_backward(sd, bq, loss_head)
         if world > 1:
-            torch.distributed.all_reduce(a.g)
+            ops.allreduce_grads(a.g)
         t[0] += 1
         ops.adam_step(a.w, a.g, a.m, a.v, 1e-4, t[0])
         net._tb["plan"].run(a.w)
         net.repack()
 
     net.forward_backward(sd, bq, hd)  # allocate the training buffers outside the timed region
+    n_launch_step = launches_of(eager_step)
+    gstep = net.make_graphed_step(sd, bq, loss_head)  # the whole step (incl. the NCCL all-reduce at N > 1) as one CUDA graph
+
+    def step():
+        gstep(1e-4)
+
     ms, clocks = timed_steps(step, args.steps, args.warmup, world, ClockSampler(torch.cuda.current_device()) if rank == 0 else None)
     value = ENET_BATCH * world * args.steps / ms * 1e3
     flops_per_patch = 3.617e9 * 3  # fwd + dgrad + wgrad, SURVEY 8 row a5: 3.617 GFLOP fwd/patch
     pk = peaks()
     tf = value * flops_per_patch / 1e12 / world
-    roofline = {"bound": "tensor", "kernel": "whole generator step (25 fwd + 24 dgrad + 25 wgrad tcgen05 convs)", "achieved": round(tf, 1),
+    roofline = {"bound": "tensor", "kernel": "whole generator step (25 fwd + 24 dgrad + 25 wgrad tcgen05 convs; one CUDA graph)", "achieved": round(tf, 1),
                 "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": round(tf / pk["tf_sust"], 4), "traffic": None, "peak_source": pk["src"]}
-    n_launch = launches_of(step) * args.steps
+    n_launch = n_launch_step * args.steps
     sd_h, bq_h, hd_h = sd.cpu().pin_memory(), bq.cpu().pin_memory(), hd.cpu().pin_memory()
     loss_h = torch.zeros(1).pin_memory()
 

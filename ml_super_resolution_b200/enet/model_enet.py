@@ -231,6 +231,52 @@ class EnetGenerator:
         return b["sr"]
 
 
+    def make_graphed_step(self, sd_static: torch.Tensor, bq_static: torch.Tensor, loss_head, group=None):
+        """Capture one generator training step -- forward, `loss_head(sr) -> d(loss)/d(sr)` (kernels writing static buffers),
+        backward, the data-parallel gradient all-reduce (srk_allreduce_grads, when a process group is up), Adam(lr, .9, .999) and
+        the weight re-pack -- into ONE CUDA graph: the ~130 launches of a step are latency-bound at 64 patches of 32x32.
+        Returns `step(lr)`; new batches are copied INTO the static tensors before each call
+        (reference: `session.run(g_trainer)` of enet/enet/experiment_train.py:100-130 with model_enet.py:336-341)."""
+        import math
+        world = 1
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            world = torch.distributed.get_world_size(group)
+        if world > 1:
+            ops.comm_init(group)
+        a = self.arena
+        lr_t = torch.zeros(1, dtype=torch.float32, device=self.device)
+
+        def body():
+            self.forward_backward(sd_static, bq_static, loss_head)
+            if world > 1:
+                ops.allreduce_grads(a.g)
+            ops.adam_step_dev(a.w, a.g, a.m, a.v, lr_t)
+            self._tb["plan"].run(a.w)
+            self.repack()
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up outside capture (allocations, kernel attributes, NCCL channels); lr_t == 0: no update
+            body()
+        torch.cuda.current_stream().wait_stream(side)
+        a.m.zero_()
+        a.v.zero_()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            body()
+        feed = ops.PinnedScalarFeed()
+        t = [0]
+
+        def step(lr: float = 1e-4):
+            t[0] += 1
+            feed.push(lr * math.sqrt(1.0 - 0.999 ** t[0]) / (1.0 - 0.9 ** t[0]), lr_t)
+            graph.replay()
+
+        step.graph = graph
+        return step
+
+
 class _EnetGraph:
     def __init__(self, net, sd_ph, bq_ph):
         self.net, self.sd_ph, self.bq_ph = net, sd_ph, bq_ph
