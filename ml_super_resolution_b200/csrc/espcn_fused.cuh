@@ -125,11 +125,7 @@ struct EspcnCfg {
   static constexpr int kColA2 = kColD2 + kND2 * kN2;
   static_assert(!kSS || (kK1 + 1 <= 32 && NP3 == 16), "kSS: the bias K-steps of the first-layer tiles must be free; 1 KB weight blocks");
   static constexpr int kColD3 = kColA2 + (kSS ? 0 : 4 * 16);
-  // kSS: the CENTRE tap (dx = 1) needs no row shift, so its A operand comes from tensor memory (TS mode: no shared-memory
-  // operand read for A, 49-cycle instruction floor instead of 60): EPI1 / EPI2 write a1 / a2 to TMEM rings as well
-  static constexpr int kColA1T = kColD3 + kN3;
-  static constexpr int kColA2T = kColA1T + kNA1S * 32;
-  static_assert(kColD3 + kN3 <= 512 && (!kSS || kColA2T + kNA2S * 16 <= 512), "tensor memory plan does not fit");
+  static_assert(kColD3 + kN3 <= 512, "tensor memory plan does not fit");
   // shared memory
   static constexpr int kTBufBytes = 32 * kCout * 4;   // per EPI3 warp: its 32 pixels' outputs in OUTPUT order [row][pixel*kRC + e]
   static constexpr int kXchBytes = 2 * 4 * 2 * 16 * 4;  // [parity][quadrant][block][16 columns]
@@ -406,10 +402,8 @@ __global__ void __launch_bounds__(EspcnCfg<C, R, SHUF>::kThreads, 1) espcn_fused
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (dx == 1) umma_bf16_ts(tmem + L::kColD2, tmem + L::kColA1T + sl * 32 + k * 8, umma_desc(hi, b0 + dx * 5 * 4096 + k * 32), idesc, 1);
-                else umma_bf16(tmem + L::kColD2, umma_desc(hi, a0 + dx * 128 + k * 32), umma_desc(hi, b0 + dx * 5 * 4096 + k * 32), idesc, 1);
-              }
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem + L::kColD2, umma_desc(hi, a0 + dx * 128 + k * 32), umma_desc(hi, b0 + dx * 5 * 4096 + k * 32), idesc, 1);
             }
             umma_commit(C2(v & 3));
           }
@@ -461,10 +455,8 @@ __global__ void __launch_bounds__(EspcnCfg<C, R, SHUF>::kThreads, 1) espcn_fused
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                if (dx == 1) umma_bf16_ts(tmem + L::kColD3, tmem + L::kColA2T + sl * 16 + k * 8, umma_desc(hi, b0 + dx * 5 * NP3 * 64 + k * 32), idesc, 1);
-                else umma_bf16(tmem + L::kColD3, umma_desc(hi, a0 + dx * 64 + k * 32), umma_desc(hi, b0 + dx * 5 * NP3 * 64 + k * 32), idesc, 1);
-              }
+              for (int k = 0; k < 2; ++k)
+                umma_bf16(tmem + L::kColD3, umma_desc(hi, a0 + dx * 64 + k * 32), umma_desc(hi, b0 + dx * 5 * NP3 * 64 + k * 32), idesc, 1);
             }
             umma_commit(C3(v & 3));
           }
@@ -626,13 +618,10 @@ __global__ void __launch_bounds__(EspcnCfg<C, R, SHUF>::kThreads, 1) espcn_fused
               }
 #pragma unroll
               for (int q = 0; q < 4; ++q) ef_sts128u(dst + (((hf * 4 + q) ^ (gl & 7)) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-              tmem_st_32x32b_x16(tmem + L::kColA1T + sl * 32 + hf * 16 + lane_addr, pk);  // (centre tap: TS-mode operand)
             }
-            tmem_st_wait();
-            tc_fence_before();
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(G2(v & 3));  // a1[v] is in shared memory and tensor memory
+            if (lane == 0) mbar_arrive(G2(v & 3));  // a1[v] is in shared memory
             if (tr) EF_EV(8, v);
             sl = (sl + 2) % L::kNA1S;
           }
@@ -672,12 +661,9 @@ __global__ void __launch_bounds__(EspcnCfg<C, R, SHUF>::kThreads, 1) espcn_fused
             const uint32_t dst = s_a2 + sl * L::kA2Bytes + gl * 64;
 #pragma unroll
             for (int q = 0; q < 4; ++q) ef_sts128u(dst + ((q ^ ((gl >> 1) & 3)) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-            tmem_st_32x32b_x16(tmem + L::kColA2T + sl * 16 + lane_addr, pk);  // (centre tap: TS-mode operand)
-            tmem_st_wait();
-            tc_fence_before();
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(G3(v2 & 3));  // a2[v2] is in shared memory and tensor memory
+            if (lane == 0) mbar_arrive(G3(v2 & 3));  // a2[v2] is in shared memory
             if (tr) EF_EV(14, v2);
             m3 = (m3 == 2) ? 0 : m3 + 1;
             sl = (sl == L::kNA2S - 1) ? 0 : sl + 1;
