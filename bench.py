@@ -142,6 +142,38 @@ def launches_of(fn) -> int:
     return _ffi.launch_count - before
 
 
+def train_e2e_leg(static_tensors, host_tensors, run_step, loss_dev, n_steps, world):
+    """End-to-end leg of a training workload: every step copies ITS batch host -> device from pinned memory (session.DeviceFeed:
+    the copy of batch k+1 overlaps step k) and reads ITS loss back (the host waits for the loss of the previous step while the
+    current one runs -- two pinned slots -- the way a training loop logs its metric without stalling the queue)."""
+    from ml_super_resolution_b200.session import DeviceFeed
+    feed = DeviceFeed(static_tensors)
+    slots = [torch.zeros_like(loss_dev, device="cpu").pin_memory() for _ in range(2)]
+    evs = [torch.cuda.Event() for _ in range(2)]
+    loss_h = torch.zeros_like(slots[0])
+    i_ = [0]
+    feed.put(host_tensors)
+
+    def e2e_step():
+        i = i_[0]
+        i_[0] += 1
+        feed.take()
+        feed.put(host_tensors)  # the next step's batch starts copying now
+        run_step()
+        slots[i & 1].copy_(loss_dev, non_blocking=True)
+        evs[i & 1].record()
+        if i > 0:
+            evs[(i - 1) & 1].synchronize()
+            loss_h.copy_(slots[(i - 1) & 1])
+
+    def finalize():
+        evs[(i_[0] - 1) & 1].synchronize()
+        feed.take()  # (drain the one batch that was prefetched beyond the last step)
+
+    ms_e, _ = timed_steps(e2e_step, n_steps, 2, world, None, finalize=finalize)
+    return ms_e
+
+
 # ------------------------------------------------------------------------------------------------ ESPCN (headline)
 ESPCN_FLOP_PER_OUT_PIXEL = 5027.6  # SURVEY 8(d) cfg2, C = 1: 2 * (25*64 + 576*32 + 288*9) / 9
 
@@ -286,29 +318,8 @@ def vdsr_train_workload(args, rank, world):
                 "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": round(tf / pk["tf_sust"], 4), "traffic": None, "peak_source": pk["src"]}
     n_launch = launches_of(lambda: net.train_step(sd, hd, lr=5e-5, use_adam=True)) * args.steps  # same kernels the graphs replay
     sd_h, hd_h = sd.cpu().pin_memory(), hd.cpu().pin_memory()
-    loss_h = torch.zeros(2).pin_memory()
-
-    # every step: H2D of its batch from pinned memory, the step, D2H of its loss.  The host waits for the loss of the PREVIOUS
-    # step while the current one runs (two pinned loss slots), the way a training loop logs its metric without stalling the queue
-    loss_slots = [torch.zeros(2).pin_memory() for _ in range(2)]
-    loss_ev = [torch.cuda.Event() for _ in range(2)]
-    e2e_i = [0]
-
-    def e2e_step():
-        i = e2e_i[0]
-        e2e_i[0] += 1
-        sd.copy_(sd_h, non_blocking=True)  # host batch -> the graph's static input buffers
-        hd.copy_(hd_h, non_blocking=True)
-        loss_slots[i & 1].copy_(gstep(5e-5), non_blocking=True)  # device->host read of this step's loss
-        loss_ev[i & 1].record()
-        if i > 0:
-            loss_ev[(i - 1) & 1].synchronize()  # previous step's loss is on the host now
-            loss_h.copy_(loss_slots[(i - 1) & 1])
-
-    def e2e_finalize():
-        loss_ev[(e2e_i[0] - 1) & 1].synchronize()
-
-    ms_e, _ = timed_steps(e2e_step, max(2, args.steps // 2), 2, world, None, finalize=e2e_finalize)
+    loss_buf = net._train_bufs["loss"]
+    ms_e = train_e2e_leg([sd, hd], [sd_h, hd_h], step, loss_buf, max(2, args.steps // 2), world)
     e2e = {"value": round(TRAIN_BATCH * world * max(2, args.steps // 2) / ms_e * 1e3, 1), "unit": "patches/s",
            "h2d_bytes_per_step": 2 * sd_h.numel() * 4, "d2h_bytes_per_step": 4}
     # ---- the same step fed by the device-resident input pipeline (crop + flip + degrade from a uint8 image
@@ -479,13 +490,9 @@ def srcnn_train_workload(args, rank, world):
     hi_h = hi.cpu().pin_memory()
     loss_h = torch.zeros(1).pin_memory()
 
-    def e2e_step():
-        hi.copy_(hi_h, non_blocking=True)
-        loss_h.copy_(gstep(1e-3), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-
+    loss_dev = gstep(1e-3)
     ne = max(2, args.steps // 2)
-    ms_e, _ = timed_steps(e2e_step, ne, 2, world, None)
+    ms_e = train_e2e_leg([hi], [hi_h], lambda: gstep(1e-3), loss_dev, ne, world)
     e2e = {"value": round(SRCNN_BATCH * world * ne / ms_e * 1e3, 1), "unit": "patches/s", "h2d_bytes_per_step": hi_h.numel() * 4, "d2h_bytes_per_step": 4}
     cfg = {"workload": f"SRCNN 9-1-5 3x training (bicubic degrade, VALID convs, row-L2 loss, Adam), {SRCNN_BATCH} synthetic 33x33 Y patches/GPU",
            "global_batch": SRCNN_BATCH * world, "parallelism": f"replicas x{world}", "l2_policy": "working set ~40 MB < L2: a 3.7 GFLOP step is launch-bound, not memory-bound"}
@@ -560,16 +567,8 @@ def enet_train_workload(args, rank, world):
     sd_h, bq_h, hd_h = sd.cpu().pin_memory(), bq.cpu().pin_memory(), hd.cpu().pin_memory()
     loss_h = torch.zeros(1).pin_memory()
 
-    def e2e_step():
-        sd.copy_(sd_h, non_blocking=True)
-        bq.copy_(bq_h, non_blocking=True)
-        hd.copy_(hd_h, non_blocking=True)
-        step()
-        loss_h.copy_(loss, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-
     ne = max(2, args.steps // 2)
-    ms_e, _ = timed_steps(e2e_step, ne, 1, world, None)
+    ms_e = train_e2e_leg([sd, bq, hd], [sd_h, bq_h, hd_h], step, loss, ne, world)
     e2e = {"value": round(ENET_BATCH * world * ne / ms_e * 1e3, 1), "unit": "patches/s",
            "h2d_bytes_per_step": (sd_h.numel() + bq_h.numel() + hd_h.numel()) * 4, "d2h_bytes_per_step": 4}
     cfg = {"workload": f"EnhanceNet 4x generator forward+backward+Adam (MSE upstream gradient), {ENET_BATCH} synthetic 32x32->128x128 patches/GPU",

@@ -116,3 +116,54 @@ class Session:
             return None
 
         return rebuild(fetches)
+
+
+class DeviceFeed:
+    """Double-buffered host -> device feed of a training loop's batches into the STATIC input tensors of a graphed step
+    (`make_graphed_step`): the copy of batch k+1 from page-locked host memory runs on a side stream while step k computes; at the
+    start of step k+1 a device-to-device copy (microseconds) moves it into the static tensors.  What `feed_dict` does in the
+    reference's loop (vdsr/vdsr/experiment_train.py:140-160), without stalling the device on PCIe.
+
+        feed = DeviceFeed([sd_static, hd_static])
+        feed.put([sd_host, hd_host])          # prefetch the first batch
+        for batch in batches:                 # steady state
+            feed.take()                       # batch k is in the static tensors (ordered on the current stream)
+            feed.put(next_batch)              # batch k+1 starts copying in the background
+            step(lr)
+    """
+
+    def __init__(self, static_tensors):
+        import torch
+        self._torch = torch
+        self.static = list(static_tensors)
+        self.stage = [[torch.empty_like(t) for t in self.static] for _ in range(2)]
+        self.stream = torch.cuda.Stream()
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.taken = [None, None]
+        self.n_put = self.n_take = 0
+
+    def put(self, host_tensors) -> None:
+        assert self.n_put - self.n_take < 2, "DeviceFeed holds at most two batches"
+        torch = self._torch
+        k = self.n_put & 1
+        self.n_put += 1
+        with torch.cuda.stream(self.stream):
+            if self.taken[k] is not None:
+                self.stream.wait_event(self.taken[k])  # the device-to-device copy that last read this staging set is done
+            for dst, src in zip(self.stage[k], host_tensors):
+                src = src if isinstance(src, torch.Tensor) else torch.from_numpy(src)
+                dst.copy_(src, non_blocking=True)
+            self.ready[k].record(self.stream)
+
+    def take(self) -> None:
+        assert self.n_take < self.n_put, "DeviceFeed.take() without a batch"
+        torch = self._torch
+        k = self.n_take & 1
+        self.n_take += 1
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.ready[k])
+        for dst, src in zip(self.static, self.stage[k]):
+            dst.copy_(src, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.taken[k] = ev

@@ -229,3 +229,26 @@ def test_cfg5_enet_generator_forward(srk_ops):
     err = np.abs(got - ref).max()
     assert got.shape == (64, 128, 128, 3)
     assert err <= TOL_BF16, f"max-abs {err:.4f}"
+
+
+def test_device_feed_double_buffering(srk_ops):
+    """session.DeviceFeed: batches put from pinned host memory arrive in the static tensors in order, one take per put, while
+    the next batch is already copying (the feed_dict of the reference's training loop, vdsr/vdsr/experiment_train.py:140-160)."""
+    from ml_super_resolution_b200.session import DeviceFeed, pinned_empty
+    a, b = torch.zeros((4, 5, 5, 3), device="cuda"), torch.zeros((4, 7), device="cuda")
+    feed = DeviceFeed([a, b])
+    hosts = []
+    for k in range(5):
+        ha, hb = pinned_empty(a.shape), pinned_empty(b.shape)
+        ha[...] = k + 1
+        hb[...] = -(k + 1)
+        hosts.append((torch.from_numpy(ha), torch.from_numpy(hb)))
+    feed.put(hosts[0])
+    for k in range(5):
+        feed.take()
+        if k + 1 < 5:
+            feed.put(hosts[k + 1])
+        torch.cuda.current_stream().synchronize()
+        assert float(a.min()) == float(a.max()) == k + 1 and float(b.min()) == float(b.max()) == -(k + 1)
+    with pytest.raises(AssertionError):
+        feed.take()
