@@ -98,6 +98,8 @@ class VdsrNet:
         a = self.arena
         assert max_panel_w <= MAX_PANEL_W
         need_tiles = W > max_panel_w or (tile_rows is not None and H > tile_rows) or world > 1
+        if need_tiles and ops.conv_form(W).form == "strip":
+            max_panel_w = min(max_panel_w, 2 * ops.STRIP_W - 1)  # a panel plus its zero column fills at most two 126-pixel strips
         if out is None:
             out = torch.empty_like(sd)
         if not need_tiles:

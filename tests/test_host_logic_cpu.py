@@ -205,3 +205,18 @@ def test_enet_resample_tables_match_the_pinned_restatement():
         ks, b, k = resample_tables(i, o, interp)
         ks2, b2, k2 = O.pil_resample_coeffs(i, o, interp)
         assert ks == ks2 and np.array_equal(b, b2) and np.array_equal(k, k2)
+
+
+def test_strip_form_rule_matches_the_kernel_geometry():
+    """ops.strip_lanes / ops.conv_form mirror cs_geom / conv_strip_applicable of csrc/conv_strip.cu: 126-pixel strips for wide rows,
+    K images side by side (each with its zero column) for narrow ones; the strip form from 80 % lane occupancy, or when the row is
+    beyond the flat-stream kernel's 254 pixels."""
+    from ml_super_resolution_b200 import ops
+    assert ops.strip_lanes(41) == 1.0           # 3 x 42 lanes: VDSR's training patches
+    assert abs(ops.strip_lanes(32) - 99 / 126) < 1e-12
+    assert abs(ops.strip_lanes(128) - 129 / 252) < 1e-12
+    assert abs(ops.strip_lanes(242) - 243 / 252) < 1e-12
+    assert ops.strip_lanes(3840) > 0.98
+    form = lambda w: ops.conv_form(w).form  # noqa: E731
+    assert [form(w) for w in (41, 99, 100, 125, 128, 200, 242, 254, 300, 3840)] == ["flat", "flat", "strip", "strip", "flat", "flat", "strip", "flat", "strip", "strip"]
+    assert form("strip") == "strip" and form("flat") == "flat"

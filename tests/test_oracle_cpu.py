@@ -174,3 +174,38 @@ def test_pil_resize_restatement_is_pinned_against_pillow():
     s, b, h_ = O.enet_batch([hd], [(0, 0, 0)])
     assert np.array_equal(s[0], sd.astype(np.float32) / 127.5 - 1.0) and np.array_equal(b[0], bq.astype(np.float32) / 127.5 - 1.0)
     assert np.array_equal(h_[0], hd.astype(np.float32) / 127.5 - 1.0)
+
+
+def test_independent_library_cross_checks():
+    """More of the restatement pinned against independent implementations that ARE in this image (TensorFlow is not):
+    nearest-neighbour resize vs torch (TF1 legacy floor(dst * in / out) == torch 'nearest' for the integer factors the models use,
+    enet/enet/model_enet.py:78-80); the Keys cubic-convolution kernel with A = -0.75 in closed form at t = 0 and 1/2 and torch's
+    own bicubic kernel (also A = -0.75) at half-pixel taps; TF's Adam against torch.optim.Adam with epsilon -> 0, where the two
+    epsilon conventions coincide (moment and bias-correction arithmetic, vdsr/vdsr/model_vdsr.py:145-148); MSE against torch."""
+    import torch
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((2, 5, 7, 3)).astype(np.float32)
+    for f in (2, 4):
+        ours = O.resize_nearest_tf1(x, 5 * f, 7 * f)
+        ref = torch.nn.functional.interpolate(torch.from_numpy(x).permute(0, 3, 1, 2), scale_factor=f, mode="nearest").permute(0, 2, 3, 1).numpy()
+        assert np.array_equal(ours, ref)
+    T = O.BICUBIC_TABLE
+    assert T[0] == 1.0 and T[1] == 0.0                                                # t = 0: the sample itself
+    assert np.allclose([T[2 * 512 + 1], T[2 * 512]], [-0.09375, 0.59375], atol=1e-7)  # t = 1/2: Keys' kernel, A = -0.75
+    # torch's bicubic (align_corners=False, A = -0.75) samples a 2x upscale at t = 1/4, 3/4: the same table rows
+    imp = np.zeros((1, 1, 1, 9), np.float32)
+    imp[0, 0, 0, 4] = 1.0
+    up = torch.nn.functional.interpolate(torch.from_numpy(imp), size=(1, 18), mode="bicubic", align_corners=False).numpy()[0, 0, 0]
+    assert np.allclose(up[[5, 7, 9, 11]], [T[2 * 768 + 1], T[2 * 768], T[2 * 256], T[2 * 256 + 1]], atol=1e-6)  # distances 1.75, .75, .25, 1.25 from the impulse
+    w = rng.standard_normal(50).astype(np.float64)
+    tw = torch.nn.Parameter(torch.from_numpy(w.copy()))
+    opt = torch.optim.Adam([tw], lr=1e-3, betas=(0.9, 0.999), eps=1e-300)
+    m, v, ours_w = np.zeros_like(w), np.zeros_like(w), w.copy()
+    for t in range(1, 6):
+        g = rng.standard_normal(50)
+        tw.grad = torch.from_numpy(g.copy())
+        opt.step()
+        ours_w, m, v = O.adam_tf(ours_w, g, m, v, t, 1e-3, eps=1e-300, dtype=np.float64)
+        assert np.abs(ours_w - tw.detach().numpy()).max() < 1e-12
+    a, b = rng.standard_normal((2, 4, 4, 3)), rng.standard_normal((2, 4, 4, 3))
+    assert abs(O.mse_mean(a, b) - float(torch.nn.functional.mse_loss(torch.from_numpy(a), torch.from_numpy(b)))) < 1e-14
