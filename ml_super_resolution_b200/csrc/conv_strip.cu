@@ -52,6 +52,7 @@ static_assert(kCsSmem <= 227 * 1024, "shared-memory plan does not fit");
 
 constexpr int kCsMaxLayers = 20;
 constexpr int kCsMaxParts = 3;
+constexpr int kCsMaxGrid = 160;
 
 struct alignas(64) CsLayer {
   CUtensorMap map_in;   // FPA 4-D (make_tensor_map_fpa4), box {64, box_x_in, 1, K}
@@ -75,6 +76,8 @@ struct alignas(64) ConvStripParams {
                         // while part A's layer l drains, is stored and passes its grid barrier, the CTAs compute part B's layer l
   int part_g0[kCsMaxParts + 1];  // image groups [part_g0[q], part_g0[q+1]) belong to part q
   unsigned int* sync;   // grid-barrier counters (one per part), zeroed before the launch (n_layers > 1)
+  int use_bounds;       // single-part launches of short images: CTA b owns the units [bounds[b], bounds[b+1]) -- cut so that no CTA
+  int bounds[kCsMaxGrid + 1];  // straddles two images (every straddle costs two more apron rows on the critical path)
 };
 
 // Grid barrier between the layers of a chain: every epilogue set of every CTA adds one when its stores of the layer are
@@ -135,7 +138,9 @@ __global__ void __launch_bounds__(kCsThreads, 1) conv_strip_kernel(const __grid_
   if (threadIdx.x >= 64 && threadIdx.x < 64 + P) {  // this CTA's share of every part: an even cut of the part's unit range
     const int q = threadIdx.x - 64;
     const long long units = (long long)(p.part_g0[q + 1] - p.part_g0[q]) * p.strips * p.H;
-    ef_build_segments(s_tab + q * kEfTabInts, uint32_t((units * blockIdx.x) / gridDim.x), uint32_t((units * (blockIdx.x + 1)) / gridDim.x), p.H, 0, p.strips, 2);
+    const uint32_t u0 = p.use_bounds ? uint32_t(p.bounds[blockIdx.x]) : uint32_t((units * blockIdx.x) / gridDim.x);
+    const uint32_t u1 = p.use_bounds ? uint32_t(p.bounds[blockIdx.x + 1]) : uint32_t((units * (blockIdx.x + 1)) / gridDim.x);
+    ef_build_segments(s_tab + q * kEfTabInts, u0, u1, p.H, 0, p.strips, 2);
   }
   tc_fence_before();
   __syncthreads();
@@ -455,6 +460,20 @@ int launch_conv_strip_chain(srk_ctx* h, int n_layers, const void* const* x_fpa, 
     if (const char* e = std::getenv("SRK_STRIP_PARTS")) parts = std::max(1, std::min({std::atoi(e), kCsMaxParts, ng}));  // (measurement switch)
     p.parts = parts;
     for (int q = 0; q <= parts; ++q) p.part_g0[q] = g0 + int((long long)ng * q / parts);
+    // Short column walks (a few rows per CTA): give every walk a whole number of CTAs and cut it evenly, so that no CTA straddles
+    // two walks -- a straddling CTA pays the two apron rows twice and sets the launch's critical path (VDSR training: 83.0 k ->
+    // 89.4 k patches/s).
+    const int walks = ng * g.strips;
+    p.use_bounds = 0;
+    if (parts == 1 && grid <= kCsMaxGrid && walks <= grid && units / grid < 32) {
+      p.use_bounds = 1;
+      int b = 0;
+      p.bounds[0] = 0;
+      for (int wk = 0; wk < walks; ++wk) {
+        const int ctas = (grid * (wk + 1)) / walks - (grid * wk) / walks;  // >= 1
+        for (int c = 1; c <= ctas; ++c) p.bounds[++b] = wk * H + int((long long)H * c / ctas);
+      }
+    }
     if (n_layers > 1) SRK_CHECK_CUDA(cudaMemsetAsync(sync, 0, kCsMaxParts * sizeof(unsigned int), stream));
     SRK_CHECK_CUDA(launch_pdl(conv_strip_kernel, dim3(grid), dim3(kCsThreads), size_t(kCsSmem), stream, p));
   }
