@@ -237,16 +237,14 @@ class EnetGenerator:
         the weight re-pack -- into ONE CUDA graph: the ~130 launches of a step are latency-bound at 64 patches of 32x32.
         Returns `step(lr)`; new batches are copied INTO the static tensors before each call
         (reference: `session.run(g_trainer)` of enet/enet/experiment_train.py:100-130 with model_enet.py:336-341)."""
-        import math
         world = 1
         if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             world = torch.distributed.get_world_size(group)
         if world > 1:
             ops.comm_init(group)
         a = self.arena
-        lr_t = torch.zeros(1, dtype=torch.float32, device=self.device)
 
-        def body():
+        def body(lr_t):
             self.forward_backward(sd_static, bq_static, loss_head)
             if world > 1:
                 ops.allreduce_grads(a.g)
@@ -254,26 +252,12 @@ class EnetGenerator:
             self._tb["plan"].run(a.w)
             self.repack()
 
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):  # warm-up outside capture (allocations, kernel attributes, NCCL channels); lr_t == 0: no update
-            body()
-        torch.cuda.current_stream().wait_stream(side)
-        a.m.zero_()
-        a.v.zero_()
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            body()
-        feed = ops.PinnedScalarFeed()
-        t = [0]
+        gstep = ops.graph_training_step(body, a)
 
         def step(lr: float = 1e-4):
-            t[0] += 1
-            feed.push(lr * math.sqrt(1.0 - 0.999 ** t[0]) / (1.0 - 0.9 ** t[0]), lr_t)
-            graph.replay()
+            gstep(lr)
 
-        step.graph = graph
+        step.graph = gstep.graph
         return step
 
 

@@ -141,6 +141,36 @@ class EspcnNet:
         self.repack()
         return b["loss"]
 
+    def make_graphed_step(self, lr_static: torch.Tensor, hr_static: torch.Tensor, group=None):
+        """The Adam training step (forward, packed-space MSE, backward, data-parallel all-reduce, Adam, re-pack) captured into ONE
+        CUDA graph; returns `step(learning_rate) -> loss buffer`.  New batches are copied INTO the static tensors before each call
+        (reference loop: espcn/espcn/experiment_train.py:60-95 around model_espcn.py:64-96)."""
+        world = 1
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            world = torch.distributed.get_world_size(group)
+        if world > 1:
+            ops.comm_init(group)
+        a = self.arena
+        numel = float(hr_static.numel()) * world
+
+        def body(lr_t):
+            self.forward_backward(lr_static, hr_static, numel)
+            if world > 1:
+                ops.allreduce_grads(a.g)
+            ops.adam_step_dev(a.w, a.g, a.m, a.v, lr_t)
+            self._repack_train()
+            self.repack()
+
+        gstep = ops.graph_training_step(body, a)
+
+        def step(learning_rate: float):
+            self.step += 1
+            gstep(learning_rate)
+            return self._tb["loss"]
+
+        step.graph = gstep.graph
+        return step
+
     def _get_bufs(self, n, H, W):
         key = (n, H, W)
         if key not in self._bufs:

@@ -529,6 +529,36 @@ class PinnedScalarFeed:
         self.events[k] = ev
 
 
+def graph_training_step(body, arena, beta1: float = 0.9, beta2: float = 0.999):
+    """Capture `body(lr_t)` -- a whole training step: forward, loss, backward, (all-reduce,) `adam_step_dev(..., lr_t)`, re-pack --
+    into ONE CUDA graph and return `step(lr)`.  `lr_t` is a device scalar holding the bias-corrected Adam rate of the step being
+    replayed (fed through a PinnedScalarFeed ring, so the host may run many replays ahead).  The warm-up run outside capture
+    (allocations, kernel attributes, NCCL channels) runs with lr_t == 0 and the moments are cleared afterwards: no update."""
+    import math
+    lr_t = torch.zeros(1, dtype=torch.float32, device=arena.w.device)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        body(lr_t)
+    torch.cuda.current_stream().wait_stream(side)
+    arena.m.zero_()
+    arena.v.zero_()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        body(lr_t)
+    feed = PinnedScalarFeed()
+    t = [0]
+
+    def step(lr: float):
+        t[0] += 1
+        feed.push(lr * math.sqrt(1.0 - beta2 ** t[0]) / (1.0 - beta1 ** t[0]), lr_t)
+        graph.replay()
+
+    step.graph = graph
+    return step
+
+
 def sumsq_masked(w: torch.Tensor, mask: torch.Tensor | None, scale: float, out_accum: torch.Tensor) -> None:
     check(_ffi.lib().srk_sumsq_masked(handle(), _ptr(_f32(w)), _ptr(mask), w.numel(), scale, _ptr(out_accum), _stream()), "srk_sumsq_masked")
 

@@ -252,3 +252,53 @@ def test_device_feed_double_buffering(srk_ops):
         assert float(a.min()) == float(a.max()) == k + 1 and float(b.min()) == float(b.max()) == -(k + 1)
     with pytest.raises(AssertionError):
         feed.take()
+
+
+def test_espcn_and_enet_graphed_steps_equal_eager(srk_ops):
+    """ESPCN's and the EnhanceNet generator's training steps captured as one CUDA graph each (ops.graph_training_step) follow the
+    eager trajectories: same criterion as the VDSR test above (a stale Adam rate would shift every weight)."""
+    from ml_super_resolution_b200.enet.model_enet import EnetGenerator
+    from ml_super_resolution_b200.espcn.model_espcn import EspcnNet
+    lr = torch.from_numpy(OM.synthetic_images(61, 8, 17, 17, 3)).cuda()
+    hr = torch.from_numpy(OM.synthetic_images(62, 8, 17, 17, 27)).cuda()
+    params = _trained_like(OM.espcn_init(seed=4, scaling_factor=3, channels=3), scale=5.0)
+    eager, graphed = EspcnNet(params, 3, 3), EspcnNet(params, 3, 3)
+    for _ in range(8):
+        eager.train_step(lr, hr, 1e-3)
+    step = graphed.make_graphed_step(lr.clone(), hr.clone())
+    for _ in range(8):
+        loss = step(1e-3)
+    torch.cuda.synchronize()
+    d = (eager.arena.w - graphed.arena.w).abs()
+    assert float(d.mean()) <= 2e-5 and float(d.max()) <= 8 * 2e-3, (float(d.mean()), float(d.max()))
+    assert abs(float(loss) - float(eager._tb["loss"])) <= 1e-3 * abs(float(eager._tb["loss"])) + 1e-6
+    # EnhanceNet generator with an MSE loss head
+    gp = _trained_like(OM.enet_g_init(seed=8), scale=2.5)
+    sd = torch.from_numpy(OM.synthetic_images(63, 4, 16, 16, 3)).cuda()
+    bq = torch.from_numpy(OM.synthetic_images(64, 4, 64, 64, 3)).cuda()
+    hd = torch.from_numpy(OM.synthetic_images(65, 4, 64, 64, 3)).cuda()
+    nets = [EnetGenerator(gp), EnetGenerator(gp)]
+    heads = []
+    for net in nets:
+        dsr, l = torch.empty_like(hd), torch.zeros(1, device="cuda")
+
+        def head(sr, dsr=dsr, l=l):
+            l.zero_()
+            srk_ops.mse_fwd_bwd(sr, hd, l, dsr)
+            return dsr
+        heads.append(head)
+        net.arena.enable_training()
+    a = nets[0].arena
+    for t in range(1, 7):
+        nets[0].forward_backward(sd, bq, heads[0])
+        srk_ops.adam_step(a.w, a.g, a.m, a.v, 1e-4, t)
+        nets[0]._tb["plan"].run(a.w)
+        nets[0].repack()
+    gstep = nets[1].make_graphed_step(sd.clone(), bq.clone(), heads[1])
+    for _ in range(6):
+        gstep(1e-4)
+    torch.cuda.synchronize()
+    d = (nets[0].arena.w - nets[1].arena.w).abs()
+    # (fp32 atomics in the first / last-layer weight gradients flip the sign-like first Adam steps of near-zero gradients: measured
+    # mean |d| 5e-6; a stale rate -- 15..25 % off during these steps -- would give ~5e-5)
+    assert float(d.mean()) <= 1.5e-5 and float(d.max()) <= 6 * 2e-4, (float(d.mean()), float(d.max()))
