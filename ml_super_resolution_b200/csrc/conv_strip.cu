@@ -409,7 +409,6 @@ static CsGeom cs_geom(int W) {
 // AUTO form: strips wherever at least 80 % of the lanes carry pixels (3 x 42 lanes for 41-pixel patches, 242-pixel panels, whole
 // 4K rows); otherwise the flat stream, which has no such quantisation.
 bool conv_strip_applicable(srk_ctx*, int n_img, int /*H*/, int W) {
-  if (std::getenv("SRK_NO_STRIP") != nullptr) return false;  // (the environment switch is for A/B measurements)
   const CsGeom g = cs_geom(W);
   return (g.lanes >= 0.8 && n_img >= g.K) || W > 254;  // (rows wider than 254 pixels are beyond the flat stream's shared-memory ring)
 }
@@ -457,7 +456,6 @@ int launch_conv_strip_chain(srk_ctx* h, int n_layers, const void* const* x_fpa, 
     // short chains of small layers (a few rows per CTA and layer) are latency-bound at the grid barrier: two parts alternate
     int parts = 1;
     if (n_layers > 1 && ng >= 2 && units / grid < 24) parts = 2;
-    if (const char* e = std::getenv("SRK_STRIP_PARTS")) parts = std::max(1, std::min({std::atoi(e), kCsMaxParts, ng}));  // (measurement switch)
     p.parts = parts;
     for (int q = 0; q <= parts; ++q) p.part_g0[q] = g0 + int((long long)ng * q / parts);
     // Short column walks (a few rows per CTA): give every walk a whole number of CTAs and cut it evenly, so that no CTA straddles
