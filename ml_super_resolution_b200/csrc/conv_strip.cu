@@ -17,13 +17,24 @@
 //     of the ESPCN kernel does);
 //   * row v+2's slot is opened by an instruction against a block of ZERO weights (accumulate off), or by the split
 //     instruction itself when the row sits alone in it;
-//   * epilogue = tcgen05.ld -> bias -> ReLU -> bf16 -> swizzled st.shared -> one 3-D TMA store per row (clipped at the row end,
-//     so the strip that ends a row needs no special case; the zero pad column x = W is written as zero).
-// Input rows arrive by 3-D TMA ([image row][x][channel], out-of-range x = zero fill = the SAME padding; the row above the first
-// and below the last image row are the FPA's zero rows).
+//   * epilogue = tcgen05.ld -> bias -> ReLU -> [ReLU' mask of a saved activation: the data-gradient form] -> bf16 -> swizzled
+//     st.shared -> one TMA store per row (clipped at the row end, so the strip that ends a row needs no special case; the FPA's
+//     zero column x = W and the zero row above every image are written too: the output is a complete FPA).
+// Tiles are 4-D TMA boxes of the FPA ([image][image row][x][channel], out-of-range coordinates = zero fill = the SAME padding):
+//   * wide images: box {64, 128 x, 1 row, 1 image} at x = 126*strip - 1;
+//   * narrow images (2*(W+1) <= 126): K = 126 / (W+1) images SIDE BY SIDE in one tile, box {64, W+1, 1, K} at x = -1 -- each
+//     image's out-of-range column -1 is the zero separator its neighbour's right-hand tap reads (3 x 42 lanes for VDSR's 41-px
+//     training patches); the tile rows past K*(W+1) are never written and stay zero.
+// A launch may run a CHAIN of layers of one geometry (srk_conv_tc_chain): the (layer, part) phases form one continuous row
+// sequence -- ring / slot / phase counters simply continue -- with a grid barrier between layers (epilogue sets count their
+// completed TMA stores into a global counter, the producer polls it before the next layer's first load) and the weights
+// re-loaded while the barrier drains; small batches can be split into parts whose layers alternate, hiding one part's barrier
+// behind the other's work.  (Measured: not faster than PDL launches at the training shape; kept as an entry point.)
+// Short images: the host cuts the CTAs' unit ranges at image-group boundaries (`bounds`), since a CTA that straddles two
+// column walks pays the two apron rows twice.
 //
 // Warp roles (11 warps): 0..7 epilogue (two sets of four TMEM-quadrant warps taking rows alternately), 8 TMA producer,
-// 9 MMA issuer, 10 set-up (TMEM allocation, weights, zero block).
+// 9 MMA issuer, 10 set-up (TMEM allocation, weights of the current layer).
 #include <algorithm>
 #include <cstdlib>
 
