@@ -676,8 +676,25 @@ def dp_check(rank: int, world: int) -> dict:
     en.forward_fused(lrf, out=eo, rank=rank, world=world)
     dist.all_reduce(eo)
     esame = bool(torch.equal(eo, en.forward_fused(lrf)))
-    res = {"world": world, "grad_rel_err": err, "loss_rel_err": lerr, "replica_spread": spread, "tiled_equal": same, "espcn_bands_equal": esame}
-    assert err < 2e-3 and lerr < 1e-4 and spread == 0.0 and same and esame, res
+    # the graphed step with the exchange fused into Adam over NVLink peer memory (srk_allreduce_adam_step_dev) against the graphed
+    # step with the NCCL all-reduce: same trajectories (the two sum the ranks in different orders), replicas bit-identical
+    traj = {}
+    for fused in (True, False):
+        n3 = VdsrNet(params, L)
+        gs = n3.make_graphed_step(sd.clone(), hd.clone(), peer_exchange=fused)
+        for _ in range(4):
+            gs(1e-3)
+        torch.cuda.synchronize()
+        traj[fused] = (n3.arena.w.clone(), gs.fused_exchange)
+    wf = traj[True][0]
+    fmax, fmin = wf.clone(), wf.clone()
+    dist.all_reduce(fmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(fmin, op=dist.ReduceOp.MIN)
+    fspread = float((fmax - fmin).abs().max())
+    fdiff = float((wf - traj[False][0]).abs().mean())
+    res = {"world": world, "grad_rel_err": err, "loss_rel_err": lerr, "replica_spread": spread, "tiled_equal": same, "espcn_bands_equal": esame,
+           "fused_exchange": bool(traj[True][1]), "fused_replica_spread": fspread, "fused_vs_nccl_mean_abs": fdiff}
+    assert err < 2e-3 and lerr < 1e-4 and spread == 0.0 and same and esame and fspread == 0.0 and fdiff < 2e-5, res
     return res
 
 

@@ -253,6 +253,21 @@ int srk_comm_init(srk_handle_t h, const void* id128, int rank, int world);
 int srk_allreduce_grads(srk_handle_t h, float* flat, size_t n, srk_stream_t stream);
 int srk_comm_destroy(srk_handle_t h);
 
+/* The same exchange step FUSED with the optimiser over NVLink peer memory (csrc/peer_reduce.cu): one kernel per rank stages its
+ * gradient, meets its peers at per-slice flags in each other's memory, sums all ranks' gradients in rank order through the peer
+ * mappings and applies Adam -- no NCCL call, no separate pass over the summed gradient, replicas bit-identical.
+ *   srk_peer_alloc   allocates this rank's exchange region for `grad_elems` floats and returns its cudaIpcMemHandle (64 bytes)
+ *   srk_peer_open    after the ranks have all-gathered those handles (world x 64 bytes, rank-major): maps the peers' regions
+ *   srk_allreduce_adam_step_dev   g <- sum_r g_r, then the update of srk_adam_step_dev with it (same arguments); every rank
+ *                    must call it once per step with the same n; capturable in a CUDA graph (epochs live on the device)
+ *   srk_peer_close   unmaps and frees
+ * One process per GPU on one node, at most 8 ranks (extends `minimize`, vdsr/vdsr/model_vdsr.py:146-148). */
+int srk_peer_alloc(srk_handle_t h, size_t grad_elems, void* ipc_handle_out64);
+int srk_peer_open(srk_handle_t h, int rank, int world, const void* handles);
+int srk_allreduce_adam_step_dev(srk_handle_t h, float* w, float* g, float* m, float* v, size_t n, const float* lr_t_device, float beta1,
+                                float beta2, float eps, float weight_decay, const float* decay_mask, srk_stream_t stream);
+int srk_peer_close(srk_handle_t h);
+
 /* Weight gradient of a 3x3 64->64 layer on tensor cores: dW[u,v,ci,co] = sum_p x[p+(u-1)*Wp+(v-1)][ci]
  * * dy[p][co], dbias[co] = sum_p dy[p][co].  Split over CTAs along the pixel axis; every CTA stores its
  * partial [9*64*64+64] block into `workspace` and a second kernel sums the partials in a fixed order

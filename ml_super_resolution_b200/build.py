@@ -8,7 +8,7 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libsrk.so")
-SOURCES = ["api.cu", "conv_tc.cu", "conv_small.cu", "bandwidth.cu", "wgrad_tc.cu", "metrics.cu", "espcn_fused.cu", "espcn_fused_c1.cu", "espcn_fused_c3.cu", "collective.cu", "gemm_tc.cu", "f2_ops.cu", "conv_strip.cu"]
+SOURCES = ["api.cu", "conv_tc.cu", "conv_small.cu", "bandwidth.cu", "wgrad_tc.cu", "metrics.cu", "espcn_fused.cu", "espcn_fused_c1.cu", "espcn_fused_c3.cu", "collective.cu", "gemm_tc.cu", "f2_ops.cu", "conv_strip.cu", "peer_reduce.cu"]
 NVCC_FLAGS_COMPILE = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"] + os.environ.get("SRK_NVCC_EXTRA", "").split()
 NVCC_FLAGS_LINK = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"]
 

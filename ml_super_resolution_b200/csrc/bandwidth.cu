@@ -317,16 +317,8 @@ __global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ g, 
                             size_t n, float lr_t, const float* __restrict__ lr_t_dev, float b1, float b2, float eps, float wd,
                             const float* __restrict__ mask) {
   if (lr_t_dev) lr_t = __ldg(lr_t_dev);
-  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
-    float gi = g[i];
-    const float wi = w[i];
-    if (mask) gi = fmaf(wd * mask[i], wi, gi);
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    w[i] = wi - lr_t * mi / (sqrtf(vi) + eps);
-  }
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+    adam_update(w, m, v, i, g[i], lr_t, b1, b2, eps, wd, mask);
 }
 __global__ void momentum_clip_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ acc, size_t n, float lr,
                                      float mom, float cap, float wd, const float* __restrict__ mask) {

@@ -49,6 +49,7 @@ struct srk_ctx {
   int conv_form = 0;         // SRK_CONV_FORM_*: kernel form of the plain 3x3 64->64 layers (srk_set_conv_form)
   void* comm = nullptr;      // ncclComm_t once srk_comm_init has run (collective.cu)
   int comm_world = 1;
+  void* peer = nullptr;      // PeerState once srk_peer_alloc has run (peer_reduce.cu)
 };
 
 namespace srk {
@@ -148,6 +149,19 @@ int launch_conv_strip(srk_ctx* h, const void* x_fpa, const void* w_packed, const
                       const void* mask_src, cudaStream_t stream);
 
 #ifdef __CUDACC__
+// One element of tf.train.AdamOptimizer's update with the bias-corrected rate lr_t (TF's epsilon-hat form), optional masked l2
+// decay folded into the gradient first: shared by srk_adam_step(_dev) and the fused exchange + Adam kernel, with explicit
+// roundings so that both produce the same bits.
+__device__ __forceinline__ void adam_update(float* w, float* m, float* v, size_t i, float gi, float lr_t, float b1, float b2, float eps, float wd,
+                                            const float* mask) {
+  const float wi = w[i];
+  if (mask) gi = __fmaf_rn(__fmul_rn(wd, mask[i]), wi, gi);
+  const float mi = __fmaf_rn(b1, m[i], __fmul_rn(1.f - b1, gi));
+  const float vi = __fmaf_rn(b2, v[i], __fmul_rn(__fmul_rn(1.f - b2, gi), gi));
+  m[i] = mi;
+  v[i] = vi;
+  w[i] = __fsub_rn(wi, __fdiv_rn(__fmul_rn(lr_t, mi), __fadd_rn(sqrtf(vi), eps)));
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif

@@ -506,6 +506,39 @@ def allreduce_grads(flat: torch.Tensor) -> None:
     check(_ffi.lib().srk_allreduce_grads(handle(), _ptr(_f32(flat)), flat.numel(), _stream()), "srk_allreduce_grads")
 
 
+_peer_ready: dict = {}
+
+
+def peer_init(grad_elems: int, group=None) -> bool:
+    """Set up the NVLink peer-memory exchange of this rank's handle for a flat gradient arena of `grad_elems` floats
+    (srk_peer_alloc / srk_peer_open): every rank allocates its region, the 64-byte IPC handles travel through torch.distributed
+    (any backend).  Returns False (and leaves the NCCL path in charge) when the ranks are not one process per GPU of one node or
+    number more than 8."""
+    import torch.distributed as dist
+    dev = torch.cuda.current_device()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    key = (dev, world)
+    if _peer_ready.get(key, 0) >= grad_elems:
+        return True
+    if world > 8:
+        return False
+    buf = (C.c_char * 64)()
+    check(_ffi.lib().srk_peer_alloc(handle(), grad_elems, buf), "srk_peer_alloc")
+    handles = [None] * world
+    dist.all_gather_object(handles, bytes(buf), group=group)
+    blob = (C.c_char * (64 * world))(*b"".join(handles))
+    check(_ffi.lib().srk_peer_open(handle(), rank, world, blob), "srk_peer_open")
+    _peer_ready[key] = grad_elems
+    return True
+
+
+def allreduce_adam_step_dev(w, g, m, v, lr_t_dev: torch.Tensor, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, decay_mask=None) -> None:
+    """g <- sum over ranks of g (rank order, over NVLink peer memory), then Adam with the device-resident rate: ONE kernel
+    (srk_allreduce_adam_step_dev; graph-capturable).  Needs peer_init()."""
+    check(_ffi.lib().srk_allreduce_adam_step_dev(handle(), _ptr(_f32(w)), _ptr(_f32(g)), _ptr(m), _ptr(v), w.numel(), _ptr(_f32(lr_t_dev)), beta1,
+                                                 beta2, eps, weight_decay, _ptr(decay_mask), _stream()), "srk_allreduce_adam_step_dev")
+
+
 class PinnedScalarFeed:
     """Feeds one host-computed fp32 scalar per step (the bias-corrected Adam rate) into device memory without a host sync.
     The copy reads pinned memory when the GPU EXECUTES it, not when it is queued, and with graph replay the host runs several

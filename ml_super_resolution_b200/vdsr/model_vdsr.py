@@ -251,39 +251,47 @@ class VdsrNet:
         self.apply_gradients(lr, use_adam)
         return b["loss"].sum()
 
-    def make_graphed_step(self, sd_static: torch.Tensor, hd_static: torch.Tensor, group=None):
+    def make_graphed_step(self, sd_static: torch.Tensor, hd_static: torch.Tensor, group=None, peer_exchange: bool = True):
         """Capture the Adam training step into CUDA graphs (the ~85 launches of a step are latency-bound at
         64 patches of 41x41).  Returns `step(lr) -> loss buffer [mse, reg]`; new batches are copied INTO
-        `sd_static` / `hd_static` before each call.  ONE graph holds forward + loss + backward, the NCCL gradient
-        all-reduce (srk_allreduce_grads, captured like any other kernel: no host round trip between backward and
-        optimiser) and Adam (learning rate read from device memory, so the same graph serves every step) + re-pack."""
+        `sd_static` / `hd_static` before each call.  ONE graph holds forward + loss + backward, the data-parallel exchange
+        step and Adam (learning rate read from device memory, so the same graph serves every step) + re-pack.  The exchange is
+        fused with Adam over NVLink peer memory (srk_allreduce_adam_step_dev: every rank sums all ranks' gradients through the peer
+        mappings and updates its replica in one kernel; `peer_exchange=False` keeps the NCCL all-reduce of srk_allreduce_grads)."""
         world = 1
         if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             world = torch.distributed.get_world_size(group)
         numel_total = float(sd_static.numel()) * world
-        if world > 1:
-            ops.comm_init(group)
         a = self.arena
+        # the exchange step: fused with Adam over NVLink peer memory (srk_allreduce_adam_step_dev: one kernel, no NCCL call) where
+        # the ranks are peers of one node; NCCL all-reduce + Adam otherwise
+        fused = world > 1 and peer_exchange and ops.peer_init(a.w.numel(), group)
+        if world > 1 and not fused:
+            ops.comm_init(group)
+
+        def exchange_and_update(lr_t):
+            if fused:
+                ops.allreduce_adam_step_dev(a.w, a.g, a.m, a.v, lr_t, weight_decay=WEIGHT_DECAY, decay_mask=a.decay_mask)
+            else:
+                if world > 1:
+                    ops.allreduce_grads(a.g)
+                ops.adam_step_dev(a.w, a.g, a.m, a.v, lr_t, weight_decay=WEIGHT_DECAY, decay_mask=a.decay_mask)
+
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):  # warm-up outside capture: allocates buffers, sets kernel attributes
+        with torch.cuda.stream(side):  # warm-up outside capture: allocates buffers, sets kernel attributes, NCCL sets up its channels
             self.forward_backward(sd_static, hd_static, numel_total)
             b = self._train_bufs
-            ops.adam_step_dev(a.w, a.g, a.m, a.v, b["lr_t"], weight_decay=WEIGHT_DECAY, decay_mask=a.decay_mask)  # lr_t == 0: no-op update
+            exchange_and_update(b["lr_t"])  # lr_t == 0: no-op update
             self.repack()
         torch.cuda.current_stream().wait_stream(side)
         a.m.zero_()
         a.v.zero_()
         torch.cuda.synchronize()
-        if world > 1:
-            ops.allreduce_grads(a.g)  # first collective outside capture: NCCL sets up its channels here
-            torch.cuda.synchronize()
         g_step = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g_step):
             self.forward_backward(sd_static, hd_static, numel_total)
-            if world > 1:
-                ops.allreduce_grads(a.g)
-            ops.adam_step_dev(a.w, a.g, a.m, a.v, b["lr_t"], weight_decay=WEIGHT_DECAY, decay_mask=a.decay_mask)
+            exchange_and_update(b["lr_t"])
             self.repack()
         lr_feed = ops.PinnedScalarFeed()
 
@@ -294,6 +302,7 @@ class VdsrNet:
             return b["loss"]
 
         step.graphs = (g_step,)
+        step.fused_exchange = bool(fused)
         return step
 
     @staticmethod

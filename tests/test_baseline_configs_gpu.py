@@ -302,3 +302,33 @@ def test_espcn_and_enet_graphed_steps_equal_eager(srk_ops):
     # (fp32 atomics in the first / last-layer weight gradients flip the sign-like first Adam steps of near-zero gradients: measured
     # mean |d| 5e-6; a stale rate -- 15..25 % off during these steps -- would give ~5e-5)
     assert float(d.mean()) <= 1.5e-5 and float(d.max()) <= 6 * 2e-4, (float(d.mean()), float(d.max()))
+
+
+def test_fused_exchange_adam_kernel_single_rank(srk_ops):
+    """srk_allreduce_adam_step_dev with a world of one rank (the staging / flag machinery runs, there is nobody to wait for) ==
+    srk_adam_step_dev, bit for bit, over several steps and a size that is not a multiple of 4; g keeps the (summed) gradient.
+    The multi-rank behaviour is checked by bench.py's dp_check on real GPUs (fused_replica_spread, fused_vs_nccl_mean_abs)."""
+    import ctypes as C
+    from ml_super_resolution_b200 import _ffi
+    from ml_super_resolution_b200._ffi import check
+    n = 100003
+    g0 = torch.Generator(device="cuda").manual_seed(1)
+    w = torch.randn(n, device="cuda", generator=g0)
+    mask = (torch.rand(n, device="cuda", generator=g0) > 0.5).float()
+    lr_t = torch.full((1,), 3e-4, device="cuda")
+    h = srk_ops.handle()
+    buf = (C.c_char * 64)()
+    check(_ffi.lib().srk_peer_alloc(h, n, buf), "srk_peer_alloc")
+    check(_ffi.lib().srk_peer_open(h, 0, 1, buf), "srk_peer_open")
+    try:
+        wa, wb = w.clone(), w.clone()
+        ma, va, mb, vb = (torch.zeros(n, device="cuda") for _ in range(4))
+        for _ in range(5):
+            g = torch.randn(n, device="cuda", generator=g0)
+            ga, gb = g.clone(), g.clone()
+            srk_ops.adam_step_dev(wa, ga, ma, va, lr_t, weight_decay=1e-4, decay_mask=mask)
+            srk_ops.allreduce_adam_step_dev(wb, gb, mb, vb, lr_t, weight_decay=1e-4, decay_mask=mask)
+            assert torch.equal(gb, g)
+        assert torch.equal(wa, wb) and torch.equal(ma, mb) and torch.equal(va, vb)
+    finally:
+        check(_ffi.lib().srk_peer_close(h), "srk_peer_close")
