@@ -237,18 +237,13 @@ class EnetGenerator:
         the weight re-pack -- into ONE CUDA graph: the ~130 launches of a step are latency-bound at 64 patches of 32x32.
         Returns `step(lr)`; new batches are copied INTO the static tensors before each call
         (reference: `session.run(g_trainer)` of enet/enet/experiment_train.py:100-130 with model_enet.py:336-341)."""
-        world = 1
-        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            world = torch.distributed.get_world_size(group)
-        if world > 1:
-            ops.comm_init(group)
         a = self.arena
+        a.enable_training()
+        update, _ = ops.make_exchange_and_adam(a, group)  # fused exchange + Adam over NVLink peer memory, or NCCL + Adam
 
         def body(lr_t):
             self.forward_backward(sd_static, bq_static, loss_head)
-            if world > 1:
-                ops.allreduce_grads(a.g)
-            ops.adam_step_dev(a.w, a.g, a.m, a.v, lr_t)
+            update(lr_t)
             self._tb["plan"].run(a.w)
             self.repack()
 

@@ -148,16 +148,14 @@ class EspcnNet:
         world = 1
         if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             world = torch.distributed.get_world_size(group)
-        if world > 1:
-            ops.comm_init(group)
         a = self.arena
+        a.enable_training()
         numel = float(hr_static.numel()) * world
+        update, _ = ops.make_exchange_and_adam(a, group)  # fused exchange + Adam over NVLink peer memory, or NCCL + Adam
 
         def body(lr_t):
             self.forward_backward(lr_static, hr_static, numel)
-            if world > 1:
-                ops.allreduce_grads(a.g)
-            ops.adam_step_dev(a.w, a.g, a.m, a.v, lr_t)
+            update(lr_t)
             self._repack_train()
             self.repack()
 

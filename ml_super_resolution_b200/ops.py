@@ -522,6 +522,12 @@ def peer_init(grad_elems: int, group=None) -> bool:
         return True
     if world > 8:
         return False
+    if key in _peer_ready:  # a larger arena than the region holds: every rank drains its work on the old mappings first
+        torch.cuda.synchronize()
+        dist.barrier(group)
+        check(_ffi.lib().srk_peer_close(handle()), "srk_peer_close")
+        dist.barrier(group)
+    grad_elems = max(int(grad_elems), 1 << 22)  # (16 MB per staging buffer: every model of this repository fits without a re-allocation)
     buf = (C.c_char * 64)()
     check(_ffi.lib().srk_peer_alloc(handle(), grad_elems, buf), "srk_peer_alloc")
     handles = [None] * world
@@ -537,6 +543,28 @@ def allreduce_adam_step_dev(w, g, m, v, lr_t_dev: torch.Tensor, beta1=0.9, beta2
     (srk_allreduce_adam_step_dev; graph-capturable).  Needs peer_init()."""
     check(_ffi.lib().srk_allreduce_adam_step_dev(handle(), _ptr(_f32(w)), _ptr(_f32(g)), _ptr(m), _ptr(v), w.numel(), _ptr(_f32(lr_t_dev)), beta1,
                                                  beta2, eps, weight_decay, _ptr(decay_mask), _stream()), "srk_allreduce_adam_step_dev")
+
+
+def make_exchange_and_adam(arena, group=None, peer_exchange: bool = True, weight_decay: float = 0.0, decay_mask=None):
+    """The data-parallel exchange + Adam update of a graphed training step as one callable `f(lr_t_dev)`: fused over NVLink peer
+    memory (allreduce_adam_step_dev) when the ranks are peers of one node, NCCL all-reduce + Adam otherwise, plain Adam for a
+    single rank.  Returns (f, fused)."""
+    world = 1
+    if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        world = torch.distributed.get_world_size(group)
+    fused = world > 1 and peer_exchange and peer_init(arena.w.numel(), group)
+    if world > 1 and not fused:
+        comm_init(group)
+
+    def f(lr_t):
+        if fused:
+            allreduce_adam_step_dev(arena.w, arena.g, arena.m, arena.v, lr_t, weight_decay=weight_decay, decay_mask=decay_mask)
+        else:
+            if world > 1:
+                allreduce_grads(arena.g)
+            adam_step_dev(arena.w, arena.g, arena.m, arena.v, lr_t, weight_decay=weight_decay, decay_mask=decay_mask)
+
+    return f, bool(fused)
 
 
 class PinnedScalarFeed:
