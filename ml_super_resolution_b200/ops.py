@@ -529,11 +529,21 @@ def peer_init(grad_elems: int, group=None) -> bool:
         dist.barrier(group)
     grad_elems = max(int(grad_elems), 1 << 22)  # (16 MB per staging buffer: every model of this repository fits without a re-allocation)
     buf = (C.c_char * 64)()
-    check(_ffi.lib().srk_peer_alloc(handle(), grad_elems, buf), "srk_peer_alloc")
+    ok = _ffi.lib().srk_peer_alloc(handle(), grad_elems, buf) == 0
     handles = [None] * world
-    dist.all_gather_object(handles, bytes(buf), group=group)
-    blob = (C.c_char * (64 * world))(*b"".join(handles))
-    check(_ffi.lib().srk_peer_open(handle(), rank, world, blob), "srk_peer_open")
+    dist.all_gather_object(handles, bytes(buf) if ok else None, group=group)
+    if ok and all(h is not None for h in handles):
+        blob = (C.c_char * (64 * world))(*b"".join(handles))
+        ok = _ffi.lib().srk_peer_open(handle(), rank, world, blob) == 0
+    else:
+        ok = False
+    # the ranks must agree: one that could not map a peer (no IPC between these processes) sends everybody to the NCCL form
+    oks = [None] * world
+    dist.all_gather_object(oks, bool(ok), group=group)
+    if not all(oks):
+        _ffi.lib().srk_peer_close(handle())
+        _peer_ready.pop(key, None)
+        return False
     _peer_ready[key] = grad_elems
     return True
 
