@@ -269,6 +269,12 @@ def espcn_workload(args, rank, world):
     out_u8, out_f32 = pinned_empty(out.shape, "uint8"), pinned_empty(out.shape, "float32")
     sess = Session()
 
+    lr_raw = pinned_empty(lr.shape, "uint8")  # the image as the driver reads it from disk (experiment_test.py:154-159), before `/ 127.5 - 1.0`
+    lr_raw[...] = np.clip(np.rint((lr_host + 1.0) * 127.5), 0, 255).astype(np.uint8)
+
+    def e2e_raw():  # uint8 frames in (normalised on the device, bit-identical to the host arithmetic), uint8 frames out
+        sess.run(model["hr_images_u8"], feed_dict={model["lr_source_u8"]: lr_raw}, out={model["hr_images_u8"]: out_u8})
+
     def e2e_u8():
         sess.run(model["hr_images_u8"], feed_dict={lr_ph: lr_host}, out={model["hr_images_u8"]: out_u8})
 
@@ -276,11 +282,15 @@ def espcn_workload(args, rank, world):
         sess.run(model["hr_images"], feed_dict={lr_ph: lr_host}, out={model["hr_images"]: out_f32})
 
     n_e2e = max(4, args.steps // 2)
+    ms_raw, _ = timed_steps(e2e_raw, n_e2e, 2, world, None)
     ms_u8, _ = timed_steps(e2e_u8, n_e2e, 2, world, None)
     ms_f32, _ = timed_steps(e2e_f32, max(2, n_e2e // 4), 1, world, None)
-    e2e = {"value": round(out_pix * world * n_e2e / ms_u8 / 1e3, 1), "unit": "output Mpix/s", "h2d_bytes_per_step": lr_host.size * 4,
-           "d2h_bytes_per_step": out_u8.size, "form": "uint8 (saturate_cast, as the reference's PNG hand-off)",
-           "fp32_form": {"value": round(out_pix * world * max(2, n_e2e // 4) / ms_f32 / 1e3, 1), "d2h_bytes_per_step": out_f32.size * 4},
+    e2e = {"value": round(out_pix * world * n_e2e / ms_raw / 1e3, 1), "unit": "output Mpix/s", "h2d_bytes_per_step": lr_raw.size,
+           "d2h_bytes_per_step": out_u8.size,
+           "form": "uint8 frames in (the decoded image, normalised on the device as experiment_test.py:159 does on the host), uint8 frames out "
+                   "(saturate_cast, the PNG hand-off of :179-184)",
+           "fp32_in_u8_out_form": {"value": round(out_pix * world * n_e2e / ms_u8 / 1e3, 1), "h2d_bytes_per_step": lr_host.size * 4, "d2h_bytes_per_step": out_u8.size},
+           "fp32_form": {"value": round(out_pix * world * max(2, n_e2e // 4) / ms_f32 / 1e3, 1), "h2d_bytes_per_step": lr_host.size * 4, "d2h_bytes_per_step": out_f32.size * 4},
            "note": "Session.run on pinned host arrays: per call, row bands of each frame pipeline H2D / fused kernel / D2H on three streams; the call returns when the last band is on the host"}
     cfg = {"workload": f"ESPCN 3x (5x5-64 tanh, 3x3-32 tanh, 3x3-9 + pixel shuffle) inference, {FRAMES_PER_STEP} synthetic 1920x1080 Y frames/step/GPU, ONE fused kernel per step",
            "frames_per_step_per_gpu": FRAMES_PER_STEP, "lr_shape": [LR_H, LR_W, C], "scale": SCALE,

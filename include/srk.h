@@ -187,6 +187,18 @@ typedef struct {
 int srk_espcn_forward(srk_handle_t h, const srk_espcn_net* net, const float* lr, int n, int H, int W, int y_begin,
                       int y_end, int shuffle, int out_kind, void* out, srk_stream_t stream);
 
+/* The same, HOST array in, HOST array out -- `session.run(model['sr_results'], feed_dict={lr_sources: frames})` of
+ * espcn/espcn/experiment_test.py:164-169 plus the un-pack / uint8 conversion of :173-184 -- with the copies hidden: every frame
+ * is cut into bands of `band_rows` LR rows, and the host->device copy of band k+1, the fused kernel on band k and the device->host
+ * copy of band k-1 run on three streams; the call returns when the last band is in `out_host`.  lr_host / out_host should be
+ * page-locked (pageable memory works, without overlap).  lr_is_u8 != 0: `lr_host` is the decoded uint8 image; it crosses PCIe at
+ * one byte per sample and `image / 127.5 - 1.0` (:159) runs on the device (srk_u8_to_pm1_f64) into lr_dev.  lr_dev (fp32
+ * [n,H,W,C]), lr_u8_dev (uint8, only for lr_is_u8) and out_dev (the result's shape and type) are device scratch owned by the
+ * caller.  `stream`: the compute stream (weights must be ready on it). */
+int srk_espcn_forward_host(srk_handle_t h, const srk_espcn_net* net, const void* lr_host, int lr_is_u8, int n, int H, int W, int shuffle,
+                           int out_kind, void* out_host, float* lr_dev, uint8_t* lr_u8_dev, void* out_dev, int band_rows,
+                           srk_stream_t stream);
+
 /* ---- generic tensor-core GEMM and the layers built on it (csrc/gemm_tc.cu, csrc/f2_ops.cu) ------------------------------
  * D[b][M][N] = act(A[b][M][K] x B[b][N][K]^T + bias[N]): both operands row-major with K contiguous (leading dimensions lda / ldb
  * and batch strides in ELEMENTS; rows must start on 16-byte boundaries), in_dtype SRK_DT_BF16 or SRK_DT_TF32 (fp32 storage,
@@ -344,6 +356,11 @@ int srk_resample_u8(srk_handle_t h, const uint8_t* x, int n, int H, int W, int C
                     const int32_t* kx, const int32_t* bx, int ksx, const int32_t* ky, const int32_t* by, int ksy,
                     uint8_t* tmp, uint8_t* y, srk_stream_t stream);
 int srk_u8_to_pm1(srk_handle_t h, const uint8_t* x, size_t n, float* y, srk_stream_t stream);
+/* uint8 -> float32 as numpy computes `image / 127.5 - 1.0` in float64 before the feed casts it to float32
+ * (espcn/espcn/experiment_test.py:159,164; vdsr/vdsr/experiment_resolve.py likewise): the raw image crosses PCIe at one byte per
+ * sample and is normalised on the device, bit-identical to the host arithmetic (srk_u8_to_pm1 is the float32 form of
+ * enet/enet/datasets.py:114-116: one ulp apart for half of the 256 values). */
+int srk_u8_to_pm1_f64(srk_handle_t h, const uint8_t* x, size_t n, float* y, srk_stream_t stream);
 
 /* VDSR degrade pre-pass: gaussian(sigma=0.5(s-1), replicate) -> bilinear down to int(H/s) x int(W/s)
  * -> bilinear up (half-pixel, edge clamp), per-sample scale: vdsr/vdsr/dataset.py:13-38. */

@@ -44,6 +44,7 @@ SIGNATURES = {
     "srk_destroy": (_I, [_P]),
     "srk_num_sms": (_I, [_P]),
     "srk_set_conv_form": (_I, [_P, _I]),
+    "srk_espcn_forward_host": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
     "srk_peer_alloc": (_I, [_P, _SZ, _P]),
     "srk_peer_open": (_I, [_P, _I, _I, _P]),
     "srk_allreduce_adam_step_dev": (_I, [_P, _P, _P, _P, _P, _SZ, _P, _F, _F, _F, _F, _P, _P]),
@@ -83,6 +84,7 @@ SIGNATURES = {
     "srk_crop_u8": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "srk_resample_u8": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P, _P]),
     "srk_u8_to_pm1": (_I, [_P, _P, _SZ, _P, _P]),
+    "srk_u8_to_pm1_f64": (_I, [_P, _P, _SZ, _P, _P]),
     "srk_crop_flip_u8": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "srk_affine_f32": (_I, [_P, _P, _SZ, _F, _F, _P, _P]),
     "srk_gemm_tc": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I64, _I64, _I64, _I64, _I64, _I64, _P, _I, _F, _I, _I, _P]),

@@ -193,6 +193,13 @@ __global__ void __launch_bounds__(256) u8_to_pm1_kernel(const uint8_t* __restric
     y[i] = __fadd_rn(__fdiv_rn(float(x[i]), 127.5f), -1.f);  // x.astype(float32) / 127.5 - 1.0
 }
 
+// numpy's `uint8_image / 127.5 - 1.0` (float64 arithmetic) handed to a float32 placeholder: espcn/espcn/experiment_test.py:159 + :164.
+// Half of the 256 values differ by one ulp from the float32 arithmetic of u8_to_pm1_kernel, so this form computes in double too.
+__global__ void __launch_bounds__(256) u8_to_pm1_f64_kernel(const uint8_t* __restrict__ x, size_t n, float* __restrict__ y) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+    y[i] = float(__dadd_rn(__ddiv_rn(double(x[i]), 127.5), -1.0));
+}
+
 static inline int grid1(srk_ctx* h, int64_t items, int block, int per_sm) {
   const int64_t g = (items + block - 1) / block;
   const int64_t cap = int64_t(h->num_sms) * per_sm;
@@ -291,6 +298,15 @@ extern "C" int srk_crop_u8(srk_handle_t h, const uint8_t* pool, const srk_pool_i
   SRK_REQUIRE(h && pool && images_device && crops_device && out && n > 0 && S > 0 && C > 0, "srk_crop_u8: bad argument");
   if (int rc_dev = check_device(h)) return rc_dev;
   crop_u8_kernel<<<grid1(h, int64_t(n) * S * S * C, 256, 16), 256, 0, as_stream(stream)>>>(pool, images_device, crops_device, n, S, C, out);
+  SRK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int srk_u8_to_pm1_f64(srk_handle_t h, const uint8_t* x, size_t n, float* y, srk_stream_t stream) {
+  SRK_REQUIRE(h && x && y, "srk_u8_to_pm1_f64: null argument");
+  if (int rc_dev = check_device(h)) return rc_dev;
+  if (n == 0) return 0;
+  u8_to_pm1_f64_kernel<<<grid1(h, int64_t(n), 256, 16), 256, 0, as_stream(stream)>>>(x, n, y);
   SRK_LAUNCH_CHECK();
   return 0;
 }

@@ -50,6 +50,7 @@ struct srk_ctx {
   void* comm = nullptr;      // ncclComm_t once srk_comm_init has run (collective.cu)
   int comm_world = 1;
   void* peer = nullptr;      // PeerState once srk_peer_alloc has run (peer_reduce.cu)
+  void* host_pipe = nullptr; // copy streams + events of srk_espcn_forward_host (espcn_fused.cu)
 };
 
 namespace srk {

@@ -197,10 +197,11 @@ class EspcnNet:
             oshape = (n, H * r, W * r, C) if shuffle else (n, H, W, self.cout3)
             odt = torch.uint8 if uint8 else torch.float32
             st = {"key": key, "lr_dev": torch.empty((n, H, W, C), dtype=torch.float32, device=self.device),
+                  "lr_u8_dev": torch.empty((n, H, W, C), dtype=torch.uint8, device=self.device),
+                  "lr_u8_pin": torch.empty((n, H, W, C), dtype=torch.uint8).pin_memory(),
                   "out_dev": torch.empty(oshape, dtype=odt, device=self.device),
                   "lr_pin": torch.empty((n, H, W, C), dtype=torch.float32).pin_memory(),
-                  "out_pin": torch.empty(oshape, dtype=odt).pin_memory(),
-                  "s_in": torch.cuda.Stream(), "s_out": torch.cuda.Stream()}
+                  "out_pin": torch.empty(oshape, dtype=odt).pin_memory()}
             self._hs = st
         return st
 
@@ -212,13 +213,21 @@ class EspcnNet:
         `pinned_like()` returns) are used in place, pageable ones go through a pinned staging copy.  uint8=True returns
         saturate_cast(x * 127.5 + 127.5) as the reference's PNG writer does (:179-184).  Returns `out_host` (or a staging
         buffer that the next call overwrites when none was given)."""
-        lr_t = lr_host if isinstance(lr_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(lr_host, dtype=np.float32))
+        if isinstance(lr_host, torch.Tensor):
+            lr_t = lr_host
+        else:
+            lr_host = np.asarray(lr_host)
+            lr_t = torch.from_numpy(np.ascontiguousarray(lr_host, dtype=np.uint8 if lr_host.dtype == np.uint8 else np.float32))
         n, H, W, C = lr_t.shape
-        assert C == self.C and lr_t.dtype == torch.float32 and lr_t.is_contiguous()
+        # a uint8 frame is the RAW image: it crosses PCIe at one byte per sample and the drivers' `image / 127.5 - 1.0`
+        # (experiment_test.py:159) runs on the device (srk_u8_to_pm1_f64: bit-identical to the host arithmetic)
+        raw = lr_t.dtype == torch.uint8
+        assert C == self.C and (raw or lr_t.dtype == torch.float32) and lr_t.is_contiguous()
         st = self._host_state(n, H, W, shuffle, uint8)
         if not lr_t.is_pinned():
-            st["lr_pin"].copy_(lr_t)
-            lr_t = st["lr_pin"]
+            pin = st["lr_u8_pin"] if raw else st["lr_pin"]
+            pin.copy_(lr_t)
+            lr_t = pin
         out_t = st["out_pin"]
         user_out = None
         if out_host is not None:
@@ -228,32 +237,9 @@ class EspcnNet:
                 out_t = cand
             else:
                 user_out = cand
-        lr_dev, out_dev, s_in, s_out = st["lr_dev"], st["out_dev"], st["s_in"], st["s_out"]
-        s_c = torch.cuda.current_stream()
-        s_in.wait_stream(s_c)
-        s_out.wait_stream(s_c)
-        a, V, r = self.arena, self.plan.views, (self.r if shuffle else 1)
-        bands = [(f, y0, min(H, y0 + band_rows)) for f in range(n) for y0 in range(0, H, band_rows)]
-        copied = {}  # frame -> input rows already on the device
-        ev_prev_out = None
-        for f, y0, y1 in bands:
-            need = min(H, y1 + HALO)
-            have = copied.get(f, 0)
-            with torch.cuda.stream(s_in):
-                if need > have:
-                    lr_dev[f, have:need].copy_(lr_t[f, have:need], non_blocking=True)
-                    copied[f] = need
-                ev_in = torch.cuda.Event()
-                ev_in.record(s_in)
-            s_c.wait_event(ev_in)
-            ops.espcn_forward(lr_dev[f:f + 1], V[self._i1], a.view("f1/bias:0"), V[self._i2], a.view("f2/bias:0"), V[self._i3f], a.view("f3/bias:0"),
-                              self.r, shuffle, out_dev[f:f + 1], (y0, y1), uint8)
-            ev_c = torch.cuda.Event()
-            ev_c.record(s_c)
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(ev_c)
-                out_t[f, y0 * r:y1 * r].copy_(out_dev[f, y0 * r:y1 * r], non_blocking=True)
-        s_out.synchronize()
+        a, V = self.arena, self.plan.views
+        ops.espcn_forward_host(lr_t, out_t, V[self._i1], a.view("f1/bias:0"), V[self._i2], a.view("f2/bias:0"), V[self._i3f], a.view("f3/bias:0"), self.r,
+                               shuffle, uint8, st["lr_dev"], st["lr_u8_dev"] if raw else None, st["out_dev"], band_rows)
         if user_out is not None:
             user_out.copy_(out_t)
             out_t = user_out
@@ -300,6 +286,7 @@ class EspcnNet:
 class _EspcnGraph:
     def __init__(self, net, lr_ph, hr_ph=None):
         self.net, self.lr_ph, self.hr_ph = net, lr_ph, hr_ph
+        self.lr_u8_ph = Placeholder("lr_source_u8", getattr(lr_ph, "shape", None))  # raw uint8 frames (normalised on the device)
 
     @staticmethod
     def _to_device(x, device):
@@ -311,11 +298,14 @@ class _EspcnGraph:
         net = self.net
         out = {}
         outs = outs or {}
-        x = feeds[self.lr_ph]
+        raw = self.lr_u8_ph in feeds
+        x = feeds[self.lr_u8_ph] if raw else feeds[self.lr_ph]
+        if raw:
+            assert not (keys & {"optimizer", "loss"}) and not (isinstance(x, torch.Tensor) and x.is_cuda), "lr_source_u8 feeds host frames to the inference fetches"
         if not (keys & {"optimizer", "loss"}) and not (isinstance(x, torch.Tensor) and x.is_cuda):
             # inference on host arrays: band-pipelined copies around the fused kernel (EspcnNet.forward_host)
             from ..session import as_host_tensor
-            lr_h = as_host_tensor(x, np.float32)
+            lr_h = as_host_tensor(x, np.uint8 if raw else np.float32)
             for key, shuffle, u8 in (("sr_result", False, False), ("sr_results", False, False), ("hr_images", True, False), ("hr_images_u8", True, True)):
                 if key in keys and key not in out:
                     dst = outs.get(key)
@@ -358,7 +348,8 @@ def build_model(lr_source, scaling_factor=3, hr_target=None, params=None, channe
     """espcn/espcn/model_espcn.py:6 `build_model(lr_source, scaling_factor=3, hr_target=None)`."""
     net = EspcnNet(params, scaling_factor, channels, device, seed)
     g = _EspcnGraph(net, lr_source, hr_target)
-    model = {"lr_source": lr_source, "sr_result": Handle(g, "sr_result"), "hr_images": Handle(g, "hr_images"), "hr_images_u8": Handle(g, "hr_images_u8")}
+    model = {"lr_source": lr_source, "lr_source_u8": g.lr_u8_ph, "sr_result": Handle(g, "sr_result"), "hr_images": Handle(g, "hr_images"),
+             "hr_images_u8": Handle(g, "hr_images_u8")}
     if hr_target is None:
         return model
     model["hr_target"] = hr_target

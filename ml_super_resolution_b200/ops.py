@@ -298,6 +298,14 @@ def conv_tc_last(x: Fpa, w_packed: torch.Tensor, bias: torch.Tensor | None, k: i
     return out
 
 
+def u8_to_pm1_f64(x_u8: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """uint8 -> float32 `x / 127.5 - 1.0` with numpy's float64 arithmetic (srk_u8_to_pm1_f64): the reference drivers' input
+    normalisation, on the device."""
+    assert x_u8.dtype == torch.uint8 and out.dtype == torch.float32 and x_u8.numel() == out.numel() and x_u8.is_contiguous() and out.is_contiguous()
+    check(_ffi.lib().srk_u8_to_pm1_f64(handle(), _ptr(x_u8), x_u8.numel(), _ptr(out), _stream()), "srk_u8_to_pm1_f64")
+    return out
+
+
 OUT_F32, OUT_U8 = 0, 1
 
 
@@ -320,6 +328,21 @@ def espcn_forward(lr: torch.Tensor, w1p: torch.Tensor, b1: torch.Tensor, w2p: to
     check(_ffi.lib().srk_espcn_forward(handle(), C.byref(net), _ptr(_f32(lr)), n, H, W, y0, y1, int(shuffle), OUT_U8 if uint8 else OUT_F32,
                                        _ptr(out), _stream()), "srk_espcn_forward")
     return out
+
+
+def espcn_forward_host(lr_host: torch.Tensor, out_host: torch.Tensor, w1p, b1, w2p, b2, w3p, b3, scaling_factor: int, shuffle: bool, uint8: bool,
+                       lr_dev: torch.Tensor, lr_u8_dev: torch.Tensor | None, out_dev: torch.Tensor, band_rows: int = 540) -> torch.Tensor:
+    """Host tensors in / out around the fused ESPCN kernel with the copies pipelined by row bands on three streams
+    (srk_espcn_forward_host: the band loop runs in C).  `lr_host`: fp32 frames or the raw uint8 image (normalised on the device)."""
+    n, H, W, C_ = lr_host.shape
+    raw = lr_host.dtype == torch.uint8
+    assert lr_host.is_contiguous() and out_host.is_contiguous() and not lr_host.is_cuda and not out_host.is_cuda
+    assert out_host.dtype == (torch.uint8 if uint8 else torch.float32) and out_host.shape == out_dev.shape and out_dev.dtype == out_host.dtype
+    net = _ffi.SrkEspcnNet(w1p.data_ptr(), w2p.data_ptr(), w3p.data_ptr(), _f32(b1).data_ptr(), _f32(b2).data_ptr(), _f32(b3).data_ptr(), C_, scaling_factor)
+    check(_ffi.lib().srk_espcn_forward_host(handle(), C.byref(net), lr_host.data_ptr(), int(raw), n, H, W, int(shuffle), OUT_U8 if uint8 else OUT_F32,
+                                            out_host.data_ptr(), _ptr(lr_dev), _ptr(lr_u8_dev) if raw else None, _ptr(out_dev), band_rows, _stream()),
+          "srk_espcn_forward_host")
+    return out_host
 
 
 _wgrad_ws: dict = {}

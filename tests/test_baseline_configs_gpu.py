@@ -332,3 +332,25 @@ def test_fused_exchange_adam_kernel_single_rank(srk_ops):
         assert torch.equal(wa, wb) and torch.equal(ma, mb) and torch.equal(va, vb)
     finally:
         check(_ffi.lib().srk_peer_close(h), "srk_peer_close")
+
+
+def test_espcn_raw_uint8_feed_equals_host_normalisation(srk_ops):
+    """Feeding the decoded uint8 image to `lr_source_u8` == feeding `image / 127.5 - 1.0` (numpy float64, cast to float32 by the
+    feed) to `lr_source`, bit for bit (espcn/espcn/experiment_test.py:154-169): the normalisation runs on the device in double."""
+    from ml_super_resolution_b200.espcn.model_espcn import build_model
+    from ml_super_resolution_b200.session import Session, placeholder
+    params = _trained_like(OM.espcn_init(seed=3, scaling_factor=3, channels=3), scale=5.0)
+    ph = placeholder([None, None, None, 3], "lr_source")
+    model = build_model(ph, 3, params=params, channels=3)
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (2, 700, 90, 3), dtype=np.uint8)
+    img[0, 0, 0] = (0, 127, 255)
+    host = (img / 127.5 - 1.0).astype(np.float32)
+    with Session() as s:
+        a = s.run({"h": model["hr_images"], "u": model["hr_images_u8"]}, feed_dict={ph: host})
+        b = s.run({"h": model["hr_images"], "u": model["hr_images_u8"]}, feed_dict={model["lr_source_u8"]: img})
+    assert np.array_equal(a["h"], b["h"]) and np.array_equal(a["u"], b["u"])
+    # all 256 values: the device arithmetic is numpy's
+    x = torch.arange(256, dtype=torch.uint8, device="cuda")
+    y = srk_ops.u8_to_pm1_f64(x, torch.empty(256, device="cuda"))
+    assert np.array_equal(y.cpu().numpy(), (np.arange(256) / 127.5 - 1.0).astype(np.float32))
