@@ -155,6 +155,10 @@ int srk_create(int device, srk_handle_t* out) {
 }
 
 int srk_destroy(srk_handle_t h) {
+  if (!h) return 0;
+  srk_peer_close(h);              // unmaps the peers' exchange regions, frees the local one (peer_reduce.cu)
+  srk_comm_destroy(h);            // ncclCommDestroy (collective.cu)
+  srk::host_pipe_destroy(h);      // copy streams + events of srk_espcn_forward_host (espcn_fused.cu)
   delete h;
   return 0;
 }

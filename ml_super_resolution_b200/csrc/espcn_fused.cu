@@ -64,6 +64,17 @@ struct HostPipe {
     return e;
   }
 };
+void host_pipe_destroy(srk_ctx* h) {
+  HostPipe* hp = static_cast<HostPipe*>(h->host_pipe);
+  if (!hp) return;
+  cudaStreamSynchronize(hp->s_in);
+  cudaStreamSynchronize(hp->s_out);
+  for (int i = 0; i < HostPipe::kEvents; ++i) cudaEventDestroy(hp->ev[i]);
+  cudaStreamDestroy(hp->s_in);
+  cudaStreamDestroy(hp->s_out);
+  delete hp;
+  h->host_pipe = nullptr;
+}
 }  // namespace srk
 
 extern "C" int srk_espcn_forward_host(srk_handle_t h, const srk_espcn_net* net, const void* lr_host, int lr_is_u8, int n, int H, int W, int shuffle,

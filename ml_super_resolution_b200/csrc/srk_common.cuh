@@ -144,6 +144,9 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// releases what srk_espcn_forward_host created on the handle (espcn_fused.cu)
+void host_pipe_destroy(srk_ctx* h);
+
 // Column-strip form of the 3x3 64->64 FPA convolution (conv_strip.cu): srk_conv_tc routes wide frames there.
 bool conv_strip_applicable(srk_ctx* h, int n_img, int H, int W);
 int launch_conv_strip(srk_ctx* h, const void* x_fpa, const void* w_packed, const float* bias, int act, int n_img, int H, int W, void* y_fpa,
