@@ -393,13 +393,9 @@ def vdsr_infer_workload(args, rank, world):
     sd = torch.rand((1, H, W, 3), device="cuda", generator=g) * 2 - 1
     out = torch.empty_like(sd)
 
-    # tile grid: 252-px column panels,
-    from ml_super_resolution_b200.tiling import plan_tiles
-    # and with several GPUs also into `world` row bands (20-px halo): a rank's shard is one whole band, so its column panels
-    # can swap seam columns instead of recomputing halos and its host copies are contiguous full-width row ranges
+    # with several GPUs the frame is cut into a rank grid (2 x 4 regions at 8 GPUs), every region extended by the 20-px
+    # receptive-field halo on its interior sides (tiling.rank_region); inside a rank, 242-px column panels swap seam columns
     tile_rows = None
-    if world > 1:
-        tile_rows = -(-(H - 2 * VDSR_LAYERS) // world) + 2 * VDSR_LAYERS
     def step():
         net.forward(sd, out=out, rank=rank, world=world, tile_rows=tile_rows)
 
@@ -410,22 +406,14 @@ def vdsr_infer_workload(args, rank, world):
     n_launch = launches_of(step) * args.steps
     sd_h = sd.cpu().pin_memory()
     out_h = torch.empty(sd.shape).pin_memory()
-    # every rank moves only what its tile shard needs: the bounding box of the pixels its tiles read (host -> device) and of
-    # the pixels they own (device -> host); one rank = the whole frame
-    from ml_super_resolution_b200.tiling import MAX_PANEL_W, shard_tiles
-    Ht, Wt, tiles = plan_tiles(1, H, W, VDSR_LAYERS, MAX_PANEL_W, tile_rows, halo_x=1)
-
-    def boxes(r):
-        mine = shard_tiles(tiles, r, world)
-        rd = (min(t.y0 for t in mine), max(t.y0 for t in mine) + Ht, min(t.x0 for t in mine), max(t.x0 for t in mine) + Wt)
-        ow = (min(t.y0 + t.own_y0 for t in mine), max(t.y0 + t.own_y1 for t in mine), min(t.x0 + t.own_x0 for t in mine),
-              max(t.x0 + t.own_x1 for t in mine))
-        return rd, ow
-
-    # full-width row ranges: contiguous in NHWC, so the pinned copies stay single asynchronous DMA transfers
-    (ry0, ry1, _, _), (oy0, oy1, _, _) = boxes(rank)
-    h2d = sum(b[0][1] - b[0][0] for b in map(boxes, range(world))) * W * 3 * 4
-    d2h = sum(b[1][1] - b[1][0] for b in map(boxes, range(world))) * W * 3 * 4
+    # every rank moves only its region: the pixels it reads (host -> device) and the pixels it owns (device -> host), each as one
+    # strided DMA transfer (ops.copy_region); one rank = the whole frame
+    from ml_super_resolution_b200 import ops
+    from ml_super_resolution_b200.tiling import rank_region
+    own_box, read_box = rank_region(world, rank, H, W, VDSR_LAYERS)
+    area = lambda bx: (bx[1] - bx[0]) * (bx[3] - bx[2])  # noqa: E731
+    h2d = sum(area(rank_region(world, r, H, W, VDSR_LAYERS)[1]) for r in range(world)) * 3 * 4
+    d2h = sum(area(rank_region(world, r, H, W, VDSR_LAYERS)[0]) for r in range(world)) * 3 * 4
     # throughput metric: frames are double-buffered, H2D / compute / D2H run on three streams so the PCIe transfers of
     # neighbouring frames overlap the 20 layers (every byte still moves every step)
     sd_dev = [torch.empty_like(sd) for _ in range(2)]
@@ -441,7 +429,7 @@ def vdsr_infer_workload(args, rank, world):
         counter[0] += 1
         with torch.cuda.stream(s_in):
             s_in.wait_event(ev_c[b])  # the forward that last read sd_dev[b] is done
-            sd_dev[b][:, ry0:ry1].copy_(sd_h[:, ry0:ry1], non_blocking=True)
+            ops.copy_region(sd_dev[b], sd_h, read_box)
             ev_in[b].record(s_in)
         s_c.wait_event(ev_in[b])
         s_c.wait_event(ev_out[b])     # the D2H that last read out_dev[b] is done
@@ -449,7 +437,7 @@ def vdsr_infer_workload(args, rank, world):
         ev_c[b].record(s_c)
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_c[b])
-            out_h[:, oy0:oy1].copy_(out_dev[b][:, oy0:oy1], non_blocking=True)
+            ops.copy_region(out_h, out_dev[b], own_box)
             ev_out[b].record(s_out)
 
     def e2e_finalize():
@@ -459,7 +447,7 @@ def vdsr_infer_workload(args, rank, world):
     ms_e, _ = timed_steps(e2e_step, max(2, args.steps // 2), 2, world, None, finalize=e2e_finalize)
     e2e = {"value": round(H * W * max(2, args.steps // 2) / ms_e / 1e3, 1), "unit": "output Mpix/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h}
-    cfg = {"workload": "VDSR-20 3x tiled inference, one synthetic 3840x2160x3 frame/step, 242-px column panels exchanging seam columns per layer; one 20-px-halo row band per GPU",
+    cfg = {"workload": "VDSR-20 3x tiled inference, one synthetic 3840x2160x3 frame/step, 242-px column panels exchanging seam columns per layer; with several GPUs one region of a rank grid per GPU (2 x 4 at 8), 20-px halo on its interior sides",
            "parallelism": f"tiles x{world}", "l2_policy": "activations 2 x 1.26 GB ping-pong >> 126 MB L2"}
     return dict(metric="VDSR 3x output Mpix/s (fwd)", value=round(value, 1), unit="output Mpix/s", ms=ms, clocks=clocks, roofline=roofline, e2e=e2e,
                 gpu_launches=n_launch, config=cfg, scaling="strong")

@@ -65,6 +65,11 @@ int srk_num_sms(srk_handle_t h);
 enum { SRK_CONV_FORM_AUTO = 0, SRK_CONV_FORM_FLAT = 1, SRK_CONV_FORM_STRIP = 2 };
 int srk_set_conv_form(srk_handle_t h, int form);
 
+/* Strided host <-> device copy of a rectangle (rows x width_bytes) on a stream: a rank of tile-sharded inference moves only its
+ * region of the frame, as one DMA transfer (cudaMemcpy2DAsync; page-locked host memory keeps it asynchronous). */
+int srk_memcpy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows, int to_device,
+                       srk_stream_t stream);
+
 /* rows (multiple of 128) an FPA buffer for n_img images of H x W must hold */
 int64_t srk_fpa_rows(int n_img, int H, int W);
 

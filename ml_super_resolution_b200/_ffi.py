@@ -44,6 +44,7 @@ SIGNATURES = {
     "srk_destroy": (_I, [_P]),
     "srk_num_sms": (_I, [_P]),
     "srk_set_conv_form": (_I, [_P, _I]),
+    "srk_memcpy2d_async": (_I, [_P, _SZ, _P, _SZ, _SZ, _SZ, _I, _P]),
     "srk_espcn_forward_host": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
     "srk_peer_alloc": (_I, [_P, _SZ, _P]),
     "srk_peer_open": (_I, [_P, _I, _I, _P]),
@@ -135,7 +136,7 @@ def lib() -> C.CDLL:
 # kernels launched per C-ABI call (everything else: 0) -- feeds bench.py's `gpu_launches`
 KERNELS_PER_CALL = {name: 1 for name in SIGNATURES if name not in
                     ("srk_version", "srk_last_error", "srk_create", "srk_destroy", "srk_num_sms", "srk_set_conv_form", "srk_fpa_rows",
-                     "srk_conv_wgrad_tc_workspace_bytes", "srk_conv_out_size", "srk_comm_unique_id", "srk_comm_init", "srk_allreduce_grads", "srk_comm_destroy", "srk_peer_alloc", "srk_peer_open", "srk_peer_close")}
+                     "srk_conv_wgrad_tc_workspace_bytes", "srk_conv_out_size", "srk_comm_unique_id", "srk_comm_init", "srk_allreduce_grads", "srk_comm_destroy", "srk_peer_alloc", "srk_peer_open", "srk_peer_close", "srk_memcpy2d_async")}
 KERNELS_PER_CALL["srk_conv_wgrad_tc"] = 1  # +1 when it also runs the reduce (counted as srk_wgrad_reduce_many otherwise)
 launch_count = 0
 

@@ -171,6 +171,15 @@ int srk_set_conv_form(srk_handle_t h, int form) {
   return 0;
 }
 
+int srk_memcpy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows, int to_device,
+                       srk_stream_t stream) {
+  SRK_REQUIRE(dst && src && width_bytes <= dst_pitch && width_bytes <= src_pitch, "srk_memcpy2d_async: bad argument");
+  if (rows == 0 || width_bytes == 0) return 0;
+  SRK_CHECK_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
+                                   srk::as_stream(stream)));
+  return 0;
+}
+
 int64_t srk_fpa_rows(int n_img, int H, int W) { return srk::fpa_geom(n_img, H, W).rows_alloc; }
 
 }  // extern "C"

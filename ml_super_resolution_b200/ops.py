@@ -306,6 +306,20 @@ def u8_to_pm1_f64(x_u8: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def copy_region(dst: torch.Tensor, src: torch.Tensor, box: tuple[int, int, int, int]) -> None:
+    """dst[:, y0:y1, x0:x1] = src[:, y0:y1, x0:x1] between a page-locked host tensor and a device tensor of one NHWC shape (either
+    direction), one strided DMA transfer per frame on the current stream (srk_memcpy2d_async)."""
+    y0, y1, x0, x1 = box
+    n, H, W, C_ = src.shape
+    assert dst.shape == src.shape and dst.dtype == src.dtype and dst.is_contiguous() and src.is_contiguous() and dst.is_cuda != src.is_cuda
+    e = src.element_size()
+    pitch, off = W * C_ * e, (y0 * W + x0) * C_ * e
+    for f in range(n):
+        base = f * H * pitch + off
+        check(_ffi.lib().srk_memcpy2d_async(dst.data_ptr() + base, pitch, src.data_ptr() + base, pitch, (x1 - x0) * C_ * e, y1 - y0, int(dst.is_cuda),
+                                            _stream()), "srk_memcpy2d_async")
+
+
 OUT_F32, OUT_U8 = 0, 1
 
 

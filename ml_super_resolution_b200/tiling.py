@@ -101,3 +101,27 @@ def plan_seam_exchange(n_frames: int, FH: int, FW: int, halo: int, max_w: int | 
         mine = shard_tiles(tiles, rank, world)
     max_cols = 2 * max((max(t.own_x0, Wt - t.own_x1) for t in mine), default=0) if exchange else 0
     return Ht, Wt, mine, exchange, max_cols
+
+
+def rank_grid(world: int, H: int, W: int, halo: int) -> tuple[int, int]:
+    """(gy, gx), gy * gx == world: the grid of frame regions that recomputes the fewest halo pixels -- every region is extended by
+    `halo` on its interior sides, so a 2 x 4 grid of a 3840 x 2160 frame costs 5 % where 8 x 1 row bands cost 15 %."""
+    best = None
+    for gy in range(1, world + 1):
+        if world % gy:
+            continue
+        gx = world // gy
+        th, tw = -(-H // gy), -(-W // gx)
+        cost = (th + (2 * halo if gy > 2 else (halo if gy == 2 else 0))) * (tw + (2 * halo if gx > 2 else (halo if gx == 2 else 0)))
+        if best is None or cost < best[0]:
+            best = (cost, gy, gx)
+    return best[1], best[2]
+
+
+def rank_region(world: int, rank: int, H: int, W: int, halo: int):
+    """The frame region rank `rank` of `world` owns in tile-sharded inference, (y0, y1, x0, x1), and the region it reads (the owned
+    one extended by `halo` on its interior sides, clipped at the frame), (ya, yb, xa, xb)."""
+    gy, gx = rank_grid(world, H, W, halo)
+    ry, rx = divmod(rank, gx)
+    y0, y1, x0, x1 = H * ry // gy, H * (ry + 1) // gy, W * rx // gx, W * (rx + 1) // gx
+    return (y0, y1, x0, x1), (max(0, y0 - halo), min(H, y1 + halo), max(0, x0 - halo), min(W, x1 + halo))

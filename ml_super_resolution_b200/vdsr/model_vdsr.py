@@ -25,7 +25,7 @@ from .. import ops
 from ..initializers import tf_conv_name, vdsr_params
 from ..params import ParamArena
 from ..session import Handle, Placeholder
-from ..tiling import MAX_PANEL_W, plan_seam_exchange, plan_tiles
+from ..tiling import MAX_PANEL_W, plan_seam_exchange, plan_tiles, rank_region
 
 WEIGHT_DECAY = 1e-4  # tf.contrib.layers.l2_regularizer(0.0001), reference :34
 
@@ -89,7 +89,7 @@ class VdsrNet:
 
     # ------------------------------------------------------------------ inference
     def forward(self, sd: torch.Tensor, taps: dict | None = None, out: torch.Tensor | None = None, tile_rows: int | None = None,
-                rank: int = 0, world: int = 1, max_panel_w: int = MAX_PANEL_W) -> torch.Tensor:
+                rank: int = 0, world: int = 1, max_panel_w: int = MAX_PANEL_W, _form_width: int | None = None) -> torch.Tensor:
         """sd fp32 [N,H,W,C] on device -> sr.  Frames wider than 254 px (or taller than `tile_rows`) are
         cut into halo-overlapped tiles; with world > 1 this rank computes only its shard of the tiles
         (tile-sharded multi-GPU inference, no collective; pixels it does not own are left untouched)."""
@@ -97,8 +97,23 @@ class VdsrNet:
         assert C == self.C
         a = self.arena
         assert max_panel_w <= MAX_PANEL_W
-        need_tiles = W > max_panel_w or (tile_rows is not None and H > tile_rows) or world > 1
-        if need_tiles and ops.conv_form(W).form == "strip":
+        form_width = W if _form_width is None else _form_width
+        if world > 1:
+            # Tile sharding over ranks: a gy x gx grid of frame regions, one per rank, each extended by the receptive-field halo
+            # (num_layers pixels) on its interior sides and run through the single-rank path below; the rank writes only the
+            # pixels it owns.  A 2 x 4 grid of a 4K frame recomputes 5 % of the pixels where 8 row bands recompute 15 %.  Every
+            # owned pixel sees its whole receptive field (or the frame border's zero padding) and the FRAME's kernel form, so the
+            # union of the ranks' pixels equals the un-sharded frame bit for bit.
+            (y0, y1, x0, x1), (ya, yb, xa, xb) = rank_region(world, rank, H, W, self.L)
+            if y1 <= y0 or x1 <= x0:
+                return out if out is not None else torch.empty_like(sd)
+            sub = self.forward(sd[:, ya:yb, xa:xb].contiguous(), tile_rows=tile_rows, max_panel_w=max_panel_w, _form_width=form_width)
+            if out is None:
+                out = torch.empty_like(sd)
+            out[:, y0:y1, x0:x1].copy_(sub[:, y0 - ya:y1 - ya, x0 - xa:x1 - xa])
+            return out
+        need_tiles = W > max_panel_w or (tile_rows is not None and H > tile_rows)
+        if need_tiles and ops.conv_form(form_width).form == "strip":
             max_panel_w = min(max_panel_w, 2 * ops.STRIP_W - 1)  # a panel plus its zero column fills at most two 126-pixel strips
         if out is None:
             out = torch.empty_like(sd)
@@ -108,7 +123,7 @@ class VdsrNet:
             if taps is not None:
                 taps["conv.1"] = taps["relu.1"] = ops.fpa_to_nhwc(t)
             for i in range(1, self.L - 1):
-                with ops.conv_form(W):
+                with ops.conv_form(form_width):
                     t = ops.conv_tc(t, self.wf(i), a.view(self._bname(i)), 3, "relu", out=bufs[i % 2])
                 if taps is not None:
                     taps[f"conv.{i + 1}"] = taps[f"relu.{i + 1}"] = ops.fpa_to_nhwc(t)
@@ -136,7 +151,7 @@ class VdsrNet:
             if exchange:  # the gather pads a panel's window edge with zeros: its seam columns come from the neighbour too
                 ops.fpa_halo_exchange(t, panels, max_cols)
             for i in range(1, self.L - 1):
-                with ops.conv_form(W):  # the FRAME's width decides the kernel form: panels compute what the un-tiled frame would
+                with ops.conv_form(form_width):  # the FRAME's width decides the kernel form: panels compute what the un-tiled frame would
                     t = ops.conv_tc(t, self.wf(i), a.view(self._bname(i)), 3, "relu", out=bufs[i % 2])
                 if exchange:
                     ops.fpa_halo_exchange(t, panels, max_cols)

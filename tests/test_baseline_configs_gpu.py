@@ -354,3 +354,18 @@ def test_espcn_raw_uint8_feed_equals_host_normalisation(srk_ops):
     x = torch.arange(256, dtype=torch.uint8, device="cuda")
     y = srk_ops.u8_to_pm1_f64(x, torch.empty(256, device="cuda"))
     assert np.array_equal(y.cpu().numpy(), (np.arange(256) / 127.5 - 1.0).astype(np.float32))
+
+
+@pytest.mark.parametrize("world", [3, 8])
+def test_vdsr_rank_grid_sharding_is_bit_identical(srk_ops, world):
+    """Tile sharding over a rank grid (2 x 4 regions at 8 ranks, each with its receptive-field halo): the ranks write disjoint
+    regions whose union equals the un-sharded frame bit for bit (emulated on one GPU: every rank's call in turn)."""
+    from ml_super_resolution_b200.vdsr.model_vdsr import VdsrNet
+    params = _trained_like(OM.vdsr_init(seed=42, num_layers=6))
+    net = VdsrNet(params, num_layers=6)
+    x = torch.from_numpy(OM.synthetic_images(9, 1, 120, 330, 3)).cuda()
+    full = net.forward(x)
+    out = torch.full_like(x, float("nan"))
+    for rk in range(world):
+        net.forward(x, out=out, rank=rk, world=world)
+    assert torch.equal(out, full)
