@@ -103,16 +103,25 @@ def plan_seam_exchange(n_frames: int, FH: int, FW: int, halo: int, max_w: int | 
     return Ht, Wt, mine, exchange, max_cols
 
 
-def rank_grid(world: int, H: int, W: int, halo: int) -> tuple[int, int]:
-    """(gy, gx), gy * gx == world: the grid of frame regions that recomputes the fewest halo pixels -- every region is extended by
-    `halo` on its interior sides, so a 2 x 4 grid of a 3840 x 2160 frame costs 5 % where 8 x 1 row bands cost 15 %."""
+def rank_grid(world: int, H: int, W: int, halo: int, strip_w: int = 126, max_panel_w: int = 251) -> tuple[int, int]:
+    """(gy, gx), gy * gx == world: the grid of frame regions that costs a rank the least work.  Every region is extended by `halo`
+    on its interior sides (a 2-D grid recomputes fewer halo pixels than row bands), and inside a rank the region is cut
+    into equal column panels of at most `max_panel_w` pixels whose rows occupy whole 126-pixel strips of the column-strip kernel:
+    the cost of a grid is rows x strips of its largest region, so 4 x 2 beats 2 x 4 for a 4K frame on 8 GPUs (eight 245-px panels
+    fill 16 strips, five 202-px panels of a 1000-px region waste a fifth of theirs)."""
     best = None
     for gy in range(1, world + 1):
         if world % gy:
             continue
         gx = world // gy
-        th, tw = -(-H // gy), -(-W // gx)
-        cost = (th + (2 * halo if gy > 2 else (halo if gy == 2 else 0))) * (tw + (2 * halo if gx > 2 else (halo if gx == 2 else 0)))
+        rows = -(-H // gy) + (2 * halo if gy > 2 else (halo if gy == 2 else 0))
+        width = -(-W // gx) + (2 * halo if gx > 2 else (halo if gx == 2 else 0))
+        k = 1
+        while -(-width // k) + 2 > max_panel_w:
+            k += 1
+        panel = -(-width // k) + (2 if k > 1 else 0)
+        strips = k * (-(-(panel + 1) // strip_w))
+        cost = rows * strips
         if best is None or cost < best[0]:
             best = (cost, gy, gx)
     return best[1], best[2]

@@ -223,13 +223,12 @@ def test_strip_form_rule_matches_the_kernel_geometry():
 
 
 def test_rank_grid_minimises_halo_pixels():
-    """tiling.rank_grid: the rank grid of tile-sharded inference -- 2 x 4 for a 4K frame on 8 GPUs, bands for frames that
-    are much taller than wide, one region for one rank; gy * gx is always the world size."""
+    """tiling.rank_grid: the rank grid of tile-sharded inference -- the grid whose largest region costs the fewest
+    strip rows; bands for frames that are much taller than wide, one region for one rank; gy * gx is always the world size."""
     from ml_super_resolution_b200.tiling import rank_grid
-    assert rank_grid(8, 2160, 3840, 20) == (2, 4)
-    assert rank_grid(4, 2160, 3840, 20) == (2, 2)
-    assert rank_grid(2, 2160, 3840, 20) == (1, 2)
+    assert rank_grid(8, 2160, 3840, 20) == (4, 2)   # eight 245-px panels per region fill their 16 strips; 2 x 4 would waste a fifth
     assert rank_grid(1, 2160, 3840, 20) == (1, 1)
+    assert rank_grid(2, 2160, 3840, 20) in ((1, 2), (2, 1))
     assert rank_grid(8, 8000, 100, 20)[0] == 8
     for world in (1, 2, 3, 4, 6, 8):
         gy, gx = rank_grid(world, 270, 3840, 20)
