@@ -233,3 +233,17 @@ def test_rank_grid_minimises_halo_pixels():
     for world in (1, 2, 3, 4, 6, 8):
         gy, gx = rank_grid(world, 270, 3840, 20)
         assert gy * gx == world
+
+
+@pytest.mark.parametrize("world,H,W", [(1, 2160, 3840), (2, 2160, 3840), (4, 2160, 3840), (8, 2160, 3840), (3, 120, 330), (8, 120, 330), (6, 41, 41)])
+def test_rank_regions_partition_the_frame(world, H, W):
+    """tiling.rank_region: the owned regions of the ranks tile the frame exactly once; every rank reads its region plus the
+    receptive-field halo, clipped at the frame (what bench.py copies host -> device and VdsrNet.forward computes on)."""
+    from ml_super_resolution_b200.tiling import rank_region
+    halo = 20
+    cover = np.zeros((H, W), np.int32)
+    for r in range(world):
+        (y0, y1, x0, x1), (ya, yb, xa, xb) = rank_region(world, r, H, W, halo)
+        cover[y0:y1, x0:x1] += 1
+        assert ya == max(0, y0 - halo) and yb == min(H, y1 + halo) and xa == max(0, x0 - halo) and xb == min(W, x1 + halo)
+    assert cover.min() == 1 and cover.max() == 1
